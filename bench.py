@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the batched truss env-step (BASELINE.json metric: FEM env-steps/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on all host cores
+
+One "step" = one pass of the hot path over one batch: every environment of the batch executes one
+``_game_modify``-equivalent (action decode + constraint/symmetry passes + FEM assemble/solve/post +
+observation tensors + objective point).  Per-GPU batch is fixed (weak scaling); ranks share nothing.
+
+Timed region (GPU arm): inputs already resident in HBM, one CUDA-event pair per step on the launching
+stream, L2 flushed (256 MiB write) between steps because the 52 MB working set would otherwise stay in
+the 126 MB L2; value = (envs per step x N GPUs) / mean step time, max over ranks.
+e2e: the same step through ``tfem_step_host`` -- pinned HOST state tables + actions in, every float32
+tensor the reference returns out (host<->device copies inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FEM env-steps/sec (batched truss solve)"
+UNIT = "env-steps/s"
+
+
+def algorithmic_bytes(N, E, ndof):
+    """everything _game_modify consumes and produces at the reference's dtypes,
+    topology constants excluded."""
+    inb = 4 * (12 * N + 21 * E + 5 * N)
+    outb = 4 * (13 * N + 3 * N * N + 12 * N + 21 * E + 4) + 8 * (ndof + 2 * E + 1)
+    return inb + outb
+
+
+# --------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """polls SM clock / throttle reasons during the timed region (NVML; same fields as the nvidia-smi
+    recipe in B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------------
+def oracle_steps_per_sec(family, seconds, seed=0):
+    """the CPU port driven like the GPU batch (i.i.d. uniform actions, own state fed back); returns
+    (steps, elapsed)"""
+    from oracle.truss_oracle import TrussOracle
+    o = TrussOracle(family)
+    rng = np.random.RandomState(seed)
+    N = o.mesh.N
+    st = o.reset()
+    for _ in range(3):
+        st = o.step(st["nN_x_n"], st["nN_x_e"], st["max_up"], st["max_down"], rng.rand(N, 2).astype(np.float32),
+                    rng.rand(N, 3).astype(np.float32), rng.rand() >= 0.5)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        st = o.step(st["nN_x_n"], st["nN_x_e"], st["max_up"], st["max_down"], rng.rand(N, 2).astype(np.float32),
+                    rng.rand(N, 3).astype(np.float32), rng.rand() >= 0.5)
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+def _oracle_worker(args):
+    family, seconds, seed = args
+    import warnings
+    warnings.filterwarnings("ignore")
+    return oracle_steps_per_sec(family, seconds, seed)
+
+
+def run_reference_arm(args, rank, world):
+    """the reference's CPU implementation of the path = the oracle port (the Python reference itself
+    cannot travel to the GPU box), one env per process on every host core"""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step_seconds = max(2.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    ctx = mp.get_context("fork")
+    rates = []
+    with ctx.Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            res = pool.map(_oracle_worker, [(args.family, per_step_seconds, 1000 * it + c) for c in range(cores)])
+            total = sum(n for n, _ in res)
+            elapsed = max(t for _, t in res)
+            if it >= args.warmup:
+                rates.append(total / elapsed)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_seconds * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "family": args.family, "envs_per_gpu": args.batch},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d processes x %.1f s of oracle env-steps per bench step (one env each, uniform "
+                                   "actions, own state fed back)" % (cores, per_step_seconds)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return "%s B=%d per GPU: batched FEM env-step (_game_modify equivalent)" % (args.family, args.batch)
+
+
+# --------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--family", default="small_bridge")
+    ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    from mop_truss_marl_b200 import batched_env, capi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+    env = batched_env.BatchedTrussEnv(args.family, B, device=dev)
+    N, E = env.N, env.E
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    env.reset()
+    nact = 16                                   # pre-generated, resident action batches, cycled
+
+    def make_actions():
+        return (torch.rand(B, N, 2, device=dev, generator=gen), torch.rand(B, N, 3, device=dev, generator=gen),
+                (torch.rand(B, device=dev, generator=gen) >= 0.5).to(torch.uint8))
+    acts = [make_actions() for _ in range(nact)]
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one_step(i):
+        a_geo, a_topo, coin = acts[i % nact]
+        env.step(a_geo, a_topo, coin)
+
+    for i in range(8):                          # state after w = 8 warm-up steps of i.i.d. actions
+        one_step(i)
+    for i in range(W):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = env.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    torch.cuda.synchronize()
+    for i in range(K):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        starts[i].record()
+        one_step(i)
+        ends[i].record()
+    torch.cuda.synchronize()
+    launches = env.launch_count() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = B * world / (ms_per_step * 1e-3)
+    status_bad = int((env.status != 0).sum().item())
+
+    # ---- e2e: the host-buffer call (tfem_step_host) -----------------------------------------------------
+    host = {
+        "set_node": env.nN_x_n.cpu().pin_memory(), "set_element": env.nN_x_e.cpu().pin_memory(),
+        "move_range": env.move_range.cpu().pin_memory(),
+        "a_geo": torch.rand(B, N, 2).pin_memory(), "a_topo": torch.rand(B, N, 3).pin_memory(),
+        "coin": (torch.rand(B) >= 0.5).to(torch.uint8).pin_memory(),
+    }
+    out_host = {k: torch.empty(s, dtype=torch.float32).pin_memory() for k, s in (
+        ("x_n", (B, N, 13)), ("A_s", (B, N, N)), ("A_n_ts", (B, N, N)), ("A_n_cs", (B, N, N)),
+        ("nN_x_n", (B, N, 12)), ("nN_x_e", (B, E, 21)), ("point", (B, 4)))}
+    out_host["status"] = torch.zeros(B, dtype=torch.int32).pin_memory()
+    out_np = {k: v.numpy() for k, v in out_host.items()}
+    a_geo0, a_topo0 = host["a_geo"].clone(), host["a_topo"].clone()
+
+    def e2e_step():
+        host["a_geo"].copy_(a_geo0); host["a_topo"].copy_(a_topo0)      # fresh (unclipped) actions each step
+        batched_env.step_host(env.handle, host["set_node"].numpy(), host["set_element"].numpy(),
+                              host["move_range"].numpy(), host["a_geo"].numpy(), host["a_topo"].numpy(),
+                              host["coin"].numpy(), want_fp64=False, out=out_np)
+        # the state the call returned is the next call's input, like the reference driver does
+        host["set_node"].copy_(out_host["nN_x_n"]); host["set_element"].copy_(out_host["nN_x_e"])
+    ke = max(5, min(K, 50))
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / ke
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.result()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values()) + sum(
+        host[k].numel() * host[k].element_size() for k in ("a_geo", "a_topo", "move_range"))
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        abytes = algorithmic_bytes(N, E, env.ndof)
+        kernel_ms = float(np.mean(step_ms))             # the step IS one kernel launch; events bracket it
+        achieved = abytes * B / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("%s_B%d" % (args.family, B))
+        n_cpu, t_cpu = oracle_steps_per_sec(args.family, args.cpu_seconds)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "family": args.family, "envs_per_gpu": B,
+                       "nodes": N, "elements": E, "free_dofs": env.ndof,
+                       "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
+                       "actions": "uniform [0,1) float32, coin Bernoulli(1/2), own state fed back",
+                       "parallelism": "env-parallel, %d independent shard(s), no collective" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "tfem_step_kernel", "algorithmic_bytes_per_env": abytes,
+                         "kernel_ms": kernel_ms},
+            "cpu_baseline": {"value": n_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "%d oracle env-steps of %s in %.1f s, one process" % (n_cpu, args.family, t_cpu)},
+            "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "path": "tfem_step_host: pinned host state tables + actions in, all float32 tensors out"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "status_nonzero_envs": status_bad,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,30 @@
+// Launch interface between the C ABI (tfem_capi.cu) and the device code (tfem_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "tfem_family.h"
+
+namespace tfem {
+
+enum StepMode { MODE_STEP = 0, MODE_RESET = 1, MODE_SOLVE_ONLY = 2 };
+
+struct StepArgs {
+  const FamilyTables* fam;     // device copy
+  const uint16_t* maps;        // device copy of Family::maps
+  int B;
+  int mode;
+  tfem_step_in in;             // device pointers (MODE_STEP)
+  tfem_step_out out;           // device pointers
+  const double* so_y;          // MODE_SOLVE_ONLY: [B,N]
+  const int32_t* so_sec;       // MODE_SOLVE_ONLY: [B,E]
+  float* reset_move_range;     // MODE_RESET: [B,N,2]
+};
+
+struct LaunchInfo {
+  int grid, block, smem_bytes, ctas_per_sm;
+};
+
+// one-time per-handle setup (opt-in shared memory, occupancy query); returns cudaError_t as int
+int step_kernel_configure(int nx, int device, int map_entries, LaunchInfo* info);
+int step_kernel_launch(int nx, const StepArgs& args, const LaunchInfo& info, cudaStream_t stream);
+
+}  // namespace tfem

@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the golden vectors recorded from the
+reference and against the CPU oracle on seeded random inputs.
+
+  bit-exact ... post-transition heights, sections, move range, in-place clipped actions, 0/1 flags
+  1e-9 ....... d, axial force, stress ratio, U, reactions (normwise, FEM-coerced float64 reference)
+  2 ulp ...... float32 observation tensors and the objective point
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import FAMILY_NAMES, F32_FIELDS, FP64_TOL, assert_f32_close, load_golden, nrm
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def envmod():
+    from mop_truss_marl_b200 import batched_env
+    return batched_env
+
+
+def make_env(envmod, name, B):
+    return envmod.BatchedTrussEnv(name, B, device="cuda:0")
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def load_state(env, set_node, set_element, max_up, max_down):
+    env.nN_x_n.copy_(torch.from_numpy(np.ascontiguousarray(set_node)))
+    env.nN_x_e.copy_(torch.from_numpy(np.ascontiguousarray(set_element)))
+    env.move_range.copy_(torch.from_numpy(np.stack([max_up, max_down], axis=-1).astype(np.float32)))
+
+
+def fp64_tol(cond_like=None):
+    return FP64_TOL
+
+
+def compare_env(env, i, want, point=None, tag=""):
+    """want: dict with the oracle/golden fields of ONE environment"""
+    raw_n, raw_e = cpu(env.nN_x_n[i]), cpu(env.nN_x_e[i])
+    # bit-exact
+    assert np.array_equal(raw_n[:, 1], want["y"].astype(np.float32)), tag + " y"
+    assert np.array_equal(raw_e[:, 0].astype(np.int32), want["section"]), tag + " section"
+    mr = cpu(env.move_range[i])
+    assert np.array_equal(mr[:, 0], want["max_up"]) and np.array_equal(mr[:, 1], want["max_down"]), tag + " move range"
+    assert np.array_equal(raw_e[:, 4].astype(np.int32), want["iscompress"]), tag + " iscompress"
+    assert int(env.status[i]) == 0
+    # float64
+    for k in ("d", "axial", "ratio", "reactions"):
+        e = nrm(cpu(getattr(env, k)[i]), want[k])
+        assert e <= FP64_TOL, "%s %s: %.3e" % (tag, k, e)
+    assert abs(float(env.U[i]) - float(want["U"])) <= FP64_TOL * abs(float(want["U"])), tag + " U"
+    # float32 tensors
+    for k in F32_FIELDS:
+        assert_f32_close(tag + " " + k, cpu(getattr(env, k)[i]), want[k])
+    for k, cols in (("nN_x_n", [11]), ("nN_x_e", [0, 3, 4, 6, 13, 20])):
+        assert np.array_equal(cpu(getattr(env, k)[i])[:, cols], want[k][:, cols]), tag + " flags " + k
+    assert np.array_equal(cpu(env.x_n[i])[:, 12] > 0.5, want["x_n"][:, 12] > 0.5)
+    if point is not None:
+        assert_f32_close(tag + " point", cpu(env.point[i]), point)
+
+
+@pytest.mark.parametrize("name", FAMILY_NAMES)
+def test_constants_and_reset_vs_golden(envmod, name):
+    g = load_golden(name)
+    env = make_env(envmod, name, 3)
+    assert np.array_equal(cpu(env.A_n), g["A_n"]) and np.array_equal(cpu(env.mask), g["mask"])
+    assert np.array_equal(cpu(env.nC_e), g["nC_e"])
+    env.reset()
+    torch.cuda.synchronize()
+    want = {k[len("reset_"):]: v for k, v in g.items() if k.startswith("reset_")}
+    for i in range(3):
+        compare_env(env, i, want, tag="reset[%d]" % i)
+
+
+@pytest.mark.parametrize("name", FAMILY_NAMES)
+def test_transitions_vs_golden(envmod, name):
+    g = load_golden(name)
+    T = g["tr_mode"].shape[0]
+    env = make_env(envmod, name, T)
+    load_state(env, g["tr_in_set_node"], g["tr_in_set_element"], g["tr_in_max_up"], g["tr_in_max_down"])
+    a_geo = torch.from_numpy(g["tr_in_a_geo"].copy()).cuda()
+    a_topo = torch.from_numpy(g["tr_in_a_topo"].copy()).cuda()
+    coin = torch.from_numpy(g["tr_in_coin"].copy()).cuda()
+    env.step(a_geo, a_topo, coin)
+    torch.cuda.synchronize()
+    assert np.array_equal(cpu(a_geo), g["tr_out_a_geo"]) and np.array_equal(cpu(a_topo), g["tr_out_a_topo"])
+    for i in range(T):
+        want = {k[len("tr_out_"):]: v[i] for k, v in g.items() if k.startswith("tr_out_")}
+        compare_env(env, i, want, point=g["tr_out_point"][i], tag="%s tr[%d] mode %d" % (name, i, g["tr_mode"][i]))
+
+
+@pytest.mark.parametrize("name", FAMILY_NAMES)
+def test_random_walk_vs_oracle(envmod, name):
+    """every environment feeds its own state back; the oracle follows each one"""
+    from oracle.truss_oracle import TrussOracle
+    o = TrussOracle(name)
+    B = 48 if o.mesh.N == 16 else 16
+    steps = 4
+    env = make_env(envmod, name, B)
+    env.reset()
+    rng = np.random.RandomState(7)
+    N = o.mesh.N
+    for s in range(steps):
+        scale = 1.0 if s % 2 == 0 else 0.3
+        a_geo = (rng.rand(B, N, 2) * scale).astype(np.float32)
+        a_topo = (rng.rand(B, N, 3) * np.array([scale, scale, 1.0])).astype(np.float32)
+        if s == 2:
+            a_geo = (rng.randn(B, N, 2) + 0.5).astype(np.float32)
+        coin = (rng.rand(B) >= 0.5).astype(np.uint8)
+        set_node, set_elem, mr = cpu(env.nN_x_n).copy(), cpu(env.nN_x_e).copy(), cpu(env.move_range).copy()
+        tg, tt, tc = torch.from_numpy(a_geo.copy()).cuda(), torch.from_numpy(a_topo.copy()).cuda(), torch.from_numpy(coin).cuda()
+        env.step(tg, tt, tc)
+        torch.cuda.synchronize()
+        for i in range(B):
+            ag, at = a_geo[i].copy(), a_topo[i].copy()
+            want = o.step(set_node[i], set_elem[i], mr[i, :, 0], mr[i, :, 1], ag, at, bool(coin[i]))
+            assert np.array_equal(cpu(tg[i]), ag) and np.array_equal(cpu(tt[i]), at)
+            compare_env(env, i, want, point=want["point"], tag="%s step %d env %d" % (name, s, i))
+            assert nrm(cpu(env.point64[i]), want["point64"]) <= FP64_TOL
+
+
+@pytest.mark.parametrize("name", ["small_bridge", "large_roof"])
+def test_step_host_equals_step(envmod, name):
+    g = load_golden(name)
+    T = g["tr_mode"].shape[0]
+    env = make_env(envmod, name, T)
+    load_state(env, g["tr_in_set_node"], g["tr_in_set_element"], g["tr_in_max_up"], g["tr_in_max_down"])
+    a_geo = torch.from_numpy(g["tr_in_a_geo"].copy()).cuda(); a_topo = torch.from_numpy(g["tr_in_a_topo"].copy()).cuda()
+    env.step(a_geo, a_topo, torch.from_numpy(g["tr_in_coin"].copy()).cuda())
+    torch.cuda.synchronize()
+    mr = np.stack([g["tr_in_max_up"], g["tr_in_max_down"]], axis=-1).astype(np.float32)
+    hg, ht = g["tr_in_a_geo"].copy(), g["tr_in_a_topo"].copy()
+    out = envmod.step_host(env.handle, g["tr_in_set_node"].copy(), g["tr_in_set_element"].copy(), mr, hg, ht,
+                           g["tr_in_coin"].copy())
+    for k in F32_FIELDS + ("point", "point64", "d", "axial", "ratio", "U", "reactions", "status"):
+        assert np.array_equal(out[k], cpu(getattr(env, k))), k
+    assert np.array_equal(mr, cpu(env.move_range)) and np.array_equal(hg, cpu(a_geo)) and np.array_equal(ht, cpu(a_topo))
+
+
+@pytest.mark.parametrize("name", ["small_roof", "large_bridge"])
+def test_solve_only_vs_oracle(envmod, name):
+    from oracle.truss_oracle import TrussOracle
+    o = TrussOracle(name)
+    m = o.mesh
+    rng = np.random.RandomState(11)
+    B = 64
+    y = np.zeros((B, m.N))
+    y[:, m.N // 2:] = 1.0 + rng.rand(B, m.N // 2) * (m.y_max - 1.0)
+    y[:, 1:m.N // 2 - 1] = rng.rand(B, m.N // 2 - 2) * 0.6
+    sec = rng.randint(0, 5, size=(B, m.E)).astype(np.int32)
+    env = make_env(envmod, name, 1)
+    out = env.solve_only(torch.from_numpy(y).cuda(), torch.from_numpy(sec).cuda())
+    torch.cuda.synchronize()
+    for i in range(B):
+        want = o.solve_only(y[i], sec[i])
+        assert int(out["status"][i]) == 0
+        for k in ("d", "axial", "ratio", "reactions"):
+            assert nrm(cpu(out[k][i]), want[k]) <= FP64_TOL, (k, i)
+        assert abs(float(out["U"][i]) - want["U"]) <= FP64_TOL * abs(want["U"])
+
+
+def test_degenerate_geometry_sets_status(envmod):
+    """zero-length vertical: the reference divides by zero (python float) / raises; we flag the env"""
+    from oracle.truss_oracle import TrussOracle
+    o = TrussOracle("small_bridge")
+    m = o.mesh
+    y = np.array([0.0] * 8 + [4.0] * 8)[None].repeat(2, 0)
+    y[1, 8 + 3] = 0.0                                   # top node 3 on top of bottom node 3
+    sec = np.full((2, m.E), 4, dtype=np.int32)
+    env = make_env(envmod, "small_bridge", 1)
+    out = env.solve_only(torch.from_numpy(y).cuda(), torch.from_numpy(sec).cuda())
+    torch.cuda.synchronize()
+    assert int(out["status"][0]) == 0 and int(out["status"][1]) != 0
+    with pytest.raises((ZeroDivisionError, FloatingPointError, Exception)):
+        o.solve_only(y[1], sec[1])
+
+
+@pytest.mark.parametrize("name,B", [("small_bridge", 4096), ("small_roof", 16384), ("large_bridge", 8192)])
+def test_full_size_properties(envmod, name, B):
+    """BASELINE.json batch sizes: size-independent properties of the solved batch"""
+    env = make_env(envmod, name, B)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    N, E = env.N, env.E
+    for s in range(3):
+        a_geo = torch.rand(B, N, 2, device="cuda", generator=g) * 0.5
+        a_topo = torch.rand(B, N, 3, device="cuda", generator=g)
+        coin = (torch.rand(B, device="cuda", generator=g) >= 0.5).to(torch.uint8)
+        env.step(a_geo, a_topo, coin)
+    torch.cuda.synchronize()
+    assert int(env.status.abs().max()) == 0
+    P = torch.from_numpy(env.handle.table("loadvec")).cuda()
+    # (1) strain energy = half the work of the loads
+    work = 0.5 * (env.d @ P)
+    assert float(((env.U - work).abs() / work.abs()).max()) <= 1e-9
+    # (2) reactions balance the applied load
+    tnsc = env.handle.table("tnsc"); ndof = env.ndof
+    res_ids = [(i, a) for i in range(N) for a in range(2) if tnsc[i, a] > ndof]
+    ry = sum(env.reactions[:, tnsc[i, a] - 1 - ndof] for i, a in res_ids if a == 1)
+    rx = sum(env.reactions[:, tnsc[i, a] - 1 - ndof] for i, a in res_ids if a == 0)
+    assert float(((ry + P.sum()).abs() / P.sum().abs()).max()) <= 1e-9
+    assert float((rx.abs() / P.sum().abs()).max()) <= 1e-9
+    # (3) the symmetry pass leaves mirror-symmetric geometry and sections -> mirror-symmetric deflections
+    nx = N // 2
+    y = env.nN_x_n[:, :, 1]
+    assert torch.equal(y[:, nx:], y[:, nx:].flip(1)) and torch.equal(y[:, :nx], y[:, :nx].flip(1))
+    dy = env.nN_x_n[:, :, 10].double()
+    assert float(((dy[:, :nx] - dy[:, :nx].flip(1)).abs().max() / dy.abs().max())) <= 1e-6
+    # (4) re-solving the emitted geometry reproduces d bit-exactly (idempotence of the FEM stage)
+    sec = env.nN_x_e[:, :, 0].to(torch.int32).contiguous()
+    again = env.solve_only(y.double().contiguous(), sec)
+    assert torch.equal(again["d"], env.d) and torch.equal(again["axial"], env.axial)
+    # (5) sharding invariance: the second half of the batch alone gives the same bits
+    half = make_env(envmod, name, B // 2)
+    half.reset()
+    g2 = torch.Generator(device="cuda").manual_seed(0)
+    for s in range(3):
+        a_geo = torch.rand(B, N, 2, device="cuda", generator=g2) * 0.5
+        a_topo = torch.rand(B, N, 3, device="cuda", generator=g2)
+        coin = (torch.rand(B, device="cuda", generator=g2) >= 0.5).to(torch.uint8)
+        half.step(a_geo[B // 2:].contiguous(), a_topo[B // 2:].contiguous(), coin[B // 2:].contiguous())
+    torch.cuda.synchronize()
+    for k in F32_FIELDS + ("point", "d", "axial", "ratio", "U"):
+        assert torch.equal(getattr(half, k), getattr(env, k)[B // 2:]), k
+
+
+def test_empty_batch_and_bad_args(envmod):
+    env = make_env(envmod, "small_bridge", 4)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(4, 16, 2), torch.zeros(4, 16, 3))          # CPU tensors
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(3, 16, 2, device="cuda"), torch.zeros(4, 16, 3, device="cuda"))
+    from mop_truss_marl_b200 import capi
+    sin, sout = capi.StepIn(), capi.StepOut()
+    assert capi.lib.tfem_step(env.handle.ptr, 0, C.byref(sin), C.byref(sout), None) == 0   # B = 0 is a no-op
+    assert capi.lib.tfem_step(env.handle.ptr, 4, C.byref(sin), C.byref(sout), None) == -1  # missing inputs
