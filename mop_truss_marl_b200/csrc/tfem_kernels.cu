@@ -94,12 +94,17 @@ __device__ __forceinline__ float pairwise_sum_warp(const float* a, int n, int la
   return res;
 }
 
-__device__ __forceinline__ float warp_max_nonneg(float v) {   // v >= 0 or NaN (NaN sorts above inf)
-  return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+// float min/max over the warp with one REDUX each: map the bit pattern to an unsigned key that is
+// monotonic over all floats (-0.0 sorts just below +0.0, which is value-equal; +NaN sorts above +inf).
+__device__ __forceinline__ unsigned f32_key(float v) {
+  const unsigned b = __float_as_uint(v);
+  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
 }
-__device__ __forceinline__ float warp_min_nonneg(float v) {
-  return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+__device__ __forceinline__ float f32_unkey(unsigned k) {
+  return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
 }
+__device__ __forceinline__ float warp_max_f32(float v) { return f32_unkey(__reduce_max_sync(0xffffffffu, f32_key(v))); }
+__device__ __forceinline__ float warp_min_f32(float v) { return f32_unkey(__reduce_min_sync(0xffffffffu, f32_key(v))); }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -464,7 +469,7 @@ tfem_step_kernel(const StepArgs args) {
       const float cols[7] = {y32o, up32, down32, x9, dy32, x11, x12};
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
-        const float mn = warp_min_nonneg(cols[k]), mx = warp_max_nonneg(cols[k]);
+        const float mn = warp_min_f32(cols[k]), mx = warp_max_f32(cols[k]);
         if (node_lane) dyn[k * N + node] = norm_f32(cols[k], mn, mx);
       }
       if (node_lane) {
@@ -493,9 +498,9 @@ tfem_step_kernel(const StepArgs args) {
     float con1 = 0.f;
 #pragma unroll
     for (int p = 0; p < EPL; ++p) con1 = fmaxf(con1, __double2float_rn(ratio[p]));
-    con1 = warp_max_nonneg(con1);
+    con1 = warp_max_f32(con1);
     const float alld = is_top ? 0.f : fabsf(__double2float_rn(__ddiv_rn(ddy, fam->max_def)));
-    const float con2 = warp_max_nonneg(alld);
+    const float con2 = warp_max_f32(alld);
     if (lane == 0 && args.out.point) {
       reinterpret_cast<float4*>(args.out.point)[b] =
           make_float4(__fdiv_rn(obj1, fam->int_obj1), __fdiv_rn(obj2, fam->int_obj2), con1, con2);

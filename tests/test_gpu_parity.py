@@ -37,11 +37,16 @@ def load_state(env, set_node, set_element, max_up, max_down):
     env.move_range.copy_(torch.from_numpy(np.stack([max_up, max_down], axis=-1).astype(np.float32)))
 
 
-def fp64_tol(cond_like=None):
-    return FP64_TOL
+def fp64_tol(cond=None):
+    """1e-9 (north_star) over the conditioning range the reference reaches in normal play (cond(K) <= 1e6,
+    SURVEY.md section 0); beyond that the reference's own LU result is only good to ~eps*cond, so the
+    tolerance grows linearly with cond (saturated golden walks reach cond 1.9e8)."""
+    if cond is None or cond <= 1e6:
+        return FP64_TOL
+    return FP64_TOL * cond / 1e6
 
 
-def compare_env(env, i, want, point=None, tag=""):
+def compare_env(env, i, want, point=None, tag="", cond=None):
     """want: dict with the oracle/golden fields of ONE environment"""
     raw_n, raw_e = cpu(env.nN_x_n[i]), cpu(env.nN_x_e[i])
     # bit-exact
@@ -54,8 +59,8 @@ def compare_env(env, i, want, point=None, tag=""):
     # float64
     for k in ("d", "axial", "ratio", "reactions"):
         e = nrm(cpu(getattr(env, k)[i]), want[k])
-        assert e <= FP64_TOL, "%s %s: %.3e" % (tag, k, e)
-    assert abs(float(env.U[i]) - float(want["U"])) <= FP64_TOL * abs(float(want["U"])), tag + " U"
+        assert e <= fp64_tol(cond), "%s %s: %.3e (cond %s)" % (tag, k, e, cond)
+    assert abs(float(env.U[i]) - float(want["U"])) <= fp64_tol(cond) * abs(float(want["U"])), tag + " U"
     # float32 tensors
     for k in F32_FIELDS:
         assert_f32_close(tag + " " + k, cpu(getattr(env, k)[i]), want[k])
@@ -91,9 +96,13 @@ def test_transitions_vs_golden(envmod, name):
     env.step(a_geo, a_topo, coin)
     torch.cuda.synchronize()
     assert np.array_equal(cpu(a_geo), g["tr_out_a_geo"]) and np.array_equal(cpu(a_topo), g["tr_out_a_topo"])
+    from oracle.truss_oracle import TrussOracle
+    o = TrussOracle(name)
     for i in range(T):
         want = {k[len("tr_out_"):]: v[i] for k, v in g.items() if k.startswith("tr_out_")}
-        compare_env(env, i, want, point=g["tr_out_point"][i], tag="%s tr[%d] mode %d" % (name, i, g["tr_mode"][i]))
+        cond = float(np.linalg.cond(o.solve_only(want["y"], want["section"])["K"]))
+        compare_env(env, i, want, point=g["tr_out_point"][i], cond=cond,
+                    tag="%s tr[%d] mode %d" % (name, i, g["tr_mode"][i]))
 
 
 @pytest.mark.parametrize("name", FAMILY_NAMES)
