@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtfem.so")
+LIB_PATH = os.environ.get("TFEM_LIB", os.path.join(_HERE, "lib", "libtfem.so"))
 
 MAX_NX = 16
 NSEC = 5

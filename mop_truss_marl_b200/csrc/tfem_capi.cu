@@ -148,6 +148,7 @@ static int launch(tfem_handle_t h, tfem::StepArgs& a, void* stream) {
   if (h->device < 0) return fail(TFEM_ERR_CUDA, "tables-only handle (device < 0): libtfem has no CPU path");
   a.fam = h->d_tables;
   a.maps = h->d_maps;
+  a.map_entries = (int)h->fam.maps.size();
   DeviceGuard guard(h->device);
   if (!guard.ok) return fail(TFEM_ERR_CUDA, "cudaSetDevice failed");
   int rc = tfem::step_kernel_launch(h->fam.t.nx, a, h->launch, (cudaStream_t)stream);

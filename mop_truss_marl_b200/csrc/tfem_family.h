@@ -37,7 +37,7 @@ struct PoolLayout {
 enum ElCol { EL_SEC = 0, EL_A, EL_L, EL_TENS, EL_COMP, EL_Q, EL_VIOL, EL_AS, EL_TS, EL_CS };
 
 // Flat POD copied verbatim to the device.
-struct FamilyTables {
+struct alignas(16) FamilyTables {
   int32_t nx, N, E, ndof, nres, truss_type, symmetry, pad0;
   // scalars ("weak" python numbers of the reference, kept in float64)
   double y_max, y_min, d_min, ymax_minus_dmin, max_def, young, allow, load_y;
@@ -64,6 +64,7 @@ struct FamilyTables {
   // output maps (offsets into `maps`, counted in uint16 entries)
   int32_t map_xn, map_as, map_ts, map_cs, map_rawn, map_rawe, map_total, pad3;
 };
+static_assert(sizeof(FamilyTables) % 16 == 0, "FamilyTables is staged with 16-byte copies");
 
 struct Family {
   tfem_family_desc desc;

@@ -27,8 +27,12 @@ namespace tfem {
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 8;
+#ifndef TFEM_WARPS_PER_CTA
+#define TFEM_WARPS_PER_CTA 8
+#endif
+constexpr int WARPS_PER_CTA = TFEM_WARPS_PER_CTA;
 constexpr int BAND = 8;  // stored sub-diagonals + diagonal per column
+constexpr int PADC = 8;  // zero columns appended to the band so the elimination needs no bounds checks
 
 // ---- "typed" scalar: value + whether the reference holds it as a python scalar (weak) or np.float32 ----
 struct TS {
@@ -127,13 +131,19 @@ struct Dims {
   static constexpr int EPL = (E + 31) / 32;     // element passes per lane
   static constexpr int POOL = 2 + 12 * N + 13 * N + 10 * E;
   static constexpr int POOL_PAD = (POOL + 3) & ~3;
-  static constexpr int WARP_BYTES = NI * BAND * 8 + NI * 8 + POOL_PAD * 4;
+  static constexpr int WARP_BYTES = (NI + PADC) * BAND * 8 + (NI + PADC) * 8 + NI * 8 + POOL_PAD * 4;
 };
 
 __host__ __device__ constexpr int align16(int v) { return (v + 15) & ~15; }
 
+#ifndef TFEM_MINB_SMALL
+#define TFEM_MINB_SMALL 2
+#endif
+#ifndef TFEM_MINB_LARGE
+#define TFEM_MINB_LARGE 2
+#endif
 template <int NX>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (NX == 8) ? TFEM_MINB_SMALL : TFEM_MINB_LARGE)
 tfem_step_kernel(const StepArgs args) {
   using D = Dims<NX>;
   constexpr int N = D::N, E = D::E, NI = D::NI, EPL = D::EPL;
@@ -142,23 +152,42 @@ tfem_step_kernel(const StepArgs args) {
   uint16_t* maps = reinterpret_cast<uint16_t*>(smem_raw + align16((int)sizeof(FamilyTables)));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  {  // stage the family tables and output maps once per CTA
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(args.fam);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(fam);
-    for (int i = tid; i < (int)(sizeof(FamilyTables) / 4); i += blockDim.x) dst[i] = src[i];
+  const int mode = args.mode;
+  const int warps_total = gridDim.x * WARPS_PER_CTA;
+  const int node = lane % N;                 // lanes >= N mirror a node so warp reductions stay exact
+  // ---- per-env inputs are fetched one environment ahead (the first batch overlaps the table staging) ----
+  float in_y = 0.f, in_at0 = 0.f, in_at1 = 0.f, in_at2 = 0.f, in_sec[EPL];
+  float2 in_mr = make_float2(0.f, 0.f), in_ag = make_float2(0.f, 0.f);
+  int in_coin = 0;
+  auto fetch_inputs = [&](int b) {
+    if (mode != MODE_STEP || b >= args.B) return;
+    in_y = args.in.set_node[((size_t)b * N + node) * 12 + 1];
+    in_mr = reinterpret_cast<const float2*>(args.in.move_range)[(size_t)b * N + node];
+    in_ag = reinterpret_cast<const float2*>(args.in.a_geo)[(size_t)b * N + node];
+    const float* atp = args.in.a_topo + ((size_t)b * N + node) * 3;
+    in_at0 = atp[0]; in_at1 = atp[1]; in_at2 = atp[2];
+#pragma unroll
+    for (int p = 0; p < EPL; ++p) {
+      const int e = lane + 32 * p;
+      in_sec[p] = (e < E) ? args.in.set_element[((size_t)b * E + e) * 21] : 0.f;
+    }
+    in_coin = args.in.coin ? (int)args.in.coin[b] : 0;
+  };
+  fetch_inputs(blockIdx.x * WARPS_PER_CTA + warp);
+  {  // stage the family tables and output maps once per CTA (L2-resident, 8..15 KB)
+    const uint4* src = reinterpret_cast<const uint4*>(args.fam);
+    uint4* dst = reinterpret_cast<uint4*>(fam);
+    for (int i = tid; i < (int)(sizeof(FamilyTables) / 16); i += blockDim.x) dst[i] = src[i];
+    const uint4* msrc = reinterpret_cast<const uint4*>(args.maps);
+    uint4* mdst = reinterpret_cast<uint4*>(maps);
+    for (int i = tid; i < args.map_entries / 8; i += blockDim.x) mdst[i] = msrc[i];
   }
   __syncthreads();
-  const int map_total = fam->map_total;
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(args.maps);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(maps);
-    for (int i = tid; i < (map_total + 1) / 2; i += blockDim.x) dst[i] = src[i];
-  }
-  unsigned char* wbase = smem_raw + align16((int)sizeof(FamilyTables)) + align16(((map_total + 7) & ~7) * 2) +
-                         warp * D::WARP_BYTES;
+  unsigned char* wbase = smem_raw + align16((int)sizeof(FamilyTables)) + align16(args.map_entries * 2) + warp * D::WARP_BYTES;
   double* Kb = reinterpret_cast<double*>(wbase);            // [NI][BAND]: Kb[j*8+k] = K[j+k][j]
-  double* z = Kb + NI * BAND;                               // [NI] rhs -> solution
-  float* pool = reinterpret_cast<float*>(z + NI);           // value pool
+  double* z = Kb + (NI + PADC) * BAND;                      // [NI + PADC] rhs -> solution
+  double* dinv = z + NI + PADC;                             // [NI] 1 / pivot
+  float* pool = reinterpret_cast<float*>(dinv + NI);        // value pool
   const PoolLayout pl{N, E};
   float* dyn = pool + pl.dyn_base();
   // scratch that aliases the (not yet written) dynamic pool during transition / assembly
@@ -166,7 +195,7 @@ tfem_step_kernel(const StepArgs args) {
   float* at_s = dyn;                                        // [N][3] clipped a_topo (before g is written)
   int* sec_s = reinterpret_cast<int*>(dyn + 3 * N);         // [E] sections after the action
   for (int i = lane; i < pl.dyn_base(); i += 32) pool[i] = fam->pool_const[i];
-  __syncthreads();
+  __syncwarp();
 
   // trailing-update role of this lane: (a, b), 1 <= b <= a <= 7, for lanes 0..27
   int ta = 0, tb = 0;
@@ -175,14 +204,11 @@ tfem_step_kernel(const StepArgs args) {
     for (int b = 1; b <= 7; ++b)
       for (int a = b; a <= 7; ++a) { if (t == lane) { ta = a; tb = b; } ++t; }
   }
-  const int node = lane % N;                 // lanes >= N mirror a node so warp reductions stay exact
   const bool node_lane = lane < N;
   const int colc = lane % NX;                // chord column handled in the constraint passes
   const int bi = 4 * (node % NX) + 2 * (node / NX);
   const unsigned res_bits = fam->res[node];
   const bool is_top = fam->top[node] != 0;
-  const int mode = args.mode;
-  const int warps_total = gridDim.x * WARPS_PER_CTA;
 
   for (int b = blockIdx.x * WARPS_PER_CTA + warp; b < args.B; b += warps_total) {
     int status = 0;
@@ -190,11 +216,12 @@ tfem_step_kernel(const StepArgs args) {
     int sec[EPL];
     // ======================================= geometry =======================================
     if (mode == MODE_STEP) {
-      const float y32 = args.in.set_node[((size_t)b * N + node) * 12 + 1];
-      const float2 mr = reinterpret_cast<const float2*>(args.in.move_range)[(size_t)b * N + node];
-      float2 ag = reinterpret_cast<const float2*>(args.in.a_geo)[(size_t)b * N + node];
+      const float y32 = in_y;
+      const float2 mr = in_mr;
+      float2 ag = in_ag;
       float* atp = args.in.a_topo + ((size_t)b * N + node) * 3;
-      float at0 = atp[0], at1 = atp[1], at2 = atp[2];
+      float at0 = in_at0, at1 = in_at1, at2 = in_at2;
+      const int coin = in_coin != 0;
       ag.x = clip01(ag.x); ag.y = clip01(ag.y);
       at0 = clip01(at0); at1 = clip01(at1); at2 = clip01(at2);
       if (node_lane) {                       // the reference clips the caller's arrays in place
@@ -205,8 +232,9 @@ tfem_step_kernel(const StepArgs args) {
 #pragma unroll
       for (int p = 0; p < EPL; ++p) {
         const int e = lane + 32 * p;
-        sec[p] = (e < E) ? __float2int_rz(args.in.set_element[((size_t)b * E + e) * 21]) : 0;
+        sec[p] = (e < E) ? __float2int_rz(in_sec[p]) : 0;
       }
+      fetch_inputs(b + warps_total);          // next environment of this warp (if any)
       // ---- action decode (truss2D_ENV.py:401-416) ----
       y = S(y32);
       {
@@ -244,7 +272,6 @@ tfem_step_kernel(const StepArgs args) {
       if (ts_gt(yt, YMAX)) yt = YMAX;
       if (ts_lt(ts_abs(ts_sub(yt, yb)), DMIN)) yt = ts_add(yb, DMIN);
       // ---- symmetry copy (:460-502 small / :460-557 large) ----
-      const int coin = args.in.coin ? (args.in.coin[b] != 0) : 0;
       const int srcb = fam->sym_src[coin][colc], srct = fam->sym_src[coin][colc + NX] - NX;
       yb = ts_shfl(yb, srcb);
       yt = ts_shfl(yt, srct);
@@ -291,7 +318,8 @@ tfem_step_kernel(const StepArgs args) {
 
     // ======================================= assembly ========================================
     // zero the band, publish float(y) for the element lanes
-    for (int i = lane; i < NI * BAND / 2; i += 32) reinterpret_cast<double2*>(Kb)[i] = make_double2(0.0, 0.0);
+    for (int i = lane; i < (NI + PADC) * BAND / 2; i += 32) reinterpret_cast<double2*>(Kb)[i] = make_double2(0.0, 0.0);
+    if (lane < PADC) z[NI + lane] = 0.0;
     if (node_lane) { z[bi] = y.v; }          // z doubles as y64 storage until the rhs is written
     __syncwarp();
     double eL[EPL], ec[EPL], es[EPL], ek[EPL];
@@ -341,38 +369,34 @@ tfem_step_kernel(const StepArgs args) {
     __syncwarp();
 
     // ======================================= banded LDL^T + forward substitution ==========================
-    for (int j = 0; j < NI; ++j) {
-      const double piv = Kb[j * BAND];
-      if (!(piv > 0.0)) status |= TFEM_STATUS_NOT_SPD;
-      const double inv = 1.0 / piv;
-      const double zj = z[j];
-      double la = 0.0, upd = 0.0;
-      int tgt = -1;
-      if (lane < 28 && j + ta < NI) {
-        la = Kb[j * BAND + ta] * inv;                       // L[j+a][j]
-        const double lb = Kb[j * BAND + tb];                // K[j+b][j] (unscaled)
-        tgt = (j + tb) * BAND + (ta - tb);
-        upd = fma(-la, lb, Kb[tgt]);
+    // Column j: every lane forms 1/pivot; lane (a,b) updates K[j+a][j+b] -= L[j+a][j] * K[j+b][j]; the rhs
+    // rows ride along (lanes 28..31 take a = 1..4, lanes 0..2 also take a = 5..7).  The zero padding makes
+    // every access in-bounds, and keeping 1/pivot in its own array leaves ONE warp barrier per column.
+    {
+      const int za = (lane >= 28) ? lane - 27 : (lane < 3 ? lane + 5 : 0);
+      const int tgt_off = tb * BAND + (ta - tb);
+      double* col = Kb;
+#pragma unroll 4
+      for (int j = 0; j < NI; ++j, col += BAND) {
+        const double inv = 1.0 / col[0];
+        const double la = col[ta] * inv;                      // L[j+a][j]
+        const double upd = fma(-la, col[tb], col[tgt_off]);
+        double zl = 0.0;
+        if (za) zl = fma(-(col[za] * inv), z[j], z[j + za]);
+        if (lane < 28) col[tgt_off] = upd;
+        if (za) z[j + za] = zl;
+        dinv[j] = inv;
+        __syncwarp();
       }
-      double zl = 0.0;
-      int zt = -1;
-      {   // rhs rows a = 1..7: lanes 28..31 take a = 1..4, lanes 0..2 take a = 5..7
-        const int za = (lane >= 28) ? lane - 27 : (lane < 3 ? lane + 5 : 0);
-        if (za > 0 && j + za < NI) {
-          zt = j + za;
-          zl = fma(-(Kb[j * BAND + za] * inv), zj, z[zt]);
-        }
-      }
-      __syncwarp();
-      if (tgt >= 0) Kb[tgt] = upd;
-      if (zt >= 0) z[zt] = zl;
-      if (lane == 0) Kb[j * BAND] = inv;
-      __syncwarp();
     }
-    // scale the stored columns to L and apply D^-1
+    // SPD check, scale the stored columns to L, apply D^-1
+    for (int i = lane; i < NI; i += 32) {
+      const double iv = dinv[i];
+      if (!(iv > 0.0) || !(iv < CUDART_INF)) status |= TFEM_STATUS_NOT_SPD;
+      z[i] *= iv;
+    }
     for (int i = lane; i < NI * BAND; i += 32)
-      if (i % BAND) Kb[i] *= Kb[i - (i % BAND)];
-    for (int i = lane; i < NI; i += 32) z[i] *= Kb[i * BAND];
+      if (i % BAND) Kb[i] *= dinv[i / BAND];
     __syncwarp();
     // back substitution L^T x = w, column oriented
     for (int j = NI - 1; j > 0; --j) {
@@ -572,10 +596,14 @@ int step_kernel_configure(int nx, int device, int map_entries, LaunchInfo* info)
     smem = smem_bytes_for<8>(map_entries);
     err = cudaFuncSetAttribute(tfem_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(tfem_step_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (err != cudaSuccess) return (int)err;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tfem_step_kernel<8>, WARPS_PER_CTA * 32, smem);
   } else if (nx == 16) {
     smem = smem_bytes_for<16>(map_entries);
     err = cudaFuncSetAttribute(tfem_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(tfem_step_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (err != cudaSuccess) return (int)err;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tfem_step_kernel<16>, WARPS_PER_CTA * 32, smem);
   } else {

@@ -10,6 +10,7 @@ enum StepMode { MODE_STEP = 0, MODE_RESET = 1, MODE_SOLVE_ONLY = 2 };
 struct StepArgs {
   const FamilyTables* fam;     // device copy
   const uint16_t* maps;        // device copy of Family::maps
+  int map_entries;             // padded to a multiple of 8
   int B;
   int mode;
   tfem_step_in in;             // device pointers (MODE_STEP)
