@@ -1,0 +1,67 @@
+/* tactor.h -- C ABI of the batched node-agent GCN actor forward pass (libtfem.so).
+ *
+ * Replaces, for B environments at once, what the reference does one environment at a time:
+ *   multimodes_actor.call  (train/code/truss2D_RL.py:75-127)   13 GCNConv layers, hidden 200
+ *   multimodals_OneAgent.act (truss2D_RL.py:328-354)            forward + Ornstein-Uhlenbeck noise
+ *
+ * GCNConv (spektral 1.2.0, use_bias=True, no activation): out = A . (X . W) + b, followed by ReLU /
+ * sigmoid in the caller.  All device buffers are caller-owned, contiguous, 16-byte aligned float32.
+ * Return value 0 = ok, < 0 = error (tactor_last_error(); same codes as tfem.h).
+ */
+#ifndef TACTOR_H_
+#define TACTOR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TACTOR_HIDDEN 200
+#define TACTOR_NLAYERS 13
+
+typedef struct tactor_handle_s* tactor_handle_t;
+
+/* Layer order = the checkpoint's variable names (model/2000pickle_base/AgentK_Actor_pickle.index):
+ * gcn_l1_1, l1_2, l1_3 [13,200]; l1_4 [4,200]; l2_1..l2_5, l3_1, l3_2 [200,200]; l4_1 [200,2];
+ * l4_2 [200,3].  kernel[i] is row-major [in,out] HOST float32, bias[i] HOST float32 [out]. */
+typedef struct tactor_weights {
+  const float* kernel[TACTOR_NLAYERS];
+  const float* bias[TACTOR_NLAYERS];
+} tactor_weights;
+
+/* Inputs of multimodes_actor.call for B environments (device pointers). */
+typedef struct tactor_inputs {
+  const float* x_n;      /* [B,N,13] */
+  const float* A_n;      /* [N,N]    topology constant (TFEM_TAB_A_N), shared by all environments */
+  const float* A_s;      /* [B,N,N] */
+  const float* A_n_ts;   /* [B,N,N] */
+  const float* A_n_cs;   /* [B,N,N] */
+  const float* x_p;      /* [B,P,4]  Pareto-front graph features (truss2D_ENV.py:22-41) */
+  const float* A_p;      /* [B,P,P] */
+  const int32_t* n_pf;   /* [B] valid Pareto rows per environment (<= P); NULL = all P rows */
+  int32_t P;             /* padded Pareto-front length (1..50) */
+} tactor_inputs;
+
+const char* tactor_last_error(void);
+
+/* nodes = N (16 or 32), max_batch = largest B of any later call (workspace is allocated once). */
+int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device, tactor_handle_t* out);
+int tactor_destroy(tactor_handle_t h);
+
+/* geo [B,N,2], topo [B,N,3] = sigmoid outputs of gcn_l4_1 / gcn_l4_2 (no noise). */
+int tactor_forward(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, void* stream);
+
+/* act(): forward + OU noise theta*(mu-x)*1e-4 + sigma*n, n ~ N(0,1) from a counter-based generator
+ * keyed by (seed, call counter, element index) -- statistically, not bit-wise, the reference's
+ * np.random.randn stream (truss2D_RL.py:41-48).  sigma == 0 and theta == 0 gives tactor_forward. */
+int tactor_act(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo,
+               float mu, float theta, float sigma, uint64_t seed, void* stream);
+
+int64_t tactor_launch_count(tactor_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACTOR_H_ */

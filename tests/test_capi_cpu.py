@@ -21,6 +21,12 @@ def test_exports_match_header():
     for name in declared:
         assert hasattr(capi.lib, name), name
     assert b"sm_100a" in capi.lib.tfem_version()
+    hdr2 = open(os.path.join(ROOT, "include", "tactor.h")).read()
+    declared2 = set(re.findall(r"\b(tactor_[a-z_0-9]+)\s*\(", hdr2))
+    assert declared2 == {"tactor_last_error", "tactor_create", "tactor_destroy", "tactor_forward", "tactor_act",
+                         "tactor_launch_count"}
+    for name in declared2:
+        assert hasattr(capi.lib, name), name
 
 
 def test_struct_sizes():

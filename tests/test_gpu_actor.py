@@ -1,0 +1,72 @@
+"""GPU: batched actor forward (libtfem tactor_*) against the numpy restatement in float64.
+
+The actor has no recorded outputs in the reference (parity unpinned): the bar here
+is float32-GEMM agreement with the float64 oracle of the same restated network (|delta| <= 2e-5 on the
+sigmoid outputs), plus determinism and the statistics of the OU noise."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ATOL = 2e-5
+
+
+def random_inputs(rng, B, N, P):
+    x_n = rng.rand(B, N, 13).astype(np.float32)
+    A = (rng.rand(B, N, N) < 0.3).astype(np.float32)
+    A = np.maximum(A, A.transpose(0, 2, 1))
+    A_s = (A * rng.rand(B, N, N)).astype(np.float32)
+    A_ts = (A * rng.rand(B, N, N) * (rng.rand(B, N, N) < 0.5)).astype(np.float32)
+    A_cs = (A * rng.rand(B, N, N) * (rng.rand(B, N, N) < 0.5)).astype(np.float32)
+    A_n = rng.rand(N, N).astype(np.float32) * 0.3
+    x_p = rng.rand(B, P, 4).astype(np.float32)
+    A_p = (rng.rand(B, P, P) * 0.5).astype(np.float32)
+    return x_n, A_n, A_s, A_ts, A_cs, x_p, A_p
+
+
+@pytest.mark.parametrize("N,B,P", [(16, 37, 1), (16, 64, 7), (32, 9, 50), (32, 32, 3)])
+def test_forward_matches_float64_oracle(N, B, P):
+    from mop_truss_marl_b200 import actor, tf_checkpoint
+    from oracle.actor_oracle import actor_forward
+    rng = np.random.RandomState(N + B)
+    w = tf_checkpoint.random_actor_weights(seed=3)
+    for k in w:                                      # non-zero biases
+        w[k] = (w[k][0], (rng.randn(*w[k][1].shape) * 0.05).astype(np.float32))
+    inp = random_inputs(rng, B, N, P)
+    n_pf = rng.randint(1, P + 1, size=B).astype(np.int32)
+    a = actor.BatchedActor(w, N, max_batch=B)
+    dev = [torch.from_numpy(t).cuda() for t in inp]
+    geo, topo = a.forward(*dev, n_pf=torch.from_numpy(n_pf).cuda())
+    torch.cuda.synchronize()
+    g64, t64 = actor_forward(w, *inp, n_pf=n_pf)
+    assert geo.shape == (B, N, 2) and topo.shape == (B, N, 3)
+    assert np.abs(geo.cpu().numpy() - g64).max() <= ATOL
+    assert np.abs(topo.cpu().numpy() - t64).max() <= ATOL
+    # determinism + n_pf=None means "all P rows"
+    geo2, topo2 = a.forward(*dev, n_pf=torch.from_numpy(n_pf).cuda())
+    assert torch.equal(geo, geo2) and torch.equal(topo, topo2)
+    g3, t3 = a.forward(*dev)
+    g64b, t64b = actor_forward(w, *inp)
+    assert np.abs(g3.cpu().numpy() - g64b).max() <= ATOL and np.abs(t3.cpu().numpy() - t64b).max() <= ATOL
+    assert a.launch_count() == 3 * 13
+
+
+def test_act_noise_statistics():
+    from mop_truss_marl_b200 import actor, tf_checkpoint
+    rng = np.random.RandomState(0)
+    N, B = 16, 2048
+    w = tf_checkpoint.random_actor_weights(seed=1)
+    inp = [torch.from_numpy(t).cuda() for t in random_inputs(rng, B, N, 1)]
+    a = actor.BatchedActor(w, N, max_batch=B, mu=0.1, theta=0.1, sigma=0.1, seed=20)
+    geo0, topo0 = a.forward(*inp)
+    geo1, topo1 = a.act(*inp)
+    geo2, topo2 = a.act(*inp)
+    torch.cuda.synchronize()
+    d = torch.cat([(geo1 - geo0).flatten(), (topo1 - topo0).flatten()]).double().cpu().numpy()
+    drift = (0.1 * (0.1 - torch.cat([geo0.flatten(), topo0.flatten()]).double().cpu().numpy()) * 1e-4)
+    z = (d - drift) / 0.1
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    assert abs(np.mean(z ** 3)) < 0.05 and abs(np.mean(z ** 4) - 3.0) < 0.1
+    assert not torch.equal(geo1, geo2)               # a new call draws new noise
+    assert a.update_num == 2
