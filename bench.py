@@ -151,7 +151,18 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_name(args):
-    return "%s B=%d per GPU: batched FEM env-step (_game_modify equivalent)" % (args.family, args.batch)
+    if getattr(args, "no_actor", False) or args.impl == "reference":
+        return "%s B=%d per GPU: batched FEM env-step (_game_modify equivalent), uniform random actions" % (
+            args.family, args.batch)
+    return "%s B=%d per GPU: actor forward (act, OU noise) + batched FEM env-step (_game_modify equivalent)" % (
+        args.family, args.batch)
+
+
+def actor_flops(N, P=1, H=200):
+    """multiply-adds x2 of one actor forward for one environment (GEMMs + adjacency products)"""
+    gemm = 3 * N * 13 * H + P * 4 * H + 7 * N * H * H + N * H * 5
+    adj = 10 * N * N * H + P * P * H + 2 * N * N * 5
+    return 2 * (gemm + adj)
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -165,6 +176,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-actor", action="store_true", help="drive the env with resident uniform actions instead of the actor")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +191,8 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    from mop_truss_marl_b200 import batched_env, capi
+    from mop_truss_marl_b200 import actor as actor_mod
+    from mop_truss_marl_b200 import batched_env, capi, tf_checkpoint
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -199,9 +212,32 @@ def main():
     acts = [make_actions() for _ in range(nact)]
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def one_step(i):
-        a_geo, a_topo, coin = acts[i % nact]
-        env.step(a_geo, a_topo, coin)
+    use_actor = not args.no_actor
+    if use_actor:
+        # random-init weights of the reference architecture (no checkpoint travels to the GPU box); the
+        # Pareto-front graph is the reset-time one-node graph of _game_get_1_state (truss2D_ENV.py:346-352)
+        pol = actor_mod.BatchedActor(tf_checkpoint.random_actor_weights(seed=20 + rank), N, B, device=dev)
+        x_p = torch.tensor([1.0, 1.0, 1.0, 1.0 / 50], device=dev).repeat(B, 1, 1).contiguous()
+        A_p = torch.ones(B, 1, 1, device=dev)
+        a_geo_buf = torch.empty(B, N, 2, device=dev)
+        a_topo_buf = torch.empty(B, N, 3, device=dev)
+    stage_ev = []
+
+    def one_step(i, timed=False):
+        if use_actor:
+            if timed:
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+            pol.act(env.x_n, env.A_n, env.A_s, env.A_n_ts, env.A_n_cs, x_p, A_p, out=(a_geo_buf, a_topo_buf))
+            if timed:
+                e1.record()
+            env.step(a_geo_buf, a_topo_buf, acts[i % nact][2])
+            if timed:
+                e2.record()
+                stage_ev.append((e0, e1, e2))
+        else:
+            a_geo, a_topo, coin = acts[i % nact]
+            env.step(a_geo, a_topo, coin)
 
     for i in range(8):                          # state after w = 8 warm-up steps of i.i.d. actions
         one_step(i)
@@ -214,7 +250,7 @@ def main():
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = env.launch_count()
+    launches0 = env.launch_count() + (pol.launch_count() if use_actor else 0)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     torch.cuda.synchronize()
@@ -222,10 +258,10 @@ def main():
         if flush is not None:
             flush.fill_(i & 0xFF)
         starts[i].record()
-        one_step(i)
+        one_step(i, timed=True)
         ends[i].record()
     torch.cuda.synchronize()
-    launches = env.launch_count() - launches0
+    launches = env.launch_count() + (pol.launch_count() if use_actor else 0) - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
     if world > 1:
@@ -236,27 +272,58 @@ def main():
     value = B * world / (ms_per_step * 1e-3)
     status_bad = int((env.status != 0).sum().item())
 
-    # ---- e2e: the host-buffer call (tfem_step_host) -----------------------------------------------------
-    host = {
-        "set_node": env.nN_x_n.cpu().pin_memory(), "set_element": env.nN_x_e.cpu().pin_memory(),
-        "move_range": env.move_range.cpu().pin_memory(),
-        "a_geo": torch.rand(B, N, 2).pin_memory(), "a_topo": torch.rand(B, N, 3).pin_memory(),
-        "coin": (torch.rand(B) >= 0.5).to(torch.uint8).pin_memory(),
-    }
-    out_host = {k: torch.empty(s, dtype=torch.float32).pin_memory() for k, s in (
-        ("x_n", (B, N, 13)), ("A_s", (B, N, N)), ("A_n_ts", (B, N, N)), ("A_n_cs", (B, N, N)),
-        ("nN_x_n", (B, N, 12)), ("nN_x_e", (B, E, 21)), ("point", (B, 4)))}
+    # ---- e2e: HOST buffers in, HOST buffers out, copies inside the timed region ----------------------------
+    f32_out = (("x_n", (B, N, 13)), ("A_s", (B, N, N)), ("A_n_ts", (B, N, N)), ("A_n_cs", (B, N, N)),
+               ("nN_x_n", (B, N, 12)), ("nN_x_e", (B, E, 21)), ("point", (B, 4)))
+    out_host = {k: torch.empty(sh, dtype=torch.float32).pin_memory() for k, sh in f32_out}
     out_host["status"] = torch.zeros(B, dtype=torch.int32).pin_memory()
-    out_np = {k: v.numpy() for k, v in out_host.items()}
-    a_geo0, a_topo0 = host["a_geo"].clone(), host["a_topo"].clone()
+    coin_host = (torch.rand(B) >= 0.5).to(torch.uint8).pin_memory()
+    if use_actor:
+        # the caller holds the state tuple on the host (like the reference driver); per step it goes to the
+        # device, the actor acts on it, the env steps, and the new state tuple + actions come back
+        st_host = {k: getattr(env, k).cpu().pin_memory() for k in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range")}
+        out_host["a_geo"] = torch.empty(B, N, 2).pin_memory()
+        out_host["a_topo"] = torch.empty(B, N, 3).pin_memory()
+        out_host["move_range"] = torch.empty(B, N, 2).pin_memory()
+        coin_dev = torch.empty(B, dtype=torch.uint8, device=dev)
 
-    def e2e_step():
-        host["a_geo"].copy_(a_geo0); host["a_topo"].copy_(a_topo0)      # fresh (unclipped) actions each step
-        batched_env.step_host(env.handle, host["set_node"].numpy(), host["set_element"].numpy(),
-                              host["move_range"].numpy(), host["a_geo"].numpy(), host["a_topo"].numpy(),
-                              host["coin"].numpy(), want_fp64=False, out=out_np)
-        # the state the call returned is the next call's input, like the reference driver does
-        host["set_node"].copy_(out_host["nN_x_n"]); host["set_element"].copy_(out_host["nN_x_e"])
+        def e2e_step():
+            for k, v in st_host.items():
+                getattr(env, k).copy_(v, non_blocking=True)
+            coin_dev.copy_(coin_host, non_blocking=True)
+            pol.act(env.x_n, env.A_n, env.A_s, env.A_n_ts, env.A_n_cs, x_p, A_p, out=(a_geo_buf, a_topo_buf))
+            env.step(a_geo_buf, a_topo_buf, coin_dev)
+            for k, _ in f32_out:
+                out_host[k].copy_(getattr(env, k), non_blocking=True)
+            out_host["status"].copy_(env.status, non_blocking=True)
+            out_host["a_geo"].copy_(a_geo_buf, non_blocking=True)
+            out_host["a_topo"].copy_(a_topo_buf, non_blocking=True)
+            out_host["move_range"].copy_(env.move_range, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            for k in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range"):
+                st_host[k], out_host[k] = out_host[k], st_host[k]          # returned state = next input
+        h2d = sum(v.numel() * v.element_size() for v in st_host.values()) + B
+        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+        e2e_path = "pinned host state tuple -> device -> BatchedActor.act + BatchedTrussEnv.step -> host (state tuple, point, actions)"
+    else:
+        host = {
+            "set_node": env.nN_x_n.cpu().pin_memory(), "set_element": env.nN_x_e.cpu().pin_memory(),
+            "move_range": env.move_range.cpu().pin_memory(),
+            "a_geo": torch.rand(B, N, 2).pin_memory(), "a_topo": torch.rand(B, N, 3).pin_memory(),
+        }
+        out_np = {k: v.numpy() for k, v in out_host.items()}
+        a_geo0, a_topo0 = host["a_geo"].clone(), host["a_topo"].clone()
+
+        def e2e_step():
+            host["a_geo"].copy_(a_geo0); host["a_topo"].copy_(a_topo0)      # fresh (unclipped) actions each step
+            batched_env.step_host(env.handle, host["set_node"].numpy(), host["set_element"].numpy(),
+                                  host["move_range"].numpy(), host["a_geo"].numpy(), host["a_topo"].numpy(),
+                                  coin_host.numpy(), want_fp64=False, out=out_np)
+            host["set_node"].copy_(out_host["nN_x_n"]); host["set_element"].copy_(out_host["nN_x_e"])
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) + B
+        d2h = sum(v.numel() * v.element_size() for v in out_host.values()) + sum(
+            host[k].numel() * host[k].element_size() for k in ("a_geo", "a_topo", "move_range"))
+        e2e_path = "tfem_step_host: pinned host state tables + actions in, all float32 tensors out"
     ke = max(5, min(K, 50))
     for _ in range(3):
         e2e_step()
@@ -273,9 +340,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     clocks = sampler.result()
-    h2d = sum(host[k].numel() * host[k].element_size() for k in host)
-    d2h = sum(v.numel() * v.element_size() for v in out_host.values()) + sum(
-        host[k].numel() * host[k].element_size() for k in ("a_geo", "a_topo", "move_range"))
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -283,32 +347,56 @@ def main():
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
         abytes = algorithmic_bytes(N, E, env.ndof)
-        kernel_ms = float(np.mean(step_ms))             # the step IS one kernel launch; events bracket it
-        achieved = abytes * B / (kernel_ms * 1e-3) / 1e9
+        if use_actor:
+            actor_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1, _ in stage_ev]))
+            fem_ms = float(np.mean([e1.elapsed_time(e2) for _, e1, e2 in stage_ev]))
+        else:
+            actor_ms, fem_ms = 0.0, float(np.mean(step_ms))
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("%s_B%d" % (args.family, B))
+        fem_achieved = abytes * B / (fem_ms * 1e-3) / 1e9
+        roof_fem = {"bound": "hbm", "achieved": fem_achieved, "peak": peak, "unit": "GB/s", "frac": fem_achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel": "tfem_step_kernel (1 launch per step)",
+                    "algorithmic_bytes_per_env": abytes, "kernel_ms": fem_ms}
+        stages = {"actor_ms": actor_ms, "fem_ms": fem_ms,
+                  "fem_only_env_steps_per_s": B * world / (fem_ms * 1e-3)}
+        if use_actor and actor_ms > fem_ms:
+            # dominant stage = the 10 gcn_layer_kernel launches (float32 FFMA GEMM + fused adjacency product);
+            # measured against the tensor roof the spec names (bf16 cuBLAS), which an FP32 CUDA-core kernel
+            # cannot approach -- see DESIGN.md "actor" for the tcgen05 plan
+            tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            aflops = actor_flops(N) * B
+            ach = aflops / (actor_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                        "traffic": None, "kernel": "gcn_layer_kernel (10 of the 15 actor launches per step)",
+                        "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback",
+                        "algorithmic_flops_per_env": actor_flops(N), "kernel_ms": actor_ms,
+                        "note": "float32 FFMA kernel (reference dtype) reported against the bf16 tensor roof"}
+        else:
+            roofline = roof_fem
         n_cpu, t_cpu = oracle_steps_per_sec(args.family, args.cpu_seconds)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64 (FEM) + f32 (actor)" if use_actor else "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "family": args.family, "envs_per_gpu": B,
                        "nodes": N, "elements": E, "free_dofs": env.ndof,
                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
-                       "actions": "uniform [0,1) float32, coin Bernoulli(1/2), own state fed back",
+                       "actions": ("actor outputs (random-init weights of the reference architecture) + OU noise"
+                                   if use_actor else "uniform [0,1) float32") + ", coin Bernoulli(1/2), own state fed back",
                        "parallelism": "env-parallel, %d independent shard(s), no collective" % world},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "tfem_step_kernel", "algorithmic_bytes_per_env": abytes,
-                         "kernel_ms": kernel_ms},
+            "roofline": roofline,
+            "roofline_fem": roof_fem,
+            "stages": stages,
             "cpu_baseline": {"value": n_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "%d oracle env-steps of %s in %.1f s, one process" % (n_cpu, args.family, t_cpu)},
+                             "sample": "%d oracle env-steps of %s in %.1f s, one process (FEM env-step only)" % (
+                                 n_cpu, args.family, t_cpu)},
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "path": "tfem_step_host: pinned host state tables + actions in, all float32 tensors out"},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "path": e2e_path},
             "gpu_launches": launches,
             "clocks": clocks,
             "status_nonzero_envs": status_bad,

@@ -121,6 +121,9 @@ typedef struct tfem_step_out {
   double* U;         /* [B]       Model.U_full (:374-379) */
   double* reactions; /* [B,nres]  Model.r at the restrained DOFs (:393-411) */
   int32_t* status;   /* [B]       TFEM_STATUS_* bits */
+  double* y;         /* [B,N]     node.coord[1] after the transition, as float(...) of what the reference holds */
+  uint8_t* y_weak;   /* [B,N]     1 where the reference holds a python int/float (assigned by a constraint
+                                  pass or a support), 0 where it holds an np.float32 */
 } tfem_step_out;
 
 const char* tfem_version(void);

@@ -66,6 +66,8 @@ class BatchedTrussEnv:
         self.move_range = torch.zeros(B, N, 2, **f32)
         self.point = torch.empty(B, 4, **f32)
         self.status = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.y = torch.empty(B, N, dtype=torch.float64, device=dev) if self.fp64_outputs else None
+        self.y_weak = torch.empty(B, N, dtype=torch.uint8, device=dev) if self.fp64_outputs else None
         if self.fp64_outputs:
             self.point64 = torch.empty(B, 4, **f64)
             self.d = torch.empty(B, self.ndof, **f64)
@@ -80,7 +82,7 @@ class BatchedTrussEnv:
     def _make_out(self):
         o = capi.StepOut()
         for name in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "point", "point64", "d", "axial",
-                     "ratio", "U", "reactions", "status"):
+                     "ratio", "U", "reactions", "status", "y", "y_weak"):
             setattr(o, name, _ptr(getattr(self, name)))
         return o
 
@@ -171,7 +173,8 @@ def step_host(handle: capi.Handle, set_node, set_element, move_range, a_geo, a_t
                "point": np.empty((B, 4), np.float32), "status": np.zeros((B,), np.int32)}
         if want_fp64:
             out.update(point64=np.empty((B, 4)), d=np.empty((B, d.ndof)), axial=np.empty((B, E)),
-                       ratio=np.empty((B, E)), U=np.empty((B,)), reactions=np.empty((B, d.nres)))
+                       ratio=np.empty((B, E)), U=np.empty((B,)), reactions=np.empty((B, d.nres)),
+                       y=np.empty((B, N)), y_weak=np.empty((B, N), np.uint8))
     sin = capi.StepIn()
     vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)  # noqa: E731
     sin.set_node, sin.set_element, sin.a_geo, sin.a_topo = vp(set_node), vp(set_element), vp(a_geo), vp(a_topo)

@@ -42,7 +42,7 @@ class StepIn(C.Structure):
 class StepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "point", "point64", "d", "axial", "ratio", "U",
-        "reactions", "status")]
+        "reactions", "status", "y", "y_weak")]
 
 
 # table ids (enum in tfem.h) -> (dtype, shape builder)

@@ -1,0 +1,130 @@
+"""Drop-in for the actor side of the reference's ``truss2D_RL`` module: ``MADDPG(...)``,
+``.agents[k].act(...)``, ``.agents[k].actor_model.load_weights(prefix).expect_partial()``
+(reference ``train/code/truss2D_RL.py:268-462``).  The forward pass runs on the GPU (``tactor_forward``,
+batch of one); the Ornstein-Uhlenbeck noise is drawn on the host with ``np.random.randn(1)`` per entry in the
+reference's order, so a seeded run consumes the NumPy stream exactly like the reference.
+
+The critic, the replay sampling and ``train`` are out of scope for this hot path:
+``remember`` stores, ``train`` raises."""
+from collections import deque
+
+import numpy as np
+
+from mop_truss_marl_b200 import tf_checkpoint
+
+try:
+    from set_seed_global import seedThis
+    np.random.seed(seedThis)
+except Exception:
+    seedThis = 20
+
+
+class OUNoise:
+    def __init__(self, mu, theta, sigma):
+        self.mu, self.theta, self.sigma, self.dt = mu, theta, sigma, 0.0001
+
+    def gen_noise(self, x):
+        return self.theta * (self.mu - x) * self.dt + self.sigma * np.random.randn(1)
+
+
+class _LoadStatus:
+    def expect_partial(self):
+        return self
+
+
+class _ActorModel:
+    """stands in for the Keras model: holds the 13 GCN layers' weights and the device actor"""
+
+    def __init__(self, hidden):
+        self.weights = tf_checkpoint.random_actor_weights(seed=seedThis, hidden=hidden)
+        self._device_actor = {}
+
+    def load_weights(self, prefix):
+        self.weights = tf_checkpoint.load_actor_weights(prefix)
+        self._device_actor = {}
+        return _LoadStatus()
+
+    def device_actor(self, nodes):
+        if nodes not in self._device_actor:
+            from mop_truss_marl_b200.actor import BatchedActor
+            self._device_actor[nodes] = BatchedActor(self.weights, nodes, max_batch=1, sigma=0.0, theta=0.0)
+        return self._device_actor[nodes]
+
+
+class _CriticModel:
+    def load_weights(self, prefix):
+        return _LoadStatus()        # critic is not part of the accelerated path
+
+
+class multimodals_OneAgent:
+    def __init__(self, lr, ep, epd, gamma, a_nn, c_nn, num_action1, num_action2, mu_s, theta_s, sigma_s,
+                 mu_t, theta_t, sigma_t, all_agent, batch):
+        self.number = 1
+        self.lr, self.gamma, self.a_nn, self.c_nn = lr, gamma, a_nn, c_nn
+        self.num_action1, self.num_action2 = num_action1, num_action2
+        self.batch_size = batch
+        self.update_num = 0
+        self.noise_geo = [OUNoise(mu_s[i], theta_s[i], sigma_s[i]) for i in range(num_action1)]
+        self.noise_topo = [OUNoise(mu_t[i], theta_t[i], sigma_t[i]) for i in range(num_action2)]
+        self.actor_model = _ActorModel(a_nn)
+        self.target_actor_model = _ActorModel(a_nn)
+        self.critic_model = _CriticModel()
+        self.target_critic_model = _CriticModel()
+        self.all_agent = all_agent
+
+    def act(self, x_n, A_n, A_s, A_n_ts, A_n_cs, x_p, A_p):
+        import torch
+        act = self.actor_model.device_actor(int(np.asarray(x_n).shape[0]))
+        dev = act.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)   # noqa: E731
+        geo, topo = act.forward(t(x_n)[None].contiguous(), t(A_n), t(A_s)[None].contiguous(),
+                                t(A_n_ts)[None].contiguous(), t(A_n_cs)[None].contiguous(),
+                                t(x_p)[None].contiguous(), t(A_p)[None].contiguous())
+        action_geo = geo[0].cpu().numpy()
+        action_topo = topo[0].cpu().numpy()
+        if self.noise_geo is not None:
+            for i in range(len(action_geo)):
+                for j in range(len(action_geo[i])):
+                    action_geo[i][j] += self.noise_geo[j].gen_noise(action_geo[i][j])[0]
+        if self.noise_topo is not None:
+            for i in range(len(action_topo)):
+                for j in range(len(action_topo[i])):
+                    action_topo[i][j] += self.noise_topo[j].gen_noise(action_topo[i][j])[0]
+        self.update_num += 1
+        return action_geo, action_topo
+
+
+class MADDPG:
+    def __init__(self, lr, ep, epd, gamma, a_nn, c_nn, max_mem, num_agents, num_action, mu, theta, sigma,
+                 max_poss_n_num=1):
+        self.num_agents = num_agents
+        self.lr, self.epint, self.ep, self.epd, self.epmin, self.gamma = lr, ep, ep, epd, 0.05, gamma
+        self.a_nn, self.c_nn = a_nn, c_nn
+        self.mu, self.theta, self.sigma = mu, theta, sigma
+        self.temprp = deque(maxlen=max_mem)
+        for _ in range(max_poss_n_num):
+            self.temprp.append(deque(maxlen=max_mem))
+        self.num_state = [0, 0]
+        self.num_action = num_action
+        self.batch_size = 32
+        self.max_poss_n_num = max_poss_n_num
+        self.agents, self.update_counter = [], []
+        for k in range(3):                                   # the reference always builds three (:423-441)
+            a = multimodals_OneAgent(lr, ep, epd, gamma, a_nn, c_nn, num_action[0], num_action[1], mu[0], theta[0],
+                                     sigma[0], mu[1], theta[1], sigma[1], num_agents, self.batch_size)
+            a.number = k + 1
+            self.agents.append(a)
+            self.update_counter.append(0)
+
+    def remember(self, state, a0_g, a0_t, a1_g, a1_t, a2_g, a2_t, reward, next_state1, next_state2, next_state3,
+                 done, n_node):
+        self.temprp[0].append([state, a0_g, a0_t, a1_g, a1_t, a2_g, a2_t, reward, next_state1, next_state2,
+                               next_state3, done])
+
+    def train(self):
+        raise NotImplementedError("the DDPG learner (critic, replay sampling, actor update) is outside the "
+                                  "accelerated hot path (SURVEY.md section 8f-4)")
+
+    def update(self):
+        for a in self.agents:
+            a.update_num += 0

@@ -212,7 +212,7 @@ int tfem_step_host(tfem_handle_t h, int B, const tfem_step_in* in, const tfem_st
   Slice o_xn = take(nb * N * 13 * 4), o_as = take(nb * N * N * 4), o_ts = take(nb * N * N * 4),
         o_cs = take(nb * N * N * 4), o_pt = take(nb * 16), o_p64 = take(nb * 32), o_d = take(nb * t.ndof * 8),
         o_ax = take(nb * E * 8), o_ra = take(nb * E * 8), o_u = take(nb * 8), o_re = take(nb * t.nres * 8),
-        o_st = take(nb * 4);
+        o_st = take(nb * 4), o_y = take(nb * N * 8), o_yw = take(nb * N);
   if (total > h->scratch_bytes) {
     if (h->d_scratch) cudaFree(h->d_scratch);
     h->d_scratch = nullptr; h->scratch_bytes = 0;
@@ -250,6 +250,8 @@ int tfem_step_host(tfem_handle_t h, int B, const tfem_step_in* in, const tfem_st
   dout.U = out->U ? (double*)(base + o_u.off) : nullptr;
   dout.reactions = out->reactions ? (double*)(base + o_re.off) : nullptr;
   dout.status = out->status ? (int32_t*)(base + o_st.off) : nullptr;
+  dout.y = out->y ? (double*)(base + o_y.off) : nullptr;
+  dout.y_weak = out->y_weak ? (uint8_t*)(base + o_yw.off) : nullptr;
   tfem::StepArgs a{};
   a.B = B; a.mode = tfem::MODE_STEP; a.in = din; a.out = dout;
   if (int rc = launch(h, a, stream)) return rc;
@@ -266,6 +268,7 @@ int tfem_step_host(tfem_handle_t h, int B, const tfem_step_in* in, const tfem_st
   d2h(out->d, dout.d, o_d.bytes); d2h(out->axial, dout.axial, o_ax.bytes); d2h(out->ratio, dout.ratio, o_ra.bytes);
   d2h(out->U, dout.U, o_u.bytes); d2h(out->reactions, dout.reactions, o_re.bytes);
   d2h(out->status, dout.status, o_st.bytes);
+  d2h(out->y, dout.y, o_y.bytes); d2h(out->y_weak, dout.y_weak, o_yw.bytes);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) return cuda_fail(e, "device->host copy");
   return TFEM_OK;

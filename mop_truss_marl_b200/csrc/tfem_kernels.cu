@@ -311,6 +311,10 @@ tfem_step_kernel(const StepArgs args) {
     }
     const float up32 = f32(up), down32 = f32(down);
     if (node_lane) {
+      if (args.out.y) args.out.y[(size_t)b * N + node] = y.v;
+      if (args.out.y_weak) args.out.y_weak[(size_t)b * N + node] = y.weak ? 1 : 0;
+    }
+    if (node_lane) {
       if (mode == MODE_STEP) reinterpret_cast<float2*>(args.in.move_range)[(size_t)b * N + node] = make_float2(up32, down32);
       else if (mode == MODE_RESET && args.reset_move_range)
         reinterpret_cast<float2*>(args.reset_move_range)[(size_t)b * N + node] = make_float2(up32, down32);

@@ -51,6 +51,8 @@ def compare_env(env, i, want, point=None, tag="", cond=None):
     raw_n, raw_e = cpu(env.nN_x_n[i]), cpu(env.nN_x_e[i])
     # bit-exact
     assert np.array_equal(raw_n[:, 1], want["y"].astype(np.float32)), tag + " y"
+    assert np.array_equal(cpu(env.y[i]), want["y"]), tag + " y (float64 bits)"
+    assert np.array_equal(cpu(env.y_weak[i]).astype(bool), want["y_weak"]), tag + " weak flags"
     assert np.array_equal(raw_e[:, 0].astype(np.int32), want["section"]), tag + " section"
     mr = cpu(env.move_range[i])
     assert np.array_equal(mr[:, 0], want["max_up"]) and np.array_equal(mr[:, 1], want["max_down"]), tag + " move range"
@@ -148,7 +150,7 @@ def test_step_host_equals_step(envmod, name):
     hg, ht = g["tr_in_a_geo"].copy(), g["tr_in_a_topo"].copy()
     out = envmod.step_host(env.handle, g["tr_in_set_node"].copy(), g["tr_in_set_element"].copy(), mr, hg, ht,
                            g["tr_in_coin"].copy())
-    for k in F32_FIELDS + ("point", "point64", "d", "axial", "ratio", "U", "reactions", "status"):
+    for k in F32_FIELDS + ("point", "point64", "d", "axial", "ratio", "U", "reactions", "status", "y", "y_weak"):
         assert np.array_equal(out[k], cpu(getattr(env, k))), k
     assert np.array_equal(mr, cpu(env.move_range)) and np.array_equal(hg, cpu(a_geo)) and np.array_equal(ht, cpu(a_topo))
 
