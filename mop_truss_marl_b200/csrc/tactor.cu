@@ -19,6 +19,8 @@
 
 #include "../../include/tactor.h"
 #include "../../include/tfem.h"
+#include "tactor_tc.cuh"
+#include <stdlib.h>
 
 namespace tactor {
 
@@ -279,6 +281,9 @@ struct tactor_handle_s {
   float* d_w[TACTOR_NLAYERS] = {};     // packed [Kpad, 208]
   float* d_b[TACTOR_NLAYERS] = {};     // [208]
   float* buf[5] = {};                  // activations [max_batch*nodes, 208]
+  float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
+  int* d_error = nullptr;              // set by a kernel whose mbarrier wait timed out
+  bool use_tc = false;
   std::atomic<int64_t> launches{0};
   uint64_t calls = 0;
 };
@@ -302,7 +307,12 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   const int smem = layer_smem_bytes<NODES>();
   float *x11 = h->buf[0], *x12 = h->buf[1], *x13 = h->buf[2], *x14b = h->buf[3], *S = h->buf[4];
   auto layer = [&](const float* X, int ldx, int K, int li, const float* adj, int batched, float* Y, int accum) {
-    gcn_layer_kernel<NODES><<<grid, NTHREADS, smem, st>>>(X, ldx, K, h->d_w[li], h->d_b[li], adj, batched, Y, accum, M);
+    if (h->use_tc && h->d_wimg[li] && ldx == LD) {
+      tc::gcn_layer_tc_kernel<NODES><<<(M + tc::TCM - 1) / tc::TCM, tc::THREADS, tc::smem_bytes(NODES), st>>>(
+          X, K, h->d_wimg[li], h->d_b[li], adj, batched, Y, accum, M, h->d_error);
+    } else {
+      gcn_layer_kernel<NODES><<<grid, NTHREADS, smem, st>>>(X, ldx, K, h->d_w[li], h->d_b[li], adj, batched, Y, accum, M);
+    }
     h->launches.fetch_add(1);
   };
   layer(in->x_n, 13, 13, 0, in->A_n, 0, x11, 0);
@@ -355,7 +365,40 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
     if (e == cudaSuccess) e = cudaMemcpy(h->d_w[l], wp.data(), wp.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_b[l], bp.data(), bp.size() * 4, cudaMemcpyHostToDevice);
   }
-  const size_t rows = ((size_t)max_batch * nodes + tactor::TM - 1) / tactor::TM * tactor::TM;
+  // tcgen05 operand images of the [200,200] layers: per 32-wide K chunk, [hi|lo][kb][n(208)][4 floats]
+  {
+    const char* impl = getenv("TACTOR_IMPL");
+    h->use_tc = !(impl && strcmp(impl, "ffma") == 0);
+  }
+  for (int l = 4; l <= 10 && e == cudaSuccess && h->use_tc; ++l) {
+    const int K = kIn[l], kout = kOut[l];
+    std::vector<float> img;
+    for (int c = 0; c * tactor::tc::KCH < K; ++c) {
+      const int kw = tactor::tc::chunk_kw(K, c), nkb = kw / 4;
+      for (int part = 0; part < 2; ++part)
+        for (int kb = 0; kb < nkb; ++kb)
+          for (int n = 0; n < tactor::tc::TCN; ++n)
+            for (int t = 0; t < 4; ++t) {
+              const int k = c * tactor::tc::KCH + 4 * kb + t;
+              float v = (n < kout && k < K) ? w->kernel[l][(size_t)k * kout + n] : 0.f;
+              uint32_t bits;
+              memcpy(&bits, &v, 4);
+              bits &= 0xFFFFE000u;
+              float hi;
+              memcpy(&hi, &bits, 4);
+              img.push_back(part == 0 ? hi : v - hi);
+            }
+    }
+    e = cudaMalloc(&h->d_wimg[l], img.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size() * 4, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4);
+  if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4);
+  if (e == cudaSuccess && h->use_tc) {
+    if (nodes == 16) e = cudaFuncSetAttribute(tactor::tc::gcn_layer_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::smem_bytes(16));
+    else e = cudaFuncSetAttribute(tactor::tc::gcn_layer_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::smem_bytes(32));
+  }
+  const size_t rows = ((size_t)max_batch * nodes + tactor::tc::TCM - 1) / tactor::tc::TCM * tactor::tc::TCM;
   for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaMalloc(&h->buf[i], rows * tactor::LD * 4);
   if (e == cudaSuccess) {
     if (nodes == 16) e = cudaFuncSetAttribute(tactor::gcn_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::layer_smem_bytes<16>());
@@ -371,6 +414,8 @@ int tactor_destroy(tactor_handle_t h) {
   Guard g(h->device);
   for (int l = 0; l < TACTOR_NLAYERS; ++l) { if (h->d_w[l]) cudaFree(h->d_w[l]); if (h->d_b[l]) cudaFree(h->d_b[l]); }
   for (int i = 0; i < 5; ++i) if (h->buf[i]) cudaFree(h->buf[i]);
+  for (int l = 0; l < TACTOR_NLAYERS; ++l) if (h->d_wimg[l]) cudaFree(h->d_wimg[l]);
+  if (h->d_error) cudaFree(h->d_error);
   delete h;
   return TFEM_OK;
 }
