@@ -176,7 +176,8 @@ constexpr int layer_smem_bytes() {
 template <int NODES>
 __global__ void __launch_bounds__(256)
 pareto_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
-              int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ X14b, int B) {
+              int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ X14b,
+              float* __restrict__ pooled_out, int B) {
   __shared__ float xs[50 * 4];
   __shared__ float as[50 * 50];
   __shared__ float pooled[HID];
@@ -201,6 +202,10 @@ pareto_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, cons
     pooled[tid] = sum;
   }
   __syncthreads();
+  if (pooled_out) {                                  // fused path: the scramble happens in the GEMM's operand generator
+    for (int i = tid; i < LD; i += blockDim.x) pooled_out[(size_t)b * LD + i] = (i < HID) ? pooled[i] : 0.f;
+    return;
+  }
   for (int i = tid; i < NODES * LD; i += blockDim.x) {
     const int n = i / LD, h = i % LD;
     X14b[((size_t)b * NODES + n) * LD + h] = (h < HID) ? pooled[(n * HID + h) / NODES] : 0.f;
@@ -306,6 +311,20 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   const int grid = (M + TM - 1) / TM;
   const int smem = layer_smem_bytes<NODES>();
   float *x11 = h->buf[0], *x12 = h->buf[1], *x13 = h->buf[2], *x14b = h->buf[3], *S = h->buf[4];
+  if (h->use_tc) {
+    // fused path: Pareto embedding, then ONE kernel for the whole network (tactor_tc.cuh)
+    float* pooled = h->buf[0];
+    pareto_kernel<NODES><<<B, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], nullptr, pooled, B);
+    tc::fused::Params p{};
+    p.x_n = in->x_n; p.A_n = in->A_n; p.A_s = in->A_s; p.A_ts = in->A_n_ts; p.A_cs = in->A_n_cs; p.pooled = pooled;
+    for (int k = 0; k < 3; ++k) { p.w1[k] = h->d_w[k]; p.b1[k] = h->d_b[k]; }
+    for (int g2 = 0; g2 < tc::fused::NGEMM; ++g2) { p.wimg[g2] = h->d_wimg[4 + g2]; p.bias[g2] = h->d_b[4 + g2]; }
+    p.w_head[0] = h->d_w[11]; p.w_head[1] = h->d_w[12]; p.b_head[0] = h->d_b[11]; p.b_head[1] = h->d_b[12];
+    p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error;
+    tc::fused::actor_fused_kernel<NODES><<<(M + tc::TCM - 1) / tc::TCM, tc::fused::FTHREADS, tc::fused::fused_smem_bytes<NODES>(), st>>>(p);
+    h->launches.fetch_add(2);
+    return cudaGetLastError();
+  }
   auto layer = [&](const float* X, int ldx, int K, int li, const float* adj, int batched, float* Y, int accum) {
     if (h->use_tc && h->d_wimg[li] && ldx == LD) {
       tc::gcn_layer_tc_kernel<NODES><<<(M + tc::TCM - 1) / tc::TCM, tc::THREADS, tc::smem_bytes(NODES), st>>>(
@@ -318,7 +337,7 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   layer(in->x_n, 13, 13, 0, in->A_n, 0, x11, 0);
   layer(in->x_n, 13, 13, 1, in->A_n, 0, x12, 0);
   layer(in->x_n, 13, 13, 2, in->A_n, 0, x13, 0);
-  pareto_kernel<NODES><<<B, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], x14b, B);
+  pareto_kernel<NODES><<<B, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], x14b, nullptr, B);
   h->launches.fetch_add(1);
   layer(x11, LD, HID, 4, in->A_n, 0, S, 0);          // x_2_1
   layer(x12, LD, HID, 5, in->A_n_ts, 1, S, 1);       // x_2_2
@@ -395,8 +414,8 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4);
   if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4);
   if (e == cudaSuccess && h->use_tc) {
-    if (nodes == 16) e = cudaFuncSetAttribute(tactor::tc::gcn_layer_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::smem_bytes(16));
-    else e = cudaFuncSetAttribute(tactor::tc::gcn_layer_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::smem_bytes(32));
+    if (nodes == 16) e = cudaFuncSetAttribute(tactor::tc::fused::actor_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::fused::fused_smem_bytes<16>());
+    else e = cudaFuncSetAttribute(tactor::tc::fused::actor_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::fused::fused_smem_bytes<32>());
   }
   const size_t rows = ((size_t)max_batch * nodes + tactor::tc::TCM - 1) / tactor::tc::TCM * tactor::tc::TCM;
   for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaMalloc(&h->buf[i], rows * tactor::LD * 4);

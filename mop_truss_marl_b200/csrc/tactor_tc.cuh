@@ -19,7 +19,7 @@ namespace tc {
 
 constexpr int TCM = 128;             // rows per CTA
 constexpr int TCN = 208;             // padded output columns (UMMA N, multiple of 16)
-constexpr int KCH = 32;              // K elements per chunk (4 MMA k-steps of 8)
+constexpr int KCH = 16;              // K elements per chunk (2 MMA k-steps of 8)
 constexpr int NKB = KCH / 4;         // 16-byte core-matrix columns per chunk
 constexpr int A_LBO = TCM * 16;      // bytes between core matrices adjacent in K (A operand)
 constexpr int B_LBO = TCN * 16;      // same for the B operand
@@ -31,8 +31,10 @@ constexpr int THREADS = 256;
 constexpr int TMEM_COLS = 256;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
+constexpr int STAGES = 2;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // Ahi, Alo, Bhi, Blo of one K chunk
 __host__ __device__ constexpr int smem_bytes(int nodes) {
-  return 2 * A_BYTES + 2 * B_BYTES + (TCM / nodes) * nodes * nodes * 4 + 64;
+  return STAGES * STAGE_BYTES + (TCM / nodes) * nodes * nodes * 4 + 64;
 }
 // W operand image in global memory: per chunk, [hi: kb][n][4 floats] then [lo: ...]
 __host__ __device__ constexpr int chunk_kw(int K, int c) { return (K - c * KCH) < KCH ? (K - c * KCH) : KCH; }
@@ -95,17 +97,15 @@ gcn_layer_tc_kernel(const float* __restrict__ X, int K, const float* __restrict_
   constexpr int ENVS = TCM / NODES;
   constexpr int LDX = 208;
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* Ahi = smem;
-  unsigned char* Alo = Ahi + A_BYTES;
-  unsigned char* Bimg = Alo + A_BYTES;                       // hi then lo, as laid out in global memory
-  float* Ad = reinterpret_cast<float*>(Bimg + 2 * B_BYTES);  // [ENVS][NODES(j)][NODES(i)]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ad + ENVS * NODES * NODES);   // [0] bulk copy, [1] MMA done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  float* Ts = reinterpret_cast<float*>(smem);                // epilogue tile [64][LDT], aliases the operands
+  // stage s: [Ahi | Alo | Bhi,Blo (as laid out in global memory)]
+  float* Ad = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);         // [ENVS][NODES(j)][NODES(i)]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ad + ENVS * NODES * NODES);   // [0,1] W chunk landed, [2,3] MMAs of a stage done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* Ts = reinterpret_cast<float*>(smem);                // epilogue tile [64][LDT], aliases the stages
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TCM;
-  const uint32_t bar_b = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1]);
+  const uint32_t bar_b0 = smem_u32(&bars[0]), bar_m0 = smem_u32(&bars[2]);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -114,8 +114,7 @@ gcn_layer_tc_kernel(const float* __restrict__ X, int K, const float* __restrict_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    mbar_init(bar_b, 1);
-    mbar_init(bar_m, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int idx = tid; idx < ENVS * NODES * NODES; idx += THREADS) {
@@ -125,42 +124,72 @@ gcn_layer_tc_kernel(const float* __restrict__ X, int K, const float* __restrict_
     if (env * NODES < M) v = adj_batched ? adj[(size_t)env * NODES * NODES + r] : adj[r];
     Ad[(e * NODES + j) * NODES + i] = v;
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
 
   const int nchunks = (K + KCH - 1) / KCH;
-  const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(Wimg);
-  uint32_t phase = 0;
+  // ---- X chunk loader: 128 rows x 4 core columns = 512 float4, two per thread, lanes along rows ----------
+  const int lr = tid % TCM, lkb = tid / TCM;                 // (row, core column) and (row, core column + 2)
+  auto load_x = [&](int c, float4 (&v)[2]) {
+    const int nkb = chunk_kw(K, c) / 4;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int kb = lkb + 2 * q;
+      v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kb < nkb && row0 + lr < M)
+        v[q] = *reinterpret_cast<const float4*>(X + (size_t)(row0 + lr) * LDX + c * KCH + 4 * kb);
+    }
+  };
+  auto store_x = [&](int c, const float4 (&v)[2]) {
+    unsigned char* Ahi = smem + (c & 1) * STAGE_BYTES;
+    unsigned char* Alo = Ahi + A_BYTES;
+    const int nkb = chunk_kw(K, c) / 4;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int kb = lkb + 2 * q;
+      if (kb >= nkb) continue;
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(v[q].x) & 0xFFFFE000u); l.x = v[q].x - h.x;
+      h.y = __uint_as_float(__float_as_uint(v[q].y) & 0xFFFFE000u); l.y = v[q].y - h.y;
+      h.z = __uint_as_float(__float_as_uint(v[q].z) & 0xFFFFE000u); l.z = v[q].z - h.z;
+      h.w = __uint_as_float(__float_as_uint(v[q].w) & 0xFFFFE000u); l.w = v[q].w - h.w;
+      *reinterpret_cast<float4*>(Ahi + kb * A_LBO + lr * 16) = h;
+      *reinterpret_cast<float4*>(Alo + kb * A_LBO + lr * 16) = l;
+    }
+  };
+  // W image offsets: chunk c starts at 2 * B_LBO * (number of core columns before it)
+  auto w_chunk = [&](int c, uint32_t& bytes) -> const unsigned char* {
+    bytes = 2u * (chunk_kw(K, c) / 4) * B_LBO;
+    return reinterpret_cast<const unsigned char*>(Wimg) + (size_t)c * (2u * NKB * B_LBO);
+  };
+  auto issue_w = [&](int c) {                                // one elected thread
+    uint32_t bytes;
+    const unsigned char* src = w_chunk(c, bytes);
+    const uint32_t bar = bar_b0 + 8 * (c & 1);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(smem + (c & 1) * STAGE_BYTES + 2 * A_BYTES), src, bytes, bar);
+  };
+
+  float4 xa[2], xb[2];                                       // chunks c+1 and c+2 in flight
+  load_x(0, xa);
+  if (nchunks > 1) load_x(1, xb);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();                                           // barriers initialised, TMEM allocated
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) issue_w(0);
+  store_x(0, xa);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
   bool ok = true;
   for (int c = 0; c < nchunks; ++c) {
-    const int kw = chunk_kw(K, c), nkb = kw / 4;
-    const uint32_t bbytes = 2u * nkb * B_LBO;
-    if (tid == 0) {                                          // W chunk: one bulk copy (hi + lo)
-      mbar_expect_tx(bar_b, bbytes);
-      bulk_g2s(smem_u32(Bimg), wsrc, bbytes, bar_b);
-    }
-    wsrc += bbytes;
-    // X chunk: lanes run along rows (conflict-free 16-byte shared stores), split into hi / lo
-    for (int idx = tid; idx < TCM * nkb; idx += THREADS) {
-      const int r = idx % TCM, kb = idx / TCM;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < M) v = *reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * LDX + c * KCH + 4 * kb);
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-      *reinterpret_cast<float4*>(Ahi + kb * A_LBO + r * 16) = h;
-      *reinterpret_cast<float4*>(Alo + kb * A_LBO + r * 16) = l;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (MMA)
-    __syncthreads();
-    if (tid == 0) {
-      ok = mbar_wait(bar_b, phase) && ok;
+    const int s = c & 1;
+    const uint32_t use_parity = (uint32_t)((c >> 1) & 1);    // parity of this use of stage s
+    if (tid == 0) {                                          // MMAs of chunk c (asynchronous)
+      ok = mbar_wait(bar_b0 + 8 * s, use_parity) && ok;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(Ahi), a_lo = smem_u32(Alo), b_hi = smem_u32(Bimg), b_lo = b_hi + nkb * B_LBO;
+      const int kw = chunk_kw(K, c), nkb = kw / 4;
+      const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+      const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + nkb * B_LBO;
       for (int ks = 0; ks < kw / 8; ++ks) {
         const uint32_t ao = 2 * ks * A_LBO, bo = 2 * ks * B_LBO;
         const uint64_t dah = make_desc(a_hi + ao, A_LBO), dal = make_desc(a_lo + ao, A_LBO);
@@ -169,11 +198,21 @@ gcn_layer_tc_kernel(const float* __restrict__ X, int K, const float* __restrict_
         mma_tf32(tmem_base, dah, dbl, 1);
         mma_tf32(tmem_base, dal, dbh, 1);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m0 + 8 * s)
+                   : "memory");
     }
-    ok = mbar_wait(bar_m, phase) && ok;                      // operands consumed, accumulator updated
-    phase ^= 1;
+    if (c + 1 < nchunks) {
+      // stage s^1 was last used by chunk c-1: wait for its MMAs before overwriting it
+      if (c >= 1) ok = mbar_wait(bar_m0 + 8 * (s ^ 1), (uint32_t)(((c - 1) >> 1) & 1)) && ok;
+      if (tid == 0) issue_w(c + 1);
+      if (c & 1) store_x(c + 1, xa); else store_x(c + 1, xb);
+      if (c + 2 < nchunks) { if (c & 1) load_x(c + 2, xb); else load_x(c + 2, xa); }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
   }
+  // both stages' last MMAs (the commit of the final chunk covers every earlier MMA)
+  ok = mbar_wait(bar_m0 + 8 * ((nchunks - 1) & 1), (uint32_t)(((nchunks - 1) >> 1) & 1)) && ok;
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!ok && error_flag) atomicExch(error_flag, 1);
 
@@ -246,6 +285,314 @@ gcn_layer_tc_kernel(const float* __restrict__ X, int K, const float* __restrict_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
+
+// =========================================================================================================
+// Whole-network fusion: one CTA carries a 128-row tile (ENVS environments) through all 13 GCN layers.
+// Activations never leave the SM:
+//   Z   = A_n . x_n                                   [128,13]   shared memory (registers per loader thread)
+//   A operand of GEMM g, generated chunk by chunk by the loader threads:
+//     g=0  x11 = relu(Z W11 + b11)      g=1,2  x12 = relu(Z W12 + b12)      g=3  x13 = relu(Z W13 + b13)
+//     g=4  x14b[r][k] = pooled[env][(n*200+k)/N]       g=5,6  H (the five-way sum, shared memory)
+//   D (TMEM) = A . W_g  by tcgen05.mma kind::tf32 with the 3xTF32 split
+//   epilogue g: T = D -> shared; V = relu(Adj_g . T + b_g);  g<=4: H (+)= V;  g=5: geo head;  g=6: topo head
+// HBM traffic per environment: x_n, three [N,N] adjacencies, pooled row in; 5N floats out.
+namespace fused {
+
+constexpr int FTHREADS = 256;                              // 8 warps: 256 loaders, 208 epilogue patches of 16 x 4
+constexpr int LDH = 212;                                   // padded row length of the H tile
+constexpr int NGEMM = 7;
+constexpr int KH = 200;
+
+struct Params {
+  const float* x_n;       // [B,N,13]
+  const float* A_n;       // [N,N]
+  const float* A_s;       // [B,N,N]
+  const float* A_ts;      // [B,N,N]
+  const float* A_cs;      // [B,N,N]
+  const float* pooled;    // [B,208]
+  const float* w1[3];     // layer-1 kernels packed [16,208]
+  const float* b1[3];     // [208]
+  const float* wimg[NGEMM];
+  const float* bias[NGEMM];
+  const float* w_head[2]; // packed [208,208], first 2 / 3 columns used
+  const float* b_head[2];
+  float* geo;             // [B,N,2]
+  float* topo;            // [B,N,3]
+  int M;                  // B*N
+  int* error_flag;
+};
+
+template <int NODES>
+__host__ __device__ constexpr int fused_smem_bytes() {
+  return STAGES * STAGE_BYTES + TCM * LDH * 4 + (TCM / NODES) * NODES * NODES * 4 + NODES * NODES * 4 +
+         13 * 208 * 4 + (TCM / NODES) * 208 * 4 + 64 * 4 * 4 + 128;
+}
+
+template <int NODES>
+__global__ void __launch_bounds__(FTHREADS, 1)
+actor_fused_kernel(const Params P) {
+  constexpr int ENVS = TCM / NODES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* H = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [128][LDH]
+  float* Ad = H + TCM * LDH;                                                 // [ENVS][N(j)][N(i)] adjacency of the current GEMM
+  float* An = Ad + ENVS * NODES * NODES;                                     // [N(j)][N(i)] shared A_n, transposed
+  float* W1s = An + NODES * NODES;                                           // [13][208] layer-1 kernel of the current GEMM
+  float* Pl = W1s + 13 * 208;                                                // [ENVS][208] pooled Pareto embedding
+  float* Zs = reinterpret_cast<float*>(smem);                                // [128][16], only until the first stage fill
+  float* Us = Pl + ENVS * 208;                                               // [64][4] head pre-activations
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Us + 64 * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* Ts = reinterpret_cast<float*>(smem);                                // [64][LDT], aliases the stages
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * TCM;
+  const int env0 = row0 / NODES;
+  const int M = P.M;
+  const uint32_t bar_b0 = smem_u32(&bars[0]), bar_m0 = smem_u32(&bars[2]);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // shared A_n (transposed), pooled rows, raw x_n rows (staged in H, which is free until the first epilogue)
+  for (int idx = tid; idx < NODES * NODES; idx += FTHREADS) An[(idx % NODES) * NODES + idx / NODES] = P.A_n[idx];
+  for (int idx = tid; idx < ENVS * 208; idx += FTHREADS) {
+    const int env = env0 + idx / 208;
+    Pl[idx] = (env * NODES < M) ? P.pooled[(size_t)env * 208 + idx % 208] : 0.f;
+  }
+  float* Xraw = H;                                                           // [128][13]
+  for (int idx = tid; idx < TCM * 13; idx += FTHREADS)
+    Xraw[idx] = (row0 + idx / 13 < M) ? P.x_n[(size_t)row0 * 13 + idx] : 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  // Z = A_n . x_n  (gcn_l1_k share the input and the adjacency, so the product is formed once)
+  for (int idx = tid; idx < TCM * 16; idx += FTHREADS) {
+    const int r = idx / 16, i = idx % 16, e = r / NODES, n = r % NODES;
+    float z = 0.f;
+    if (i < 13)
+      for (int j = 0; j < NODES; ++j) z = fmaf(An[j * NODES + n], Xraw[(e * NODES + j) * 13 + i], z);
+    Zs[idx] = z;
+  }
+  __syncthreads();
+  const int lr = tid % TCM, lkb = tid / TCM;                 // loader role: row lr, core columns lkb and lkb + 2
+  float zr[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) zr[i] = Zs[lr * 16 + i];
+  const int l_env = lr / NODES, l_n = lr % NODES;
+
+  // ---- A operand generator: 4 consecutive k of row lr for GEMM g -------------------------------------------
+  auto gen_a = [&](int g, int k) -> float4 {
+    if (g <= 3) {
+      const int l1 = (g == 0) ? 0 : (g == 3 ? 2 : 1);
+      const float* w = W1s + k;
+      float4 acc = __ldg(reinterpret_cast<const float4*>(P.b1[l1] + k));
+#pragma unroll
+      for (int i = 0; i < 13; ++i) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + i * 208);
+        acc.x = fmaf(zr[i], wv.x, acc.x); acc.y = fmaf(zr[i], wv.y, acc.y);
+        acc.z = fmaf(zr[i], wv.z, acc.z); acc.w = fmaf(zr[i], wv.w, acc.w);
+      }
+      return make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+    } else if (g == 4) {
+      const float* pl = Pl + l_env * 208;
+      const int f = l_n * KH + k;
+      return make_float4(pl[f / NODES], pl[(f + 1) / NODES], pl[(f + 2) / NODES], pl[(f + 3) / NODES]);
+    }
+    return *reinterpret_cast<const float4*>(H + lr * LDH + k);
+  };
+  auto split_store = [&](int stage, int kb, const float4& v) {
+    unsigned char* Ahi = smem + stage * STAGE_BYTES;
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(Ahi + kb * A_LBO + lr * 16) = h;
+    *reinterpret_cast<float4*>(Ahi + A_BYTES + kb * A_LBO + lr * 16) = l;
+  };
+  auto fill_stage = [&](int g, int c, int stage) {
+    const int nkb = chunk_kw(KH, c) / 4;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int kb = lkb + 2 * q;
+      if (kb < nkb) split_store(stage, kb, gen_a(g, c * KCH + 4 * kb));
+    }
+  };
+  auto issue_w = [&](int g, int c, int stage) {
+    const uint32_t bytes = 2u * (chunk_kw(KH, c) / 4) * B_LBO;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg[g]) + (size_t)c * (2u * NKB * B_LBO);
+    const uint32_t bar = bar_b0 + 8 * stage;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES), src, bytes, bar);
+  };
+
+  constexpr int NCH = (KH + KCH - 1) / KCH;                  // 13 chunks per GEMM
+  uint32_t use = 0;                                          // running count of stage uses (both barriers flip per use)
+  bool ok = true;
+  const int cq = tid % 52, gq = tid / 52;                    // epilogue role (tid < 208): rows 16*gq.., columns 4*cq..
+
+  for (int g = 0; g < NGEMM; ++g) {
+    // adjacency of this GEMM (transposed per environment): A_n for g = 0, 4, 5; A_ts, A_cs, A_s otherwise
+    {
+      const float* adj = (g == 1) ? P.A_ts : (g == 2) ? P.A_cs : (g == 3 || g == 6) ? P.A_s : nullptr;
+      for (int idx = tid; idx < ENVS * NODES * NODES; idx += FTHREADS) {
+        const int e = idx / (NODES * NODES), r = idx % (NODES * NODES), i = r / NODES, j = r % NODES;
+        float v = 0.f;
+        if (adj == nullptr) v = An[j * NODES + i];
+        else if ((env0 + e) * NODES < M) v = adj[(size_t)(env0 + e) * NODES * NODES + r];
+        Ad[(e * NODES + j) * NODES + i] = v;
+      }
+      if (g == 0 || g == 1 || g == 3) {                      // g = 2 reuses gcn_l1_2's kernel
+        const float* w1 = P.w1[g == 0 ? 0 : (g == 3 ? 2 : 1)];
+        for (int idx = tid; idx < 13 * 208 / 4; idx += FTHREADS)
+          reinterpret_cast<float4*>(W1s)[idx] = __ldg(reinterpret_cast<const float4*>(w1) + idx);
+      }
+      __syncthreads();
+    }
+    // ---- main loop: chunk c in stage (use & 1) ----
+    if (tid == 0) issue_w(g, 0, use & 1);
+    fill_stage(g, 0, use & 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    for (int c = 0; c < NCH; ++c, ++use) {
+      const int s = use & 1;
+      const uint32_t parity = (use >> 1) & 1;
+      if (tid == 0) {
+        ok = mbar_wait(bar_b0 + 8 * s, parity) && ok;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int kw = chunk_kw(KH, c), nkb = kw / 4;
+        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + nkb * B_LBO;
+        for (int ks = 0; ks < kw / 8; ++ks) {
+          const uint32_t ao = 2 * ks * A_LBO, bo = 2 * ks * B_LBO;
+          const uint64_t dah = make_desc(a_hi + ao, A_LBO), dal = make_desc(a_lo + ao, A_LBO);
+          const uint64_t dbh = make_desc(b_hi + bo, B_LBO), dbl = make_desc(b_lo + bo, B_LBO);
+          mma_tf32(tmem_base, dah, dbh, (c | ks) != 0);
+          mma_tf32(tmem_base, dah, dbl, 1);
+          mma_tf32(tmem_base, dal, dbh, 1);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m0 + 8 * s)
+                     : "memory");
+      }
+      if (c + 1 < NCH) {
+        // the other stage was used by the previous chunk (use-1): its MMAs must be done before refilling it
+        if (c >= 1) ok = mbar_wait(bar_m0 + 8 * (s ^ 1), ((use - 1) >> 1) & 1) && ok;
+        if (tid == 0) issue_w(g, c + 1, s ^ 1);
+        fill_stage(g, c + 1, s ^ 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+      }
+    }
+    // all MMAs of this GEMM (the last commit covers every earlier one); also drains the second-to-last stage
+    ok = mbar_wait(bar_m0 + 8 * ((use - 1) & 1), ((use - 1) >> 1) & 1) && ok;
+    if (NCH >= 2) ok = mbar_wait(bar_m0 + 8 * ((use - 2) & 1), ((use - 2) >> 1) & 1) && ok;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue ----
+    float4 bs0 = make_float4(0, 0, 0, 0);
+    if (tid < 208) bs0 = __ldg(reinterpret_cast<const float4*>(P.bias[g] + 4 * cq));
+    const float bb[4] = {bs0.x, bs0.y, bs0.z, bs0.w};
+    for (int p = 0; p < 2; ++p) {
+      __syncthreads();                                       // Ts / Us free
+      const int q = warp & 3;
+      if ((q >> 1) == p) {
+        const int rl = (q & 1) * 32 + lane;
+        const int cbase = (warp >> 2) * 104;
+        for (int cc = 0; cc < 104; cc += 8) {
+          float v[8];
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cbase + cc), v);
+          float4* dst = reinterpret_cast<float4*>(Ts + rl * LDT + cbase + cc);
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+      __syncthreads();
+      // each thread owns 16 rows (one environment, or half of a 32-node one) x 4 columns: every T row is
+      // read once per 16 output rows and the adjacency values are warp broadcasts
+      float acc[16][4];
+      const int rt = 64 * p + 16 * gq;                       // first row of the patch inside the 128-row tile
+      if (tid < 208) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int cidx = 0; cidx < 4; ++cidx) acc[i][cidx] = 0.f;
+        const int e = rt / NODES, ri = rt % NODES;
+        const int tbase = e * NODES - 64 * p;
+#pragma unroll 2
+        for (int j = 0; j < NODES; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(Ts + (tbase + j) * LDT + 4 * cq);
+          const float4* ap = reinterpret_cast<const float4*>(Ad + (e * NODES + j) * NODES + ri);
+          const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];
+          const float a[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            acc[i][0] = fmaf(a[i], t.x, acc[i][0]); acc[i][1] = fmaf(a[i], t.y, acc[i][1]);
+            acc[i][2] = fmaf(a[i], t.z, acc[i][2]); acc[i][3] = fmaf(a[i], t.w, acc[i][3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int cidx = 0; cidx < 4; ++cidx) acc[i][cidx] = fmaxf(acc[i][cidx] + bb[cidx], 0.f);
+      }
+      if (g <= 4) {
+        if (tid < 208) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float4* dst = reinterpret_cast<float4*>(H + (rt + i) * LDH + 4 * cq);
+            float4 o0 = make_float4(0, 0, 0, 0);
+            if (g > 0) o0 = dst[0];
+            dst[0] = make_float4(acc[i][0] + o0.x, acc[i][1] + o0.y, acc[i][2] + o0.z, acc[i][3] + o0.w);
+          }
+        }
+      } else {
+        // output heads (truss2D_RL.py:121-125): sigmoid(A_n (x3 W4) + b4); x3 goes back through Ts
+        const int hd = g - 5, nout = 2 + hd;
+        __syncthreads();                                     // every thread is done reading T
+        if (tid < 208) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            *reinterpret_cast<float4*>(Ts + (16 * gq + i) * LDT + 4 * cq) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+        if (tid < 64 * nout) {
+          const int r = tid / nout, o = tid % nout;
+          const float* w = P.w_head[hd] + o;
+          float u = 0.f;
+          for (int k = 0; k < KH; ++k) u = fmaf(Ts[r * LDT + k], __ldg(w + (size_t)k * 208), u);
+          Us[r * 4 + o] = u;
+        }
+        __syncthreads();
+        if (tid < 64 * nout) {
+          const int r = tid / nout, o = tid % nout;
+          const int e = r / NODES, n = r % NODES;
+          float v = 0.f;
+          for (int j = 0; j < NODES; ++j) v = fmaf(An[j * NODES + n], Us[(e * NODES + j) * 4 + o], v);
+          v += P.b_head[hd][o];
+          const int row = row0 + 64 * p + r;
+          if (row < M) (hd == 0 ? P.geo : P.topo)[(size_t)row * nout + o] = 1.f / (1.f + expf(-v));
+        }
+      }
+    }
+    __syncthreads();                                         // H / Ts settled before the next GEMM refills the stages
+  }
+  if (!ok && P.error_flag) atomicExch(P.error_flag, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace fused
 
 }  // namespace tc
 }  // namespace tactor
