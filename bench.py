@@ -92,30 +92,41 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------------------
-def oracle_steps_per_sec(family, seconds, seed=0):
-    """the CPU port driven like the GPU batch (i.i.d. uniform actions, own state fed back); returns
-    (steps, elapsed)"""
+def oracle_steps_per_sec(family, seconds, seed=0, with_actor=False):
+    """the CPU port driven like the GPU batch (own state fed back; actions from the numpy actor restatement
+    with random-init weights + OU noise, or i.i.d. uniform when with_actor is False); returns (steps, elapsed)"""
     from oracle.truss_oracle import TrussOracle
     o = TrussOracle(family)
     rng = np.random.RandomState(seed)
     N = o.mesh.N
     st = o.reset()
+    if with_actor:
+        from oracle import actor_oracle
+        from mop_truss_marl_b200.tf_checkpoint import random_actor_weights
+        w = random_actor_weights(seed=20)
+        x_p = np.array([[1, 1, 1, 1 / 50]], dtype=np.float32)
+        A_p = np.ones((1, 1), dtype=np.float32)
+
+    def actions():
+        if not with_actor:
+            return rng.rand(N, 2).astype(np.float32), rng.rand(N, 3).astype(np.float32)
+        return actor_oracle.act(w, (st["x_n"], o.A_n, st["A_s"], st["A_n_ts"], st["A_n_cs"], x_p, A_p), rng=rng)
     for _ in range(3):
-        st = o.step(st["nN_x_n"], st["nN_x_e"], st["max_up"], st["max_down"], rng.rand(N, 2).astype(np.float32),
-                    rng.rand(N, 3).astype(np.float32), rng.rand() >= 0.5)
+        a_geo, a_topo = actions()
+        st = o.step(st["nN_x_n"], st["nN_x_e"], st["max_up"], st["max_down"], a_geo, a_topo, rng.rand() >= 0.5)
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
-        st = o.step(st["nN_x_n"], st["nN_x_e"], st["max_up"], st["max_down"], rng.rand(N, 2).astype(np.float32),
-                    rng.rand(N, 3).astype(np.float32), rng.rand() >= 0.5)
+        a_geo, a_topo = actions()
+        st = o.step(st["nN_x_n"], st["nN_x_e"], st["max_up"], st["max_down"], a_geo, a_topo, rng.rand() >= 0.5)
         n += 1
     return n, time.perf_counter() - t0
 
 
 def _oracle_worker(args):
-    family, seconds, seed = args
+    family, seconds, seed, with_actor = args
     import warnings
     warnings.filterwarnings("ignore")
-    return oracle_steps_per_sec(family, seconds, seed)
+    return oracle_steps_per_sec(family, seconds, seed, with_actor)
 
 
 def run_reference_arm(args, rank, world):
@@ -125,12 +136,13 @@ def run_reference_arm(args, rank, world):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_step_seconds = max(2.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    per_step_seconds = max(0.25, min(10.0, 120.0 / max(1, args.steps + args.warmup)))   # whole run ~2 minutes
+    with_actor = not args.no_actor
     ctx = mp.get_context("fork")
     rates = []
     with ctx.Pool(cores) as pool:
         for it in range(args.warmup + args.steps):
-            res = pool.map(_oracle_worker, [(args.family, per_step_seconds, 1000 * it + c) for c in range(cores)])
+            res = pool.map(_oracle_worker, [(args.family, per_step_seconds, 1000 * it + c, with_actor) for c in range(cores)])
             total = sum(n for n, _ in res)
             elapsed = max(t for _, t in res)
             if it >= args.warmup:
@@ -139,11 +151,13 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_seconds * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (FEM) + f32 (actor)" if with_actor else "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "family": args.family, "envs_per_gpu": args.batch},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d processes x %.1f s of oracle env-steps per bench step (one env each, uniform "
-                                   "actions, own state fed back)" % (cores, per_step_seconds)},
+                         "sample": "%d processes x %.2f s of oracle env-steps per bench step (one env each, %s, own "
+                                   "state fed back)" % (cores, per_step_seconds,
+                                                        "numpy actor + OU noise" if with_actor else "uniform actions")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -151,7 +165,7 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_name(args):
-    if getattr(args, "no_actor", False) or args.impl == "reference":
+    if getattr(args, "no_actor", False):
         return "%s B=%d per GPU: batched FEM env-step (_game_modify equivalent), uniform random actions" % (
             args.family, args.batch)
     return "%s B=%d per GPU: actor forward (act, OU noise) + batched FEM env-step (_game_modify equivalent)" % (
@@ -365,20 +379,22 @@ def main():
         stages = {"actor_ms": actor_ms, "fem_ms": fem_ms,
                   "fem_only_env_steps_per_s": B * world / (fem_ms * 1e-3)}
         if use_actor and actor_ms > fem_ms:
-            # dominant stage = the 10 gcn_layer_kernel launches (float32 FFMA GEMM + fused adjacency product);
-            # measured against the tensor roof the spec names (bf16 cuBLAS), which an FP32 CUDA-core kernel
-            # cannot approach -- see DESIGN.md "actor" for the tcgen05 plan
+            # dominant stage = actor_fused_kernel (tcgen05 kind::tf32 with the 3xTF32 split = float32-equivalent
+            # accuracy, three MMAs per product).  achieved counts ALGORITHMIC flops (one multiply-add per
+            # product) against the measured bf16 cuBLAS roof; tf32 peak is half of bf16 and the split costs 3x,
+            # so 1/6 of that roof is the ceiling of this formulation.
             tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             aflops = actor_flops(N) * B
             ach = aflops / (actor_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                        "traffic": None, "kernel": "gcn_layer_kernel (10 of the 15 actor launches per step)",
+                        "traffic": None, "kernel": "actor_fused_kernel (1 of the 4 actor launches per step)",
                         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback",
                         "algorithmic_flops_per_env": actor_flops(N), "kernel_ms": actor_ms,
-                        "note": "float32 FFMA kernel (reference dtype) reported against the bf16 tensor roof"}
+                        "note": "tcgen05 kind::tf32, 3xTF32 split (float32-equivalent); algorithmic flops vs the bf16 "
+                                "tensor roof (formulation ceiling = roof/6)"}
         else:
             roofline = roof_fem
-        n_cpu, t_cpu = oracle_steps_per_sec(args.family, args.cpu_seconds)
+        n_cpu, t_cpu = oracle_steps_per_sec(args.family, args.cpu_seconds, with_actor=use_actor)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -393,8 +409,8 @@ def main():
             "roofline_fem": roof_fem,
             "stages": stages,
             "cpu_baseline": {"value": n_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "%d oracle env-steps of %s in %.1f s, one process (FEM env-step only)" % (
-                                 n_cpu, args.family, t_cpu)},
+                             "sample": "%d oracle steps (%s) of %s in %.1f s, one process" % (
+                                 n_cpu, "numpy actor + env-step" if use_actor else "env-step", args.family, t_cpu)},
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "path": e2e_path},
             "gpu_launches": launches,

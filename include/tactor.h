@@ -61,6 +61,10 @@ int tactor_act(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, fl
 
 int64_t tactor_launch_count(tactor_handle_t h);
 
+/* Synchronises the device and returns 0, or TFEM_ERR_CUDA if a kernel of this handle reported a
+ * timed-out mbarrier wait (the waits are bounded so that a programming error cannot hang the GPU). */
+int tactor_status(tactor_handle_t h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ class _Inputs(C.Structure):
 
 
 ACTOR_EXPORTS = ("tactor_last_error", "tactor_create", "tactor_destroy", "tactor_forward", "tactor_act",
-                 "tactor_launch_count")
+                 "tactor_launch_count", "tactor_status")
 
 _lib = capi.lib
 _lib.tactor_last_error.restype = C.c_char_p
@@ -34,6 +34,7 @@ _lib.tactor_act.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.c_void_p,
                             C.c_float, C.c_uint64, C.c_void_p]
 _lib.tactor_launch_count.argtypes = [C.c_void_p]
 _lib.tactor_launch_count.restype = C.c_int64
+_lib.tactor_status.argtypes = [C.c_void_p]
 
 
 def _check(rc):
@@ -117,3 +118,7 @@ class BatchedActor:
 
     def launch_count(self) -> int:
         return int(_lib.tactor_launch_count(self._h))
+
+    def check(self) -> None:
+        """synchronise and raise if a kernel reported a timed-out barrier wait"""
+        _check(_lib.tactor_status(self._h))

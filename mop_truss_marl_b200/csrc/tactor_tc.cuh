@@ -1,15 +1,14 @@
-// tcgen05 version of the hidden GCN layer:  Y (+)= relu( Ablk . (X . W) + b ),  X [M,200] fp32, W [200,200].
+// tcgen05 building blocks and the whole-network fused actor kernel.
 //
-//   * one CTA = 128 rows (8 environments of 16 nodes / 4 of 32) x all 208 (padded) output columns
+//   * a CTA owns 128 rows (8 environments of 16 nodes / 4 of 32) and all 208 (padded) output columns
 //   * X.W on the 5th-gen tensor cores: tcgen05.mma kind::tf32, M=128 N=208 K=8 per instruction, fp32
-//     accumulators in TMEM (256 columns per CTA, two CTAs per SM)
+//     accumulators in TMEM
 //   * float32-equivalent accuracy by the 3xTF32 split: x = hi + lo with hi = x truncated to 10 mantissa bits,
 //     X.W ~= Xhi.Whi + Xhi.Wlo + Xlo.Whi (three MMAs per k-step into the same accumulator)
 //   * operands in the canonical no-swizzle K-major layout (8-row x 16-byte core matrices): W is pre-split and
 //     pre-laid-out on the host so a K-chunk is ONE cp.async.bulk (TMA 1-D bulk copy, completion on an
-//     mbarrier); X chunks are split on the fly by the loader threads
-//   * epilogue: tcgen05.ld 32x32b -> shared memory tile -> block-diagonal adjacency product, bias, ReLU,
-//     optional accumulation into the five-way sum -> global
+//     mbarrier); the A operand is generated and split on the fly by the loader threads
+//   * epilogue: tcgen05.ld 32x32b -> shared memory tile -> block-diagonal adjacency product, bias, ReLU
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,15 +26,11 @@ constexpr int SBO = 128;             // bytes between 8-row groups
 constexpr int A_BYTES = NKB * A_LBO; // one of {hi, lo}
 constexpr int B_BYTES = NKB * B_LBO;
 constexpr int LDT = 212;             // padded row length of the epilogue tile
-constexpr int THREADS = 256;
 constexpr int TMEM_COLS = 256;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 constexpr int STAGES = 2;
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // Ahi, Alo, Bhi, Blo of one K chunk
-__host__ __device__ constexpr int smem_bytes(int nodes) {
-  return STAGES * STAGE_BYTES + (TCM / nodes) * nodes * nodes * 4 + 64;
-}
 // W operand image in global memory: per chunk, [hi: kb][n][4 floats] then [lo: ...]
 __host__ __device__ constexpr int chunk_kw(int K, int c) { return (K - c * KCH) < KCH ? (K - c * KCH) : KCH; }
 
@@ -87,203 +82,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-template <int NODES>
-__global__ void __launch_bounds__(THREADS, 2)
-gcn_layer_tc_kernel(const float* __restrict__ X, int K, const float* __restrict__ Wimg,
-                    const float* __restrict__ bias, const float* __restrict__ adj, int adj_batched,
-                    float* __restrict__ Y, int accumulate, int M, int* __restrict__ error_flag) {
-  constexpr int ENVS = TCM / NODES;
-  constexpr int LDX = 208;
-  extern __shared__ __align__(128) unsigned char smem[];
-  // stage s: [Ahi | Alo | Bhi,Blo (as laid out in global memory)]
-  float* Ad = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);         // [ENVS][NODES(j)][NODES(i)]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ad + ENVS * NODES * NODES);   // [0,1] W chunk landed, [2,3] MMAs of a stage done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  float* Ts = reinterpret_cast<float*>(smem);                // epilogue tile [64][LDT], aliases the stages
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * TCM;
-  const uint32_t bar_b0 = smem_u32(&bars[0]), bar_m0 = smem_u32(&bars[2]);
-
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 32) {
-    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int idx = tid; idx < ENVS * NODES * NODES; idx += THREADS) {
-    const int e = idx / (NODES * NODES), r = idx % (NODES * NODES), i = r / NODES, j = r % NODES;
-    const int env = row0 / NODES + e;
-    float v = 0.f;
-    if (env * NODES < M) v = adj_batched ? adj[(size_t)env * NODES * NODES + r] : adj[r];
-    Ad[(e * NODES + j) * NODES + i] = v;
-  }
-
-  const int nchunks = (K + KCH - 1) / KCH;
-  // ---- X chunk loader: 128 rows x 4 core columns = 512 float4, two per thread, lanes along rows ----------
-  const int lr = tid % TCM, lkb = tid / TCM;                 // (row, core column) and (row, core column + 2)
-  auto load_x = [&](int c, float4 (&v)[2]) {
-    const int nkb = chunk_kw(K, c) / 4;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int kb = lkb + 2 * q;
-      v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kb < nkb && row0 + lr < M)
-        v[q] = *reinterpret_cast<const float4*>(X + (size_t)(row0 + lr) * LDX + c * KCH + 4 * kb);
-    }
-  };
-  auto store_x = [&](int c, const float4 (&v)[2]) {
-    unsigned char* Ahi = smem + (c & 1) * STAGE_BYTES;
-    unsigned char* Alo = Ahi + A_BYTES;
-    const int nkb = chunk_kw(K, c) / 4;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int kb = lkb + 2 * q;
-      if (kb >= nkb) continue;
-      float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v[q].x) & 0xFFFFE000u); l.x = v[q].x - h.x;
-      h.y = __uint_as_float(__float_as_uint(v[q].y) & 0xFFFFE000u); l.y = v[q].y - h.y;
-      h.z = __uint_as_float(__float_as_uint(v[q].z) & 0xFFFFE000u); l.z = v[q].z - h.z;
-      h.w = __uint_as_float(__float_as_uint(v[q].w) & 0xFFFFE000u); l.w = v[q].w - h.w;
-      *reinterpret_cast<float4*>(Ahi + kb * A_LBO + lr * 16) = h;
-      *reinterpret_cast<float4*>(Alo + kb * A_LBO + lr * 16) = l;
-    }
-  };
-  // W image offsets: chunk c starts at 2 * B_LBO * (number of core columns before it)
-  auto w_chunk = [&](int c, uint32_t& bytes) -> const unsigned char* {
-    bytes = 2u * (chunk_kw(K, c) / 4) * B_LBO;
-    return reinterpret_cast<const unsigned char*>(Wimg) + (size_t)c * (2u * NKB * B_LBO);
-  };
-  auto issue_w = [&](int c) {                                // one elected thread
-    uint32_t bytes;
-    const unsigned char* src = w_chunk(c, bytes);
-    const uint32_t bar = bar_b0 + 8 * (c & 1);
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(smem_u32(smem + (c & 1) * STAGE_BYTES + 2 * A_BYTES), src, bytes, bar);
-  };
-
-  float4 xa[2], xb[2];                                       // chunks c+1 and c+2 in flight
-  load_x(0, xa);
-  if (nchunks > 1) load_x(1, xb);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();                                           // barriers initialised, TMEM allocated
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) issue_w(0);
-  store_x(0, xa);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-
-  bool ok = true;
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c & 1;
-    const uint32_t use_parity = (uint32_t)((c >> 1) & 1);    // parity of this use of stage s
-    if (tid == 0) {                                          // MMAs of chunk c (asynchronous)
-      ok = mbar_wait(bar_b0 + 8 * s, use_parity) && ok;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int kw = chunk_kw(K, c), nkb = kw / 4;
-      const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-      const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + nkb * B_LBO;
-      for (int ks = 0; ks < kw / 8; ++ks) {
-        const uint32_t ao = 2 * ks * A_LBO, bo = 2 * ks * B_LBO;
-        const uint64_t dah = make_desc(a_hi + ao, A_LBO), dal = make_desc(a_lo + ao, A_LBO);
-        const uint64_t dbh = make_desc(b_hi + bo, B_LBO), dbl = make_desc(b_lo + bo, B_LBO);
-        mma_tf32(tmem_base, dah, dbh, (c | ks) != 0);
-        mma_tf32(tmem_base, dah, dbl, 1);
-        mma_tf32(tmem_base, dal, dbh, 1);
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m0 + 8 * s)
-                   : "memory");
-    }
-    if (c + 1 < nchunks) {
-      // stage s^1 was last used by chunk c-1: wait for its MMAs before overwriting it
-      if (c >= 1) ok = mbar_wait(bar_m0 + 8 * (s ^ 1), (uint32_t)(((c - 1) >> 1) & 1)) && ok;
-      if (tid == 0) issue_w(c + 1);
-      if (c & 1) store_x(c + 1, xa); else store_x(c + 1, xb);
-      if (c + 2 < nchunks) { if (c & 1) load_x(c + 2, xb); else load_x(c + 2, xa); }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-    }
-  }
-  // both stages' last MMAs (the commit of the final chunk covers every earlier MMA)
-  ok = mbar_wait(bar_m0 + 8 * ((nchunks - 1) & 1), (uint32_t)(((nchunks - 1) >> 1) & 1)) && ok;
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (!ok && error_flag) atomicExch(error_flag, 1);
-
-  // ---- epilogue: two passes of 64 rows -------------------------------------------------------------------
-  const int tx = tid % 26, ty = tid / 26;                    // 208 threads own an 8 x 8 output patch
-  float4 bs0 = make_float4(0, 0, 0, 0), bs1 = bs0;
-  if (tid < 208) {
-    bs0 = reinterpret_cast<const float4*>(bias + 8 * tx)[0];
-    bs1 = reinterpret_cast<const float4*>(bias + 8 * tx)[1];
-  }
-  const float bb[8] = {bs0.x, bs0.y, bs0.z, bs0.w, bs1.x, bs1.y, bs1.z, bs1.w};
-  for (int p = 0; p < 2; ++p) {
-    __syncthreads();                                         // Ts free (previous pass stored / MMAs done)
-    const int q = warp & 3;                                  // TMEM lane quarter this warp may read
-    if ((q >> 1) == p) {
-      const int rl = (q & 1) * 32 + lane;                    // row inside the 64-row half
-      const int cbase = (warp >> 2) * 104;
-      for (int cc = 0; cc < 104; cc += 8) {
-        float v[8];
-        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cbase + cc), v);
-        float4* dst = reinterpret_cast<float4*>(Ts + rl * LDT + cbase + cc);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-      }
-    }
-    __syncthreads();
-    if (tid < 208) {
-      float acc[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int cidx = 0; cidx < 8; ++cidx) acc[i][cidx] = 0.f;
-      const int rt = 64 * p + 8 * ty;                        // first row of the patch inside the 128-row tile
-      const int e = rt / NODES, ri = rt % NODES;
-      const int tbase = (e * NODES - 64 * p);                // env's first row inside the 64-row half
-#pragma unroll 4
-      for (int j = 0; j < NODES; ++j) {
-        const float4 a0 = reinterpret_cast<const float4*>(Ad + (e * NODES + j) * NODES + ri)[0];
-        const float4 a1 = reinterpret_cast<const float4*>(Ad + (e * NODES + j) * NODES + ri)[1];
-        const float4 t0 = reinterpret_cast<const float4*>(Ts + (tbase + j) * LDT + 8 * tx)[0];
-        const float4 t1 = reinterpret_cast<const float4*>(Ts + (tbase + j) * LDT + 8 * tx)[1];
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int cidx = 0; cidx < 8; ++cidx) acc[i][cidx] = fmaf(a[i], t[cidx], acc[i][cidx]);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row0 + rt + i;
-        if (row >= M) continue;
-        float v[8];
-#pragma unroll
-        for (int cidx = 0; cidx < 8; ++cidx) v[cidx] = fmaxf(acc[i][cidx] + bb[cidx], 0.f);
-        float4* dst = reinterpret_cast<float4*>(Y + (size_t)row * LDX + 8 * tx);
-        if (accumulate) {
-          const float4 o0 = dst[0], o1 = dst[1];
-          v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
-          v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
-        }
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-  }
 }
 
 // =========================================================================================================

@@ -24,7 +24,7 @@ def test_exports_match_header():
     hdr2 = open(os.path.join(ROOT, "include", "tactor.h")).read()
     declared2 = set(re.findall(r"\b(tactor_[a-z_0-9]+)\s*\(", hdr2))
     assert declared2 == {"tactor_last_error", "tactor_create", "tactor_destroy", "tactor_forward", "tactor_act",
-                         "tactor_launch_count"}
+                         "tactor_launch_count", "tactor_status"}
     for name in declared2:
         assert hasattr(capi.lib, name), name
 

@@ -49,7 +49,8 @@ def test_forward_matches_float64_oracle(N, B, P):
     g3, t3 = a.forward(*dev)
     g64b, t64b = actor_forward(w, *inp)
     assert np.abs(g3.cpu().numpy() - g64b).max() <= ATOL and np.abs(t3.cpu().numpy() - t64b).max() <= ATOL
-    assert a.launch_count() >= 6          # 2 launches per forward (Pareto embedding + fused network)
+    assert a.launch_count() == 6          # 2 launches per forward (Pareto embedding + fused network)
+    a.check()
 
 
 def test_act_noise_statistics():
