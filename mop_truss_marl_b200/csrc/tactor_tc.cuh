@@ -96,7 +96,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 // HBM traffic per environment: x_n, three [N,N] adjacencies, pooled row in; 5N floats out.
 namespace fused {
 
-constexpr int FTHREADS = 256;                              // 8 warps: 256 loaders, 208 epilogue patches of 16 x 4
+constexpr int FTHREADS = 288;                              // warps 0-7: operand generators + epilogue; warp 8: TMA + MMA issuer
 constexpr int LDH = 212;                                   // padded row length of the H tile
 constexpr int NGEMM = 7;
 constexpr int KH = 200;
@@ -139,14 +139,18 @@ actor_fused_kernel(const Params P) {
   float* Zs = reinterpret_cast<float*>(smem);                                // [128][16], only until the first stage fill
   float* Us = Pl + ENVS * 208;                                               // [64][4] head pre-activations
   uint64_t* bars = reinterpret_cast<uint64_t*>(Us + 64 * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
   float* Ts = reinterpret_cast<float*>(smem);                                // [64][LDT], aliases the stages
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TCM;
   const int env0 = row0 / NODES;
   const int M = P.M;
-  const uint32_t bar_b0 = smem_u32(&bars[0]), bar_m0 = smem_u32(&bars[2]);
+  // mbarriers: [0,1] W chunk landed (TMA tx)  [2,3] stage consumed (tcgen05.commit)
+  //            [4,5] A operand written (one arrive per generator warp)  [6] accumulator complete
+  const uint32_t bar_b0 = smem_u32(&bars[0]), bar_m0 = smem_u32(&bars[2]), bar_a0 = smem_u32(&bars[4]);
+  const uint32_t bar_acc = smem_u32(&bars[6]);
+  const bool is_issuer = (warp == 8);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -156,6 +160,9 @@ actor_fused_kernel(const Params P) {
   }
   if (tid == 32) {
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    mbar_init(bar_a0, 8);
+    mbar_init(bar_a0 + 8, 8);
+    mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // shared A_n (transposed), pooled rows, raw x_n rows (staged in H, which is free until the first epilogue)
@@ -255,43 +262,53 @@ actor_fused_kernel(const Params P) {
       }
       __syncthreads();
     }
-    // ---- main loop: chunk c in stage (use & 1) ----
-    if (tid == 0) issue_w(g, 0, use & 1);
-    fill_stage(g, 0, use & 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    for (int c = 0; c < NCH; ++c, ++use) {
-      const int s = use & 1;
-      const uint32_t parity = (use >> 1) & 1;
-      if (tid == 0) {
-        ok = mbar_wait(bar_b0 + 8 * s, parity) && ok;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int kw = chunk_kw(KH, c), nkb = kw / 4;
-        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + nkb * B_LBO;
-        for (int ks = 0; ks < kw / 8; ++ks) {
-          const uint32_t ao = 2 * ks * A_LBO, bo = 2 * ks * B_LBO;
-          const uint64_t dah = make_desc(a_hi + ao, A_LBO), dal = make_desc(a_lo + ao, A_LBO);
-          const uint64_t dbh = make_desc(b_hi + bo, B_LBO), dbl = make_desc(b_lo + bo, B_LBO);
-          mma_tf32(tmem_base, dah, dbh, (c | ks) != 0);
-          mma_tf32(tmem_base, dah, dbl, 1);
-          mma_tf32(tmem_base, dal, dbh, 1);
+    // ---- main loop, warp-specialised: generators fill the A operand two chunks ahead, the issuer warp
+    //      streams the W chunks (TMA) and issues the MMAs; the only hand-offs are mbarriers ----
+    const uint32_t use0 = use;
+    if (is_issuer) {
+      if (lane == 0) {
+        issue_w(g, 0, use0 & 1);
+        for (int c = 0; c < NCH; ++c) {
+          const uint32_t u = use0 + c, s = u & 1, parity = (u >> 1) & 1;
+          ok = mbar_wait(bar_a0 + 8 * s, parity) && ok;
+          ok = mbar_wait(bar_b0 + 8 * s, parity) && ok;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int kw = chunk_kw(KH, c), nkb = kw / 4;
+          const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + nkb * B_LBO;
+          for (int ks = 0; ks < kw / 8; ++ks) {
+            const uint32_t ao = 2 * ks * A_LBO, bo = 2 * ks * B_LBO;
+            const uint64_t dah = make_desc(a_hi + ao, A_LBO), dal = make_desc(a_lo + ao, A_LBO);
+            const uint64_t dbh = make_desc(b_hi + bo, B_LBO), dbl = make_desc(b_lo + bo, B_LBO);
+            mma_tf32(tmem_base, dah, dbh, (c | ks) != 0);
+            mma_tf32(tmem_base, dah, dbl, 1);
+            mma_tf32(tmem_base, dal, dbh, 1);
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m0 + 8 * s)
+                       : "memory");
+          if (c + 1 < NCH) {
+            // W chunk c+1 goes into the other stage: its previous user (chunk c-1) must have been consumed
+            if (c >= 1) ok = mbar_wait(bar_m0 + 8 * (s ^ 1), ((u - 1) >> 1) & 1) && ok;
+            issue_w(g, c + 1, s ^ 1);
+          } else {
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc)
+                         : "memory");
+          }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m0 + 8 * s)
-                     : "memory");
       }
-      if (c + 1 < NCH) {
-        // the other stage was used by the previous chunk (use-1): its MMAs must be done before refilling it
-        if (c >= 1) ok = mbar_wait(bar_m0 + 8 * (s ^ 1), ((use - 1) >> 1) & 1) && ok;
-        if (tid == 0) issue_w(g, c + 1, s ^ 1);
-        fill_stage(g, c + 1, s ^ 1);
+      __syncwarp();
+    } else {
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t u = use0 + c, s = u & 1;
+        if (c >= 2) ok = mbar_wait(bar_m0 + 8 * s, ((u - 2) >> 1) & 1) && ok;   // chunk c-2 consumed
+        fill_stage(g, c, s);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a0 + 8 * s) : "memory");
       }
     }
-    // all MMAs of this GEMM (the last commit covers every earlier one); also drains the second-to-last stage
-    ok = mbar_wait(bar_m0 + 8 * ((use - 1) & 1), ((use - 1) >> 1) & 1) && ok;
-    if (NCH >= 2) ok = mbar_wait(bar_m0 + 8 * ((use - 2) & 1), ((use - 2) >> 1) & 1) && ok;
+    use = use0 + NCH;
+    ok = mbar_wait(bar_acc, (uint32_t)(g & 1)) && ok;        // every MMA of this GEMM has completed
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue ----
@@ -301,7 +318,7 @@ actor_fused_kernel(const Params P) {
     for (int p = 0; p < 2; ++p) {
       __syncthreads();                                       // Ts / Us free
       const int q = warp & 3;
-      if ((q >> 1) == p) {
+      if (warp < 8 && (q >> 1) == p) {
         const int rl = (q & 1) * 32 + lane;
         const int cbase = (warp >> 2) * 104;
         for (int cc = 0; cc < 104; cc += 8) {

@@ -154,6 +154,43 @@ def test_random_walk(pair, mode):
             parent = children[rng.randint(len(children))]
 
 
+def test_adversarial_walk(pair):
+    """corner cases of the transition: ties, exact bounds, inf / NaN geometry actions, absurd stale ranges"""
+    from util import adversarial_actions, adversarial_move_range
+    run, ref, orc = pair
+    rng = np.random.RandomState(11)
+    import contextlib, io
+    with ref.mods.cwd(), contextlib.redirect_stdout(io.StringIO()):
+        ref.gen.re_value(*ref.args)
+    parent = ref.reset_state()
+    N = orc.mesh.N
+    done = 0
+    for k in range(30 if N == 16 else 15):
+        a_geo, a_topo = adversarial_actions(rng, N)
+        up, down = adversarial_move_range(rng, N)
+        ref.set_move_range(up, down)
+        coin = bool(rng.rand() >= 0.5)
+        f = ref.fem_fields()
+        g2, t2 = a_geo.copy(), a_topo.copy()
+        try:
+            point, S = ref.step(parent[-3], parent[-2], parent[-1], a_geo, a_topo, coin)
+        except (np.linalg.LinAlgError, ZeroDivisionError):
+            continue
+        out = orc.step(parent[-3], parent[-2], f["max_up"], f["max_down"], g2, t2, coin)
+        assert np.array_equal(a_geo, g2, equal_nan=True) and np.array_equal(a_topo, t2)
+        f2 = ref.fem_fields()
+        assert np.array_equal(f2["y"], out["y"]) and np.array_equal(f2["section"], out["section"])
+        assert np.array_equal(f2["max_up"], out["max_up"]) and np.array_equal(f2["max_down"], out["max_down"])
+        cond = np.linalg.cond(orc.solve_only(out["y"], out["section"])["K"])
+        if cond < 1e6:
+            assert nrm(out["d"], f2["d"]) <= 1e-9
+            for name, a, b in (("x_n", out["x_n"], S[0]), ("nN_x_n", out["nN_x_n"], S[8]), ("nN_x_e", out["nN_x_e"], S[9])):
+                assert ulp_diff(a, b).max() <= 2, name
+        parent = S
+        done += 1
+    assert done >= 5
+
+
 def test_pareto_state_data(pair):
     run, ref, orc = pair
     rng = np.random.RandomState(5)

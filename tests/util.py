@@ -37,3 +37,21 @@ def assert_f32_close(name, got, want, tol=F32_ULP_TOL):
     u = ulp_diff(got, want)
     assert u.max() <= tol, "%s: %d ulp at %s (got %r want %r)" % (
         name, u.max(), np.unravel_index(u.argmax(), u.shape), got.flat[u.argmax()], want.flat[u.argmax()])
+
+
+def adversarial_actions(rng, N):
+    """actions that hit the reference's corner cases: exact 0 / 1, ties (np.argmax takes the first), out of
+    range, +-inf and NaN in a_geo (clip leaves NaN, argmax picks it, min([1, nan]) == 1).  a_topo stays finite:
+    the reference forms nC_e @ a_topo, where one NaN poisons every element through 0*NaN -- not reproduced."""
+    pool = np.array([0.0, 1.0, 0.5, 0.5, 0.25, 1.5, -0.5, 0.999999, 1e-7, np.inf, -np.inf, np.nan], dtype=np.float32)
+    a_geo = pool[rng.randint(0, len(pool), size=(N, 2))].astype(np.float32)
+    mix = rng.rand(N, 2) < 0.4
+    a_geo = np.where(mix, rng.rand(N, 2).astype(np.float32), a_geo).astype(np.float32)
+    tpool = np.array([0.0, 1.0, 0.5, 0.5, 0.25, 1.5, -0.5, 0.75], dtype=np.float32)
+    a_topo = tpool[rng.randint(0, len(tpool), size=(N, 3))].astype(np.float32)
+    return a_geo, a_topo
+
+
+def adversarial_move_range(rng, N):
+    pool = np.array([0.0, 0.3, 7.7, 8.0, 40.0, 1e-3, 2.0], dtype=np.float32)
+    return pool[rng.randint(0, len(pool), size=N)], pool[rng.randint(0, len(pool), size=N)]
