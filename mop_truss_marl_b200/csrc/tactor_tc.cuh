@@ -123,7 +123,7 @@ struct Params {
 template <int NODES>
 __host__ __device__ constexpr int fused_smem_bytes() {
   return STAGES * STAGE_BYTES + TCM * LDH * 4 + (TCM / NODES) * NODES * NODES * 4 + NODES * NODES * 4 +
-         13 * 208 * 4 + (TCM / NODES) * 208 * 4 + 64 * 4 * 4 + 128;
+         14 * 208 * 4 + (TCM / NODES) * 208 * 4 + 64 * 4 * 4 + 128;
 }
 
 template <int NODES>
@@ -134,8 +134,9 @@ actor_fused_kernel(const Params P) {
   float* H = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [128][LDH]
   float* Ad = H + TCM * LDH;                                                 // [ENVS][N(j)][N(i)] adjacency of the current GEMM
   float* An = Ad + ENVS * NODES * NODES;                                     // [N(j)][N(i)] shared A_n, transposed
-  float* W1s = An + NODES * NODES;                                           // [13][208] layer-1 kernel of the current GEMM
-  float* Pl = W1s + 13 * 208;                                                // [ENVS][208] pooled Pareto embedding
+  float* W1s = An + NODES * NODES;                                           // [14][208] layer-1 kernel + bias row of the current GEMM;
+                                                                             // for g >= 5: head kernel [200][4] + bias [4]
+  float* Pl = W1s + 14 * 208;                                                // [ENVS][208] pooled Pareto embedding
   float* Zs = reinterpret_cast<float*>(smem);                                // [128][16], only until the first stage fill
   float* Us = Pl + ENVS * 208;                                               // [64][4] head pre-activations
   uint64_t* bars = reinterpret_cast<uint64_t*>(Us + 64 * 4);
@@ -196,9 +197,8 @@ actor_fused_kernel(const Params P) {
   // ---- A operand generator: 4 consecutive k of row lr for GEMM g -------------------------------------------
   auto gen_a = [&](int g, int k) -> float4 {
     if (g <= 3) {
-      const int l1 = (g == 0) ? 0 : (g == 3 ? 2 : 1);
       const float* w = W1s + k;
-      float4 acc = __ldg(reinterpret_cast<const float4*>(P.b1[l1] + k));
+      float4 acc = *reinterpret_cast<const float4*>(W1s + 13 * 208 + k);
 #pragma unroll
       for (int i = 0; i < 13; ++i) {
         const float4 wv = *reinterpret_cast<const float4*>(w + i * 208);
@@ -239,29 +239,80 @@ actor_fused_kernel(const Params P) {
     bulk_g2s(smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES), src, bytes, bar);
   };
 
+  // ---- per-GEMM small operands: adjacency tile (<= 8 floats per thread), layer-1 kernel + bias or head
+  //      kernel + bias (<= 3 float4 per thread); loaded one GEMM ahead so their latency hides in the epilogue
+  constexpr int ADJ_PER = (ENVS * NODES * NODES + FTHREADS - 1) / FTHREADS;
+  constexpr int W1_PER = (14 * 208 / 4 + FTHREADS - 1) / FTHREADS;
+  float adj_reg[ADJ_PER];
+  float4 w1_reg[W1_PER];
+  auto prefetch_small = [&](int g) {
+    const float* adj = (g == 1) ? P.A_ts : (g == 2) ? P.A_cs : (g == 3 || g == 6) ? P.A_s : nullptr;
+#pragma unroll
+    for (int q = 0; q < ADJ_PER; ++q) {
+      const int idx = tid + q * FTHREADS;
+      float v = 0.f;
+      if (adj != nullptr && idx < ENVS * NODES * NODES) {
+        const int e = idx / (NODES * NODES), r = idx % (NODES * NODES);
+        if ((env0 + e) * NODES < M) v = __ldg(adj + (size_t)(env0 + e) * NODES * NODES + r);
+      }
+      adj_reg[q] = v;
+    }
+    if (g == 0 || g == 1 || g == 3) {                        // g = 2 reuses gcn_l1_2's kernel
+      const int l1 = g == 0 ? 0 : (g == 3 ? 2 : 1);
+#pragma unroll
+      for (int q = 0; q < W1_PER; ++q) {
+        const int idx = tid + q * FTHREADS;
+        w1_reg[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < 13 * 52) w1_reg[q] = __ldg(reinterpret_cast<const float4*>(P.w1[l1]) + idx);
+        else if (idx < 14 * 52) w1_reg[q] = __ldg(reinterpret_cast<const float4*>(P.b1[l1]) + (idx - 13 * 52));
+      }
+    } else if (g >= 5) {                                     // head kernel rows [k][0..3] (+ bias as row 200)
+      const int hd = g - 5;
+#pragma unroll
+      for (int q = 0; q < W1_PER; ++q) {
+        const int k = tid + q * FTHREADS;
+        w1_reg[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < KH) w1_reg[q] = __ldg(reinterpret_cast<const float4*>(P.w_head[hd] + (size_t)k * 208));
+        else if (k == KH) w1_reg[q] = __ldg(reinterpret_cast<const float4*>(P.b_head[hd]));
+      }
+    }
+  };
+  auto commit_small = [&](int g) {
+    const bool shared_an = !(g == 1 || g == 2 || g == 3 || g == 6);
+#pragma unroll
+    for (int q = 0; q < ADJ_PER; ++q) {
+      const int idx = tid + q * FTHREADS;
+      if (idx < ENVS * NODES * NODES) {
+        const int e = idx / (NODES * NODES), r = idx % (NODES * NODES), i = r / NODES, j = r % NODES;
+        Ad[(e * NODES + j) * NODES + i] = shared_an ? An[j * NODES + i] : adj_reg[q];
+      }
+    }
+    if (g == 0 || g == 1 || g == 3) {
+#pragma unroll
+      for (int q = 0; q < W1_PER; ++q) {
+        const int idx = tid + q * FTHREADS;
+        if (idx < 14 * 52) reinterpret_cast<float4*>(W1s)[idx] = w1_reg[q];
+      }
+    } else if (g >= 5) {
+#pragma unroll
+      for (int q = 0; q < W1_PER; ++q) {
+        const int k = tid + q * FTHREADS;
+        if (k <= KH) reinterpret_cast<float4*>(W1s)[k] = w1_reg[q];
+      }
+    }
+  };
+
   constexpr int NCH = (KH + KCH - 1) / KCH;                  // 13 chunks per GEMM
   uint32_t use = 0;                                          // running count of stage uses (both barriers flip per use)
   bool ok = true;
   const int cq = tid % 52, gq = tid / 52;                    // epilogue role (tid < 208): rows 16*gq.., columns 4*cq..
 
   for (int g = 0; g < NGEMM; ++g) {
-    // adjacency of this GEMM (transposed per environment): A_n for g = 0, 4, 5; A_ts, A_cs, A_s otherwise
-    {
-      const float* adj = (g == 1) ? P.A_ts : (g == 2) ? P.A_cs : (g == 3 || g == 6) ? P.A_s : nullptr;
-      for (int idx = tid; idx < ENVS * NODES * NODES; idx += FTHREADS) {
-        const int e = idx / (NODES * NODES), r = idx % (NODES * NODES), i = r / NODES, j = r % NODES;
-        float v = 0.f;
-        if (adj == nullptr) v = An[j * NODES + i];
-        else if ((env0 + e) * NODES < M) v = adj[(size_t)(env0 + e) * NODES * NODES + r];
-        Ad[(e * NODES + j) * NODES + i] = v;
-      }
-      if (g == 0 || g == 1 || g == 3) {                      // g = 2 reuses gcn_l1_2's kernel
-        const float* w1 = P.w1[g == 0 ? 0 : (g == 3 ? 2 : 1)];
-        for (int idx = tid; idx < 13 * 208 / 4; idx += FTHREADS)
-          reinterpret_cast<float4*>(W1s)[idx] = __ldg(reinterpret_cast<const float4*>(w1) + idx);
-      }
-      __syncthreads();
-    }
+    // adjacency (transposed per environment: A_n for g = 0, 4, 5; A_ts, A_cs, A_s otherwise) and the small
+    // weights of this GEMM were prefetched into registers during the previous epilogue
+    if (g == 0) prefetch_small(0);
+    commit_small(g);
+    __syncthreads();
     // ---- main loop, warp-specialised: generators fill the A operand two chunks ahead, the issuer warp
     //      streams the W chunks (TMA) and issues the MMAs; the only hand-offs are mbarriers ----
     const uint32_t use0 = use;
@@ -310,6 +361,7 @@ actor_fused_kernel(const Params P) {
     use = use0 + NCH;
     ok = mbar_wait(bar_acc, (uint32_t)(g & 1)) && ok;        // every MMA of this GEMM has completed
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (g + 1 < NGEMM) prefetch_small(g + 1);                // latency hidden behind the epilogue
 
     // ---- epilogue ----
     float4 bs0 = make_float4(0, 0, 0, 0);
@@ -380,10 +432,14 @@ actor_fused_kernel(const Params P) {
         __syncthreads();
         if (tid < 64 * nout) {
           const int r = tid / nout, o = tid % nout;
-          const float* w = P.w_head[hd] + o;
-          float u = 0.f;
-          for (int k = 0; k < KH; ++k) u = fmaf(Ts[r * LDT + k], __ldg(w + (size_t)k * 208), u);
-          Us[r * 4 + o] = u;
+          const float* w = W1s + o;                          // head kernel staged as [k][4]
+          float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+          for (int k = 0; k < KH; k += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(Ts + r * LDT + k);
+            u0 = fmaf(x.x, w[4 * k], u0); u1 = fmaf(x.y, w[4 * k + 4], u1);
+            u2 = fmaf(x.z, w[4 * k + 8], u2); u3 = fmaf(x.w, w[4 * k + 12], u3);
+          }
+          Us[r * 4 + o] = (u0 + u1) + (u2 + u3);
         }
         __syncthreads();
         if (tid < 64 * nout) {
@@ -391,7 +447,7 @@ actor_fused_kernel(const Params P) {
           const int e = r / NODES, n = r % NODES;
           float v = 0.f;
           for (int j = 0; j < NODES; ++j) v = fmaf(An[j * NODES + n], Us[(e * NODES + j) * 4 + o], v);
-          v += P.b_head[hd][o];
+          v += W1s[4 * KH + o];
           const int row = row0 + 64 * p + r;
           if (row < M) (hd == 0 ? P.geo : P.topo)[(size_t)row * nout + o] = 1.f / (1.f + expf(-v));
         }
