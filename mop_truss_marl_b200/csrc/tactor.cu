@@ -181,8 +181,8 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
     e = cudaMalloc(&h->d_wimg[l], img.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size() * 4, cudaMemcpyHostToDevice);
   }
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4);
-  if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4096);
+  if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4096);
   if (e == cudaSuccess) {
     if (nodes == 16) e = cudaFuncSetAttribute(tactor::tc::fused::actor_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::fused::fused_smem_bytes<16>());
     else e = cudaFuncSetAttribute(tactor::tc::fused::actor_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::fused::fused_smem_bytes<32>());
@@ -239,6 +239,8 @@ int tactor_act(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, fl
 }
 
 int64_t tactor_launch_count(tactor_handle_t h) { return h ? h->launches.load() : 0; }
+
+extern "C" int tactor_debug_dump(tactor_handle_t h, void* dst) { return (int)cudaMemcpy(dst, h->d_error, 4096, cudaMemcpyDeviceToHost); }
 
 int tactor_status(tactor_handle_t h) {
   if (!h) return afail(TFEM_ERR_ARG, "null argument");

@@ -302,6 +302,9 @@ actor_fused_kernel(const Params P) {
     }
   };
 
+#ifdef DEBUG_TIMING
+  const long long Tstart = clock64();
+#endif
   constexpr int NCH = (KH + KCH - 1) / KCH;                  // 13 chunks per GEMM
   uint32_t use = 0;                                          // running count of stage uses (both barriers flip per use)
   bool ok = true;
@@ -310,41 +313,66 @@ actor_fused_kernel(const Params P) {
   for (int g = 0; g < NGEMM; ++g) {
     // adjacency (transposed per environment: A_n for g = 0, 4, 5; A_ts, A_cs, A_s otherwise) and the small
     // weights of this GEMM were prefetched into registers during the previous epilogue
+#ifdef DEBUG_TIMING
+    const long long T0 = clock64();
+#endif
     if (g == 0) prefetch_small(0);
     commit_small(g);
     __syncthreads();
+#ifdef DEBUG_TIMING
+    const long long T1 = clock64();
+#endif
     // ---- main loop, warp-specialised: generators fill the A operand two chunks ahead, the issuer warp
     //      streams the W chunks (TMA) and issues the MMAs; the only hand-offs are mbarriers ----
     const uint32_t use0 = use;
     if (is_issuer) {
       if (lane == 0) {
+        // Measured with clock64 (round 1): issuing is latency-bound on this one thread, so the operand
+        // descriptors are formed outside the loop, and the W chunk for c+1 is requested BEFORE the MMAs of
+        // chunk c are issued so that it has a whole iteration to land.
+        uint64_t da[2][2][2], db[2][2][2];                   // [stage][k-step][hi, lo]
+#pragma unroll
+        for (int st = 0; st < 2; ++st)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES) + 2 * ks * A_LBO;
+            const uint32_t b_hi = smem_u32(smem + st * STAGE_BYTES) + 2 * A_BYTES + 2 * ks * B_LBO;
+            da[st][ks][0] = make_desc(a_hi, A_LBO);
+            da[st][ks][1] = make_desc(a_hi + A_BYTES, A_LBO);
+            db[st][ks][0] = make_desc(b_hi, B_LBO);
+            db[st][ks][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);      // lo half of a full chunk
+          }
         issue_w(g, 0, use0 & 1);
         for (int c = 0; c < NCH; ++c) {
           const uint32_t u = use0 + c, s = u & 1, parity = (u >> 1) & 1;
-          ok = mbar_wait(bar_a0 + 8 * s, parity) && ok;
-          ok = mbar_wait(bar_b0 + 8 * s, parity) && ok;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int kw = chunk_kw(KH, c), nkb = kw / 4;
-          const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + nkb * B_LBO;
-          for (int ks = 0; ks < kw / 8; ++ks) {
-            const uint32_t ao = 2 * ks * A_LBO, bo = 2 * ks * B_LBO;
-            const uint64_t dah = make_desc(a_hi + ao, A_LBO), dal = make_desc(a_lo + ao, A_LBO);
-            const uint64_t dbh = make_desc(b_hi + bo, B_LBO), dbl = make_desc(b_lo + bo, B_LBO);
-            mma_tf32(tmem_base, dah, dbh, (c | ks) != 0);
-            mma_tf32(tmem_base, dah, dbl, 1);
-            mma_tf32(tmem_base, dal, dbh, 1);
-          }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m0 + 8 * s)
-                       : "memory");
           if (c + 1 < NCH) {
             // W chunk c+1 goes into the other stage: its previous user (chunk c-1) must have been consumed
             if (c >= 1) ok = mbar_wait(bar_m0 + 8 * (s ^ 1), ((u - 1) >> 1) & 1) && ok;
             issue_w(g, c + 1, s ^ 1);
-          } else {
+          }
+          ok = mbar_wait(bar_a0 + 8 * s, parity) && ok;
+          ok = mbar_wait(bar_b0 + 8 * s, parity) && ok;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int kw = chunk_kw(KH, c);
+          if (kw == KCH) {
+            mma_tf32(tmem_base, da[s][0][0], db[s][0][0], c != 0);
+            mma_tf32(tmem_base, da[s][0][0], db[s][0][1], 1);
+            mma_tf32(tmem_base, da[s][0][1], db[s][0][0], 1);
+            mma_tf32(tmem_base, da[s][1][0], db[s][1][0], 1);
+            mma_tf32(tmem_base, da[s][1][0], db[s][1][1], 1);
+            mma_tf32(tmem_base, da[s][1][1], db[s][1][0], 1);
+          } else {                                           // tail chunk: one k-step, lo half right after hi
+            const uint32_t b_hi = smem_u32(smem + s * STAGE_BYTES) + 2 * A_BYTES;
+            const uint64_t dbl = make_desc(b_hi + (kw / 4) * B_LBO, B_LBO);
+            mma_tf32(tmem_base, da[s][0][0], db[s][0][0], c != 0);
+            mma_tf32(tmem_base, da[s][0][0], dbl, 1);
+            mma_tf32(tmem_base, da[s][0][1], db[s][0][0], 1);
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m0 + 8 * s)
+                       : "memory");
+          if (c + 1 == NCH)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc)
                          : "memory");
-          }
         }
       }
       __syncwarp();
@@ -361,6 +389,9 @@ actor_fused_kernel(const Params P) {
     use = use0 + NCH;
     ok = mbar_wait(bar_acc, (uint32_t)(g & 1)) && ok;        // every MMA of this GEMM has completed
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef DEBUG_TIMING
+    const long long T2 = clock64();
+#endif
     if (g + 1 < NGEMM) prefetch_small(g + 1);                // latency hidden behind the epilogue
 
     // ---- epilogue ----
@@ -454,6 +485,12 @@ actor_fused_kernel(const Params P) {
       }
     }
     __syncthreads();                                         // H / Ts settled before the next GEMM refills the stages
+#ifdef DEBUG_TIMING
+    if (blockIdx.x == 200 && (tid == 0 || tid == 256)) {
+      long long* dbg = reinterpret_cast<long long*>(P.error_flag) + 16 + (tid ? 64 : 0);
+      dbg[g * 4 + 0] = T1 - T0; dbg[g * 4 + 1] = T2 - T1; dbg[g * 4 + 2] = clock64() - T2; dbg[g * 4 + 3] = T0 - Tstart;
+    }
+#endif
   }
   if (!ok && P.error_flag) atomicExch(P.error_flag, 1);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
