@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <new>
@@ -94,6 +95,7 @@ struct tactor_handle_s {
   float* pooled = nullptr;             // [max_batch, 208] Pareto embedding
   float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
   int* d_error = nullptr;              // set by a kernel whose mbarrier wait timed out
+  int ncta = 1;                        // CTAs per tcgen05 group (2 = CTA pair, cta_group::2)
   std::atomic<int64_t> launches{0};
   uint64_t calls = 0;
 };
@@ -109,6 +111,28 @@ struct Guard {
   ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+template <int NODES, int NCTA>
+cudaError_t launch_fused(const tactor::tc::fused::Params& p, int M, cudaStream_t st) {
+  using namespace tactor;
+  const int tiles = (M + tc::TCM - 1) / tc::TCM;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((tiles + NCTA - 1) / NCTA * NCTA));   // a pair whose second tile is past M runs it empty
+  cfg.blockDim = dim3(tc::fused::FTHREADS);
+  cfg.dynamicSmemBytes = tc::fused::fused_smem_bytes<NODES, NCTA>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tc::fused::actor_fused_kernel<NODES, NCTA>, p);
+}
+
+template <int NODES, int NCTA>
+cudaError_t set_fused_smem() {
+  return cudaFuncSetAttribute(tactor::tc::fused::actor_fused_kernel<NODES, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              tactor::tc::fused::fused_smem_bytes<NODES, NCTA>());
+}
+
 template <int NODES>
 cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, float* geo, float* topo, cudaStream_t st) {
   using namespace tactor;
@@ -121,10 +145,9 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   for (int g = 0; g < tc::fused::NGEMM; ++g) { p.wimg[g] = h->d_wimg[4 + g]; p.bias[g] = h->d_b[4 + g]; }
   p.w_head[0] = h->d_w[11]; p.w_head[1] = h->d_w[12]; p.b_head[0] = h->d_b[11]; p.b_head[1] = h->d_b[12];
   p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error;
-  tc::fused::actor_fused_kernel<NODES><<<(M + tc::TCM - 1) / tc::TCM, tc::fused::FTHREADS,
-                                          tc::fused::fused_smem_bytes<NODES>(), st>>>(p);
+  cudaError_t e = (h->ncta == 2) ? launch_fused<NODES, 2>(p, M, st) : launch_fused<NODES, 1>(p, M, st);
   h->launches.fetch_add(2);
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 }  // namespace
 
@@ -143,6 +166,7 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   tactor_handle_s* h = new (std::nothrow) tactor_handle_s();
   if (!h) return afail(TFEM_ERR_ARG, "out of host memory");
   h->device = device; h->nodes = nodes; h->max_batch = max_batch;
+  if (const char* v = getenv("TACTOR_NCTA")) h->ncta = (atoi(v) == 2) ? 2 : 1;     // development switch (A/B timing)
   Guard g(device);
   cudaError_t e = cudaSuccess;
   for (int l = 0; l < TACTOR_NLAYERS && e == cudaSuccess; ++l) {
@@ -158,16 +182,20 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
     if (e == cudaSuccess) e = cudaMemcpy(h->d_w[l], wp.data(), wp.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_b[l], bp.data(), bp.size() * 4, cudaMemcpyHostToDevice);
   }
-  // tcgen05 operand images of the [200,200] layers: per 32-wide K chunk, [hi|lo][kb][n(208)][4 floats]
+  // tcgen05 operand images of the [200,200] layers: per 16-wide K chunk, per CTA of the pair (its half of the
+  // 208 columns), [hi|lo][kb][n][4 floats]
+  const int bn = tactor::tc::TCN / h->ncta;
   for (int l = 4; l <= 10 && e == cudaSuccess; ++l) {
     const int K = kIn[l], kout = kOut[l];
     std::vector<float> img;
     for (int c = 0; c * tactor::tc::KCH < K; ++c) {
       const int kw = tactor::tc::chunk_kw(K, c), nkb = kw / 4;
+      for (int half = 0; half < h->ncta; ++half)
       for (int part = 0; part < 2; ++part)
         for (int kb = 0; kb < nkb; ++kb)
-          for (int n = 0; n < tactor::tc::TCN; ++n)
+          for (int nl = 0; nl < bn; ++nl)
             for (int t = 0; t < 4; ++t) {
+              const int n = half * bn + nl;
               const int k = c * tactor::tc::KCH + 4 * kb + t;
               float v = (n < kout && k < K) ? w->kernel[l][(size_t)k * kout + n] : 0.f;
               uint32_t bits;
@@ -184,8 +212,8 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4096);
   if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4096);
   if (e == cudaSuccess) {
-    if (nodes == 16) e = cudaFuncSetAttribute(tactor::tc::fused::actor_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::fused::fused_smem_bytes<16>());
-    else e = cudaFuncSetAttribute(tactor::tc::fused::actor_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::tc::fused::fused_smem_bytes<32>());
+    if (nodes == 16) e = (h->ncta == 2) ? set_fused_smem<16, 2>() : set_fused_smem<16, 1>();
+    else e = (h->ncta == 2) ? set_fused_smem<32, 2>() : set_fused_smem<32, 1>();
   }
   if (e == cudaSuccess) e = cudaMalloc(&h->pooled, (size_t)max_batch * tactor::LD * 4);
   if (e != cudaSuccess) { tactor_destroy(h); return afail(TFEM_ERR_CUDA, std::string("actor setup: ") + cudaGetErrorString(e)); }

@@ -5,9 +5,12 @@
 //     accumulators in TMEM
 //   * float32-equivalent accuracy by the 3xTF32 split: x = hi + lo with hi = x truncated to 10 mantissa bits,
 //     X.W ~= Xhi.Whi + Xhi.Wlo + Xlo.Whi (three MMAs per k-step into the same accumulator)
-//   * operands in the canonical no-swizzle K-major layout (8-row x 16-byte core matrices): W is pre-split and
-//     pre-laid-out on the host so a K-chunk is ONE cp.async.bulk (TMA 1-D bulk copy, completion on an
-//     mbarrier); the A operand is generated and split on the fly by the loader threads
+//   * the B operand (W) sits in shared memory in the canonical no-swizzle K-major layout (8-row x 16-byte core
+//     matrices): W is pre-split and pre-laid-out on the host so a K-chunk is ONE cp.async.bulk (TMA 1-D bulk
+//     copy, completion on an mbarrier)
+//   * the A operand is generated and split on the fly by the generator threads and written straight into
+//     TENSOR MEMORY (tcgen05.st, lane = row, column = k): it never touches shared memory, whose bandwidth the
+//     tensor core's B reads, the TMA writes and the epilogue already compete for
 //   * epilogue: tcgen05.ld 32x32b -> shared memory tile -> block-diagonal adjacency product, bias, ReLU
 #pragma once
 #include <cuda_runtime.h>
@@ -21,17 +24,29 @@ constexpr int TCN = 208;             // padded output columns (UMMA N, multiple 
 constexpr int KCH = 16;              // K elements per chunk (2 MMA k-steps of 8)
 constexpr int NKB = KCH / 4;         // 16-byte core-matrix columns per chunk
 constexpr int A_LBO = TCM * 16;      // bytes between core matrices adjacent in K (A operand)
-constexpr int B_LBO = TCN * 16;      // same for the B operand
 constexpr int SBO = 128;             // bytes between 8-row groups
 constexpr int A_BYTES = NKB * A_LBO; // one of {hi, lo}
-constexpr int B_BYTES = NKB * B_LBO;
 constexpr int LDT = 212;             // padded row length of the epilogue tile
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;       // [0,208) accumulator, [256, 256 + 32 * AST) A-operand stages
+constexpr int AST = 4;               // A-operand stages in tensor memory: per stage [hi: 16 columns][lo: 16 columns]
+constexpr int TM_A0 = 256;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
-constexpr int STAGES = 2;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // Ahi, Alo, Bhi, Blo of one K chunk
-// W operand image in global memory: per chunk, [hi: kb][n][4 floats] then [lo: ...]
+// NCTA = 1: one CTA per 128-row tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on two
+// tiles with ONE M = 256 instruction stream: each CTA generates the A operand of its own 128 rows and holds only
+// its half of the W columns, so the weight stream out of L2 and the tensor core's B reads per SM are halved.
+template <int NCTA> struct Cfg {
+  static constexpr int BN = TCN / NCTA;                     // W columns held by one CTA
+  static constexpr int B_LBO = BN * 16;                     // bytes between core matrices adjacent in K (B operand)
+  static constexpr int B_BYTES = NKB * B_LBO;               // one of {hi, lo} of a full chunk
+  static constexpr int WST = NCTA == 1 ? 3 : 5;             // W stages in shared memory
+  static constexpr int STAGE_BYTES = 2 * B_BYTES;           // Bhi, Blo of one K chunk
+  static constexpr int CHUNK_IMG_BYTES = NCTA * 2 * B_BYTES;      // one full chunk of the W image (all CTAs)
+  // kind::tf32, fp32 accumulate, A and B K-major, M = 128 * NCTA, N = 208
+  static constexpr uint32_t IDESC =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)((TCM * NCTA) >> 4) << 24);
+};
+// W operand image in global memory: per chunk, per CTA of the pair, [hi: kb][n (BN)][4 floats] then [lo: ...]
 __host__ __device__ constexpr int chunk_kw(int K, int c) { return (K - c * KCH) < KCH ? (K - c * KCH) : KCH; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -40,15 +55,37 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((SBO >> 4) & 0x3FFFu) << 32) | (1ull << 46);        // version 1 (Blackwell), no swizzle
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 208
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
-
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
-      : "memory");
+// D[tmem] (+)= A[tmem] . B[smem]: A is [128 lanes = rows][8 columns = k] of tensor memory (of each CTA of a pair)
+template <int NCTA>
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+  if constexpr (NCTA == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(Cfg<1>::IDESC), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(Cfg<2>::IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+// all MMAs issued so far by this thread have completed -> one arrival on the barrier (of every CTA of the pair)
+template <int NCTA>
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  if constexpr (NCTA == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -68,6 +105,36 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) return true;
   }
   return false;
+}
+// the same for a barrier that peer-CTA threads arrive on
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -96,8 +163,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 // HBM traffic per environment: x_n, three [N,N] adjacencies, pooled row in; 5N floats out.
 namespace fused {
 
-constexpr int FTHREADS = 288;                              // warps 0-7: operand generators + epilogue; warp 8: TMA + MMA issuer
-constexpr int LDH = 212;                                   // padded row length of the H tile
+constexpr int FTHREADS = 320;                              // warps 0-7: operand generators + epilogue; warp 8: MMA issuer
+                                                           // (peer CTA: W-landed forwarder); warp 9: W producer (TMA)
+constexpr int LDH = 204;                                   // padded row length of the H tile
 constexpr int NGEMM = 7;
 constexpr int KH = 200;
 
@@ -120,18 +188,21 @@ struct Params {
   int* error_flag;
 };
 
-template <int NODES>
+template <int NODES, int NCTA>
 __host__ __device__ constexpr int fused_smem_bytes() {
-  return STAGES * STAGE_BYTES + TCM * LDH * 4 + (TCM / NODES) * NODES * NODES * 4 + NODES * NODES * 4 +
-         14 * 208 * 4 + (TCM / NODES) * 208 * 4 + 64 * 4 * 4 + 128;
+  return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + (TCM / NODES) * NODES * NODES * 4 + NODES * NODES * 4 +
+         14 * 208 * 4 + (TCM / NODES) * 208 * 4 + 64 * 4 * 4 + 256;
 }
 
-template <int NODES>
+template <int NODES, int NCTA>
 __global__ void __launch_bounds__(FTHREADS, 1)
 actor_fused_kernel(const Params P) {
   constexpr int ENVS = TCM / NODES;
+  constexpr int WST = Cfg<NCTA>::WST, STAGE_BYTES = Cfg<NCTA>::STAGE_BYTES;
+  constexpr int B_LBO = Cfg<NCTA>::B_LBO;
+  static_assert(WST * STAGE_BYTES >= 64 * LDT * 4, "the epilogue tile aliases the W stages");
   extern __shared__ __align__(128) unsigned char smem[];
-  float* H = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // [128][LDH]
+  float* H = reinterpret_cast<float*>(smem + WST * STAGE_BYTES);             // [128][LDH]
   float* Ad = H + TCM * LDH;                                                 // [ENVS][N(j)][N(i)] adjacency of the current GEMM
   float* An = Ad + ENVS * NODES * NODES;                                     // [N(j)][N(i)] shared A_n, transposed
   float* W1s = An + NODES * NODES;                                           // [14][208] layer-1 kernel + bias row of the current GEMM;
@@ -140,29 +211,49 @@ actor_fused_kernel(const Params P) {
   float* Zs = reinterpret_cast<float*>(smem);                                // [128][16], only until the first stage fill
   float* Us = Pl + ENVS * 208;                                               // [64][4] head pre-activations
   uint64_t* bars = reinterpret_cast<uint64_t*>(Us + 64 * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   float* Ts = reinterpret_cast<float*>(smem);                                // [64][LDT], aliases the stages
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TCM;
   const int env0 = row0 / NODES;
   const int M = P.M;
-  // mbarriers: [0,1] W chunk landed (TMA tx)  [2,3] stage consumed (tcgen05.commit)
-  //            [4,5] A operand written (one arrive per generator warp)  [6] accumulator complete
-  const uint32_t bar_b0 = smem_u32(&bars[0]), bar_m0 = smem_u32(&bars[2]), bar_a0 = smem_u32(&bars[4]);
-  const uint32_t bar_acc = smem_u32(&bars[6]);
-  const bool is_issuer = (warp == 8);
+  // mbarriers.  W ring (stage s < WST):   bar_b0+8s  this CTA's W half landed (TMA tx)
+  //                                       bar_p0+8s  the peer CTA's W half landed (leader's copy, peer arrives)
+  //                                       bar_m0+8s  W stage consumed (tcgen05.commit, multicast to the pair)
+  //             A ring (stage s < AST):   bar_a0+8s  A operand written to tensor memory (leader's copy: one arrive
+  //                                                  per generator warp of every CTA of the pair)
+  //                                       bar_e0+8s  A stage consumed (tcgen05.commit, multicast)
+  //             bar_acc                              accumulator complete
+  const uint32_t bar_b0 = smem_u32(&bars[0]), bar_p0 = smem_u32(&bars[5]), bar_m0 = smem_u32(&bars[10]);
+  const uint32_t bar_a0 = smem_u32(&bars[15]), bar_e0 = smem_u32(&bars[20]), bar_acc = smem_u32(&bars[25]);
+  const bool is_issuer = (warp == 8), is_producer = (warp == 9);
+  const uint32_t cta_rank = (NCTA == 1) ? 0u : cluster_ctarank();
+  const bool is_leader = (cta_rank == 0);
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (NCTA == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   if (tid == 32) {
-    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);
-    mbar_init(bar_a0, 8);
-    mbar_init(bar_a0 + 8, 8);
+    for (int s = 0; s < WST; ++s) {
+      mbar_init(bar_b0 + 8 * s, 1);
+      mbar_init(bar_p0 + 8 * s, 1);
+      mbar_init(bar_m0 + 8 * s, 1);
+    }
+    for (int s = 0; s < AST; ++s) {
+      mbar_init(bar_a0 + 8 * s, 8 * NCTA);
+      mbar_init(bar_e0 + 8 * s, 1);
+    }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -177,6 +268,7 @@ actor_fused_kernel(const Params P) {
     Xraw[idx] = (row0 + idx / 13 < M) ? P.x_n[(size_t)row0 * 13 + idx] : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();               // the peer's barriers are initialised before any remote arrive
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   // Z = A_n . x_n  (gcn_l1_k share the input and the adjacency, so the product is formed once)
@@ -188,7 +280,7 @@ actor_fused_kernel(const Params P) {
     Zs[idx] = z;
   }
   __syncthreads();
-  const int lr = tid % TCM, lkb = tid / TCM;                 // loader role: row lr, core columns lkb and lkb + 2
+  const int lr = tid % TCM, lkb = (tid / TCM) & 1;           // generator role: row lr, k = 8 * lkb .. 8 * lkb + 7 of a chunk
   float zr[13];
 #pragma unroll
   for (int i = 0; i < 13; ++i) zr[i] = Zs[lr * 16 + i];
@@ -213,30 +305,30 @@ actor_fused_kernel(const Params P) {
     }
     return *reinterpret_cast<const float4*>(H + lr * LDH + k);
   };
-  auto split_store = [&](int stage, int kb, const float4& v) {
-    unsigned char* Ahi = smem + stage * STAGE_BYTES;
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-    *reinterpret_cast<float4*>(Ahi + kb * A_LBO + lr * 16) = h;
-    *reinterpret_cast<float4*>(Ahi + A_BYTES + kb * A_LBO + lr * 16) = l;
-  };
+  // 3xTF32 split of 8 consecutive k of row lr, written to A stage `stage` of tensor memory
   auto fill_stage = [&](int g, int c, int stage) {
-    const int nkb = chunk_kw(KH, c) / 4;
+    if (8 * lkb < chunk_kw(KH, c)) {                         // warp-uniform (tail chunk: k-step 0 only)
+      const float4 v0 = gen_a(g, c * KCH + 8 * lkb), v1 = gen_a(g, c * KCH + 8 * lkb + 4);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float hi[8], lo[8];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int kb = lkb + 2 * q;
-      if (kb < nkb) split_store(stage, kb, gen_a(g, c * KCH + 4 * kb));
+      for (int i = 0; i < 8; ++i) {
+        hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+        lo[i] = v[i] - hi[i];
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(TM_A0 + 32 * stage + 8 * lkb);
+      tmem_st8(taddr, hi);
+      tmem_st8(taddr + 16, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
   };
   auto issue_w = [&](int g, int c, int stage) {
-    const uint32_t bytes = 2u * (chunk_kw(KH, c) / 4) * B_LBO;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg[g]) + (size_t)c * (2u * NKB * B_LBO);
+    const uint32_t bytes = 2u * (chunk_kw(KH, c) / 4) * B_LBO;                  // this CTA's half: hi then lo
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg[g]) +
+                               (size_t)c * Cfg<NCTA>::CHUNK_IMG_BYTES + (size_t)cta_rank * bytes;
     const uint32_t bar = bar_b0 + 8 * stage;
     mbar_expect_tx(bar, bytes);
-    bulk_g2s(smem_u32(smem + stage * STAGE_BYTES + 2 * A_BYTES), src, bytes, bar);
+    bulk_g2s(smem_u32(smem + stage * STAGE_BYTES), src, bytes, bar);
   };
 
   // ---- per-GEMM small operands: adjacency tile (<= 8 floats per thread), layer-1 kernel + bias or head
@@ -304,9 +396,15 @@ actor_fused_kernel(const Params P) {
 
 #ifdef DEBUG_TIMING
   const long long Tstart = clock64();
+  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define DBG_T(x) const long long x = clock64()
+#define DBG_ACC(i, v) dbg_acc[i] += (v)
+#else
+#define DBG_T(x)
+#define DBG_ACC(i, v)
 #endif
   constexpr int NCH = (KH + KCH - 1) / KCH;                  // 13 chunks per GEMM
-  uint32_t use = 0;                                          // running count of stage uses (both barriers flip per use)
+  uint32_t use = 0;                                          // running count of chunks: W stage = use % WST, A stage = use % AST
   bool ok = true;
   const int cq = tid % 52, gq = tid / 52;                    // epilogue role (tid < 208): rows 16*gq.., columns 4*cq..
 
@@ -322,68 +420,98 @@ actor_fused_kernel(const Params P) {
 #ifdef DEBUG_TIMING
     const long long T1 = clock64();
 #endif
-    // ---- main loop, warp-specialised: generators fill the A operand two chunks ahead, the issuer warp
-    //      streams the W chunks (TMA) and issues the MMAs; the only hand-offs are mbarriers ----
+    // ---- main loop, warp-specialised; the only hand-offs are mbarriers.  For the running chunk count u: W stage
+    //      u % WST (phase parity (u / WST) & 1), A stage u % AST (parity (u / AST) & 1).
+    //        generators (warps 0-7)   A operand of chunk c -> tensor memory, up to AST chunks ahead
+    //        producer   (warp 9)      this CTA's W half of chunk c -> shared memory (TMA), up to WST chunks ahead
+    //        issuer     (warp 8)      leader CTA: MMAs of the whole pair;  peer CTA: forwards "my W half landed" ----
     const uint32_t use0 = use;
-    if (is_issuer) {
+    if (is_producer) {
       if (lane == 0) {
-        // Measured with clock64 (round 1): issuing is latency-bound on this one thread, so the operand
-        // descriptors are formed outside the loop, and the W chunk for c+1 is requested BEFORE the MMAs of
-        // chunk c are issued so that it has a whole iteration to land.
-        uint64_t da[2][2][2], db[2][2][2];                   // [stage][k-step][hi, lo]
-#pragma unroll
-        for (int st = 0; st < 2; ++st)
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES) + 2 * ks * A_LBO;
-            const uint32_t b_hi = smem_u32(smem + st * STAGE_BYTES) + 2 * A_BYTES + 2 * ks * B_LBO;
-            da[st][ks][0] = make_desc(a_hi, A_LBO);
-            da[st][ks][1] = make_desc(a_hi + A_BYTES, A_LBO);
-            db[st][ks][0] = make_desc(b_hi, B_LBO);
-            db[st][ks][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);      // lo half of a full chunk
-          }
-        issue_w(g, 0, use0 & 1);
         for (int c = 0; c < NCH; ++c) {
-          const uint32_t u = use0 + c, s = u & 1, parity = (u >> 1) & 1;
-          if (c + 1 < NCH) {
-            // W chunk c+1 goes into the other stage: its previous user (chunk c-1) must have been consumed
-            if (c >= 1) ok = mbar_wait(bar_m0 + 8 * (s ^ 1), ((u - 1) >> 1) & 1) && ok;
-            issue_w(g, c + 1, s ^ 1);
+          const uint32_t u = use0 + c, s = u % WST;
+          DBG_T(t0);
+          if (c >= WST) ok = mbar_wait(bar_m0 + 8 * s, ((u / WST) - 1) & 1) && ok;    // chunk c-WST consumed
+          DBG_T(t1);
+          issue_w(g, c, s);
+          DBG_T(t2);
+          DBG_ACC(3, t1 - t0); DBG_ACC(4, t2 - t1);
+        }
+      }
+      __syncwarp();
+    } else if (is_issuer) {
+      if (lane == 0) {
+        if (is_leader) {
+          uint64_t db[WST][2][2];                            // [stage][k-step][hi, lo] of a full chunk
+#pragma unroll
+          for (int st = 0; st < WST; ++st)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t b_hi = smem_u32(smem + st * STAGE_BYTES) + 2 * ks * B_LBO;
+              db[st][ks][0] = make_desc(b_hi, B_LBO);
+              db[st][ks][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);
+            }
+          for (int c = 0; c < NCH; ++c) {
+            const uint32_t u = use0 + c, sw = u % WST, sa = u % AST;
+            DBG_T(t0);
+            ok = mbar_wait_cluster(bar_a0 + 8 * sa, (u / AST) & 1) && ok;
+            DBG_T(t1);
+            ok = mbar_wait(bar_b0 + 8 * sw, (u / WST) & 1) && ok;
+            if constexpr (NCTA == 2) ok = mbar_wait_cluster(bar_p0 + 8 * sw, (u / WST) & 1) && ok;
+            DBG_T(t2);
+            DBG_ACC(0, t1 - t0); DBG_ACC(1, t2 - t1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int kw = chunk_kw(KH, c);
+            const uint32_t a_hi = tmem_base + (uint32_t)(TM_A0 + 32 * sa), a_lo = a_hi + 16;
+#pragma unroll
+            for (int st = 0; st < WST; ++st) {
+              if (st != (int)sw) continue;                   // compile-time stage index keeps the descriptors in registers
+              if (kw == KCH) {
+                mma_tf32<NCTA>(tmem_base, a_hi, db[st][0][0], c != 0);
+                mma_tf32<NCTA>(tmem_base, a_hi, db[st][0][1], 1);
+                mma_tf32<NCTA>(tmem_base, a_lo, db[st][0][0], 1);
+                mma_tf32<NCTA>(tmem_base, a_hi + 8, db[st][1][0], 1);
+                mma_tf32<NCTA>(tmem_base, a_hi + 8, db[st][1][1], 1);
+                mma_tf32<NCTA>(tmem_base, a_lo + 8, db[st][1][0], 1);
+              } else {                                       // tail chunk: one k-step, lo half right after hi
+                const uint64_t dbl = make_desc(smem_u32(smem + st * STAGE_BYTES) + (kw / 4) * B_LBO, B_LBO);
+                mma_tf32<NCTA>(tmem_base, a_hi, db[st][0][0], c != 0);
+                mma_tf32<NCTA>(tmem_base, a_hi, dbl, 1);
+                mma_tf32<NCTA>(tmem_base, a_lo, db[st][0][0], 1);
+              }
+            }
+            mma_commit<NCTA>(bar_m0 + 8 * sw);
+            mma_commit<NCTA>(bar_e0 + 8 * sa);
+            if (c + 1 == NCH) mma_commit<NCTA>(bar_acc);
+            DBG_T(t3);
+            DBG_ACC(2, t3 - t2);
           }
-          ok = mbar_wait(bar_a0 + 8 * s, parity) && ok;
-          ok = mbar_wait(bar_b0 + 8 * s, parity) && ok;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int kw = chunk_kw(KH, c);
-          if (kw == KCH) {
-            mma_tf32(tmem_base, da[s][0][0], db[s][0][0], c != 0);
-            mma_tf32(tmem_base, da[s][0][0], db[s][0][1], 1);
-            mma_tf32(tmem_base, da[s][0][1], db[s][0][0], 1);
-            mma_tf32(tmem_base, da[s][1][0], db[s][1][0], 1);
-            mma_tf32(tmem_base, da[s][1][0], db[s][1][1], 1);
-            mma_tf32(tmem_base, da[s][1][1], db[s][1][0], 1);
-          } else {                                           // tail chunk: one k-step, lo half right after hi
-            const uint32_t b_hi = smem_u32(smem + s * STAGE_BYTES) + 2 * A_BYTES;
-            const uint64_t dbl = make_desc(b_hi + (kw / 4) * B_LBO, B_LBO);
-            mma_tf32(tmem_base, da[s][0][0], db[s][0][0], c != 0);
-            mma_tf32(tmem_base, da[s][0][0], dbl, 1);
-            mma_tf32(tmem_base, da[s][0][1], db[s][0][0], 1);
+        } else {
+          for (int c = 0; c < NCH; ++c) {                    // peer CTA: tell the leader that W chunk c has landed here
+            const uint32_t u = use0 + c, sw = u % WST;
+            ok = mbar_wait(bar_b0 + 8 * sw, (u / WST) & 1) && ok;
+            mbar_arrive_remote(bar_p0 + 8 * sw, 0);
           }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_m0 + 8 * s)
-                       : "memory");
-          if (c + 1 == NCH)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc)
-                         : "memory");
         }
       }
       __syncwarp();
     } else {
       for (int c = 0; c < NCH; ++c) {
-        const uint32_t u = use0 + c, s = u & 1;
-        if (c >= 2) ok = mbar_wait(bar_m0 + 8 * s, ((u - 2) >> 1) & 1) && ok;   // chunk c-2 consumed
-        fill_stage(g, c, s);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t u = use0 + c, sa = u % AST;
+        DBG_T(t0);
+        if (c >= AST) ok = mbar_wait(bar_e0 + 8 * sa, ((u / AST) - 1) & 1) && ok;     // chunk c-AST consumed
+        DBG_T(t1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        fill_stage(g, c, sa);
+        DBG_T(t2);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a0 + 8 * s) : "memory");
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(bar_a0 + 8 * sa);
+          else mbar_arrive_remote(bar_a0 + 8 * sa, 0);
+        }
+        DBG_T(t3);
+        DBG_ACC(5, t1 - t0); DBG_ACC(6, t2 - t1); DBG_ACC(7, t3 - t2);
       }
     }
     use = use0 + NCH;
@@ -442,7 +570,7 @@ actor_fused_kernel(const Params P) {
           for (int cidx = 0; cidx < 4; ++cidx) acc[i][cidx] = fmaxf(acc[i][cidx] + bb[cidx], 0.f);
       }
       if (g <= 4) {
-        if (tid < 208) {
+        if (tid < 208 && 4 * cq < LDH) {                      // the last column group is padding beyond the H row
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float4* dst = reinterpret_cast<float4*>(H + (rt + i) * LDH + 4 * cq);
@@ -484,19 +612,25 @@ actor_fused_kernel(const Params P) {
         }
       }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // Ts (generic proxy) before the next TMA writes into the stages
     __syncthreads();                                         // H / Ts settled before the next GEMM refills the stages
 #ifdef DEBUG_TIMING
-    if (blockIdx.x == 200 && (tid == 0 || tid == 256)) {
-      long long* dbg = reinterpret_cast<long long*>(P.error_flag) + 16 + (tid ? 64 : 0);
+    if (blockIdx.x == 200 && (tid == 0 || tid == 256 || tid == 288)) {
+      long long* dbg = reinterpret_cast<long long*>(P.error_flag) + 16 + (tid == 0 ? 0 : tid == 256 ? 128 : 256);
       dbg[g * 4 + 0] = T1 - T0; dbg[g * 4 + 1] = T2 - T1; dbg[g * 4 + 2] = clock64() - T2; dbg[g * 4 + 3] = T0 - Tstart;
+      for (int i = 0; i < 8; ++i) dbg[32 + g * 8 + i] = dbg_acc[i];      // cumulative over GEMMs 0..g
     }
 #endif
   }
   if (!ok && P.error_flag) atomicExch(P.error_flag, 1);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();               // neither CTA leaves while the pair's TMEM / barriers are in use
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if constexpr (NCTA == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
