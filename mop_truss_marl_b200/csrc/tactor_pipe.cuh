@@ -1,0 +1,559 @@
+// Whole-network fused actor kernel, fully pipelined ("pipe") formulation.
+//
+// One CTA (or CTA pair, NCTA = 2) carries a 128-row tile (ENVS environments of NODES nodes) through all 13
+// GCNConv layers of multimodes_actor.call (train/code/truss2D_RL.py:75-127).  Compared with the first fused
+// kernel the adjacency product is moved IN FRONT of the dense contraction,
+//
+//      A_g . (X_g . W_g) + b_g   ==   (A_g . X_g) . W_g + b_g          (spektral GCNConv, associativity)
+//
+// so that the tensor-core epilogue is row-local (bias, ReLU, accumulate) and three groups of warps can run
+// concurrently, coupled only by mbarriers:
+//
+//   generators  warps 0-15   row r = 32*(warp&3)+lane, k-quarter (warp>>2) of every 16-wide K chunk:
+//                            x = layer-1 activations / Pareto embedding / H  ->  y = sum_j A_g[r,j] x[j]
+//                            (neighbour rows live in the same warp: exchange through a warp-private tile,
+//                            __syncwarp only; <= 8 neighbours per row go through a compacted list, denser rows
+//                            through the full row)  ->  3xTF32 split  ->  tcgen05.st into the A stage (TMEM)
+//   producer    warp 21      streams the pre-split W chunks into shared memory (cp.async.bulk, mbarrier tx),
+//                            running ahead across GEMM boundaries
+//   issuer      warp 20      tcgen05.mma kind::tf32, A from tensor memory, B from shared memory, accumulator
+//                            g&1 of two (TMEM columns [0,208) and [256,464))
+//   epilogue    warps 16-19  tcgen05.ld the finished accumulator while the next GEMM is already running:
+//                            relu(D + b) -> H (+)= (g <= 4), or the sigmoid heads gcn_l4_1/2 (g = 5, 6)
+//
+// TMEM map (512 columns): [0,208) acc0 | [208,256) A stages hi (3 x 16) | [256,464) acc1 | [464,512) A stages lo
+#pragma once
+#include "tactor_tc.cuh"
+
+namespace tactor {
+namespace tc {
+namespace pipe {
+
+using fused::Params;
+using fused::NGEMM;
+using fused::KH;
+
+constexpr int PTHREADS = 704;
+constexpr int NGENW = 16, NEPIW = 4, W_ISSUER = 20, W_PRODUCER = 21;
+constexpr int KPT = 4;                                      // k values per generator thread and chunk
+constexpr int PAST = 3;                                     // A-operand stages in tensor memory
+constexpr int TM_ACC1 = 256, TM_AHI = 208, TM_ALO = 464;
+constexpr int LDH = 204;                                    // padded row length of the H tile (12 r mod 32 distinct for 8 rows)
+constexpr int LDX = 4;                                      // row length of the warp-private exchange tile
+constexpr int NCH = (KH + KCH - 1) / KCH;                   // 13 chunks per GEMM
+constexpr int DMAX = 8;                                     // neighbour slots of the compacted adjacency row
+
+template <int NODES, int NCTA>
+__host__ __device__ constexpr int pipe_smem_bytes() {
+  return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + NGENW * 32 * LDX * 4 + 14 * 208 * 4 +
+         (TCM / NODES) * 208 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + NGEMM * 208 * 4 + 256;
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+}
+// tcgen05.ld of 8 accumulator columns without the wait (software pipelining in the epilogue)
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int NODES, int NCTA>
+__global__ void __launch_bounds__(PTHREADS, 1)
+actor_pipe_kernel(const Params P) {
+  constexpr int ENVS = TCM / NODES;
+  constexpr int WST = Cfg<NCTA>::WST, STAGE_BYTES = Cfg<NCTA>::STAGE_BYTES, B_LBO = Cfg<NCTA>::B_LBO;
+  static_assert(pipe_smem_bytes<NODES, NCTA>() <= 232448, "shared memory budget");
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* H = reinterpret_cast<float*>(smem + WST * STAGE_BYTES);             // [128][LDH]
+  float* Xt = H + TCM * LDH;                                                 // [8 warps][32][LDX] exchange tiles
+  float* W1s = Xt + NGENW * 32 * LDX;                                        // [14][208] layer-1 kernel + bias row
+  float* Pl = W1s + 14 * 208;                                                // [ENVS][208] pooled Pareto embedding
+  float* AnT = Pl + ENVS * 208;                                              // [N(j)][N(n)] shared A_n, transposed
+  float* Wh = AnT + NODES * NODES;                                           // [2][201][4] head kernels, row 200 = bias
+  float* Us = Wh + 2 * 201 * 4;                                              // [128][4] head pre-activations
+  float* Bs = Us + TCM * 4;                                                  // [7][208] biases of the hidden layers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + NGEMM * 208);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * TCM;
+  const int env0 = row0 / NODES;
+  const int M = P.M;
+  // W ring (s < WST):  w_full  this CTA's W half landed (TMA tx)       w_peer  the peer's half landed (leader's copy)
+  //                    w_empty stage consumed (tcgen05.commit, multicast to the pair)
+  // A ring (s < PAST): a_full  A stage written (leader's copy; one arrive per generator warp of the pair)
+  //                    a_empty stage consumed (commit)
+  // acc_full[b] accumulator b complete (commit)   acc_empty[b] drained by the epilogue warps (leader's copy)
+  // h_ready     the five-way sum H is complete (epilogue of GEMM 4 -> generators of GEMM 5)
+  const uint32_t w_full = smem_u32(&bars[0]), w_peer = smem_u32(&bars[5]), w_empty = smem_u32(&bars[10]);
+  const uint32_t a_full = smem_u32(&bars[15]), a_empty = smem_u32(&bars[18]);
+  const uint32_t acc_full = smem_u32(&bars[21]), acc_empty = smem_u32(&bars[23]), h_ready = smem_u32(&bars[25]);
+  const uint32_t cta_rank = (NCTA == 1) ? 0u : cluster_ctarank();
+  const bool is_leader = (cta_rank == 0);
+
+  if (warp == 0) {
+    if constexpr (NCTA == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  if (tid == 32) {
+    for (int s = 0; s < WST; ++s) {
+      mbar_init(w_full + 8 * s, 1);
+      mbar_init(w_peer + 8 * s, 1);
+      mbar_init(w_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < PAST; ++s) {
+      mbar_init(a_full + 8 * s, NGENW * NCTA);
+      mbar_init(a_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full + 8 * b, 1);
+      mbar_init(acc_empty + 8 * b, NEPIW * NCTA);
+    }
+    mbar_init(h_ready, NEPIW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // tile constants: A_n (transposed), pooled rows, head kernels, first layer-1 kernel, raw x_n rows (staged in H,
+  // which is not written before the first epilogue)
+  for (int idx = tid; idx < NODES * NODES; idx += PTHREADS) AnT[(idx % NODES) * NODES + idx / NODES] = P.A_n[idx];
+  for (int idx = tid; idx < ENVS * 208; idx += PTHREADS) {
+    const int env = env0 + idx / 208;
+    Pl[idx] = (env * NODES < M) ? P.pooled[(size_t)env * 208 + idx % 208] : 0.f;
+  }
+  for (int idx = tid; idx < 2 * 201; idx += PTHREADS) {
+    const int hd = idx / 201, k = idx % 201;
+    reinterpret_cast<float4*>(Wh)[idx] = (k < KH) ? __ldg(reinterpret_cast<const float4*>(P.w_head[hd] + (size_t)k * 208))
+                                                  : __ldg(reinterpret_cast<const float4*>(P.b_head[hd]));
+  }
+  for (int idx = tid; idx < 14 * 52; idx += PTHREADS)
+    reinterpret_cast<float4*>(W1s)[idx] = (idx < 13 * 52) ? __ldg(reinterpret_cast<const float4*>(P.w1[0]) + idx)
+                                                          : __ldg(reinterpret_cast<const float4*>(P.b1[0]) + (idx - 13 * 52));
+  for (int idx = tid; idx < NGEMM * 52; idx += PTHREADS)
+    reinterpret_cast<float4*>(Bs)[idx] = __ldg(reinterpret_cast<const float4*>(P.bias[idx / 52]) + idx % 52);
+  float* Xraw = H;                                                           // [128][13]
+  for (int idx = tid; idx < TCM * 13; idx += PTHREADS)
+    Xraw[idx] = (row0 + idx / 13 < M) ? P.x_n[(size_t)row0 * 13 + idx] : 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  bool ok = true;
+#ifdef DEBUG_TIMING
+  // per role (generator warp 0, first epilogue warp, issuer) and GEMM: 8 cycle counters
+  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long Tstart = clock64();
+#define PDBG_T(x) const long long x = clock64()
+#define PDBG_ACC(i, v) dbg_acc[i] += (v)
+#define PDBG_FLUSH(role, g)                                                                         \
+  if (blockIdx.x == 200 && lane == 0) {                                                             \
+    long long* dbg = reinterpret_cast<long long*>(P.error_flag) + 16 + (role) * 64 + (g) * 8;      \
+    for (int i = 0; i < 7; ++i) { dbg[i] = dbg_acc[i]; dbg_acc[i] = 0; }                             \
+    dbg[7] = clock64() - Tstart;                                                                    \
+  }
+#else
+#define PDBG_T(x)
+#define PDBG_ACC(i, v)
+#define PDBG_FLUSH(role, g)
+#endif
+
+  if (warp < NGENW) {
+    // =================================================== generators ===========================================
+    const int q = warp & 3, kq = warp >> 2;
+    const int r = 32 * q + lane;                             // row of the tile
+    const int e = r / NODES, n = r % NODES;
+    const int lane_env0 = lane & ~(NODES - 1);               // first lane of this row's environment inside the warp
+    const bool env_valid = (env0 + e) * NODES < M;
+    float* xt = Xt + warp * 32 * LDX;                        // warp-private exchange tile
+    // Z = A_n . x_n (gcn_l1_1..3 share input and adjacency: formed once, kept in registers)
+    float z[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) z[i] = 0.f;
+    for (int j = 0; j < NODES; ++j) {
+      const float a = AnT[j * NODES + n];
+      const float* xr = Xraw + (e * NODES + j) * 13;
+#pragma unroll
+      for (int i = 0; i < 13; ++i) z[i] = fmaf(a, xr[i], z[i]);
+    }
+    // Sparsity pattern of this row, once per tile: the normalised adjacency A_n (adjacency + self loops) bounds the
+    // pattern of A_s / A_n_ts / A_n_cs in every reference family.  If a row has more than DMAX entries, or a
+    // per-environment matrix has an entry outside A_n's pattern, the warp uses the full row instead ("dense").
+    float coef[DMAX];
+    uint64_t nidx_packed = 0;                                // 8 neighbour lane ids, one byte each
+    uint32_t mask_n = 0;
+#pragma unroll 8
+    for (int j = 0; j < NODES; ++j) mask_n |= (AnT[j * NODES + n] != 0.f) ? (1u << j) : 0u;
+    const int cnt = __popc(mask_n);
+    uint32_t mask_o = 0;
+    if (env_valid) {
+      const size_t ro = ((size_t)(env0 + e) * NODES + n) * NODES;
+      const float4* r0 = reinterpret_cast<const float4*>(P.A_s + ro);
+      const float4* r1 = reinterpret_cast<const float4*>(P.A_ts + ro);
+      const float4* r2 = reinterpret_cast<const float4*>(P.A_cs + ro);
+#pragma unroll
+      for (int j4 = 0; j4 < NODES / 4; ++j4) {               // independent 128-bit loads, compared afterwards
+        const float4 a = __ldg(r0 + j4), b = __ldg(r1 + j4), c = __ldg(r2 + j4);
+        const uint32_t m = ((a.x != 0.f) | (b.x != 0.f) | (c.x != 0.f)) | (((a.y != 0.f) | (b.y != 0.f) | (c.y != 0.f)) << 1) |
+                           (((a.z != 0.f) | (b.z != 0.f) | (c.z != 0.f)) << 2) | (((a.w != 0.f) | (b.w != 0.f) | (c.w != 0.f)) << 3);
+        mask_o |= m << (4 * j4);
+      }
+    }
+    const bool dense = __any_sync(0xffffffffu, cnt > DMAX || (mask_o & ~mask_n) != 0u);
+    const int dcnt = min(__reduce_max_sync(0xffffffffu, cnt), DMAX);       // neighbour slots in use (largest row of the warp)
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) {
+      const int j = (d < cnt) ? (int)__fns(mask_n, 0, d + 1) : n;
+      nidx_packed |= (uint64_t)(lane_env0 + j) << (8 * d);
+    }
+    // adjacency row of this thread for GEMM g (element j at arow[j * astride]); rows past the batch read A_n
+    auto row_of = [&](int g, const float*& rowp, int& stride) {
+      const float* adj = (g == 1) ? P.A_ts : (g == 2) ? P.A_cs : (g == 3 || g == 6) ? P.A_s : nullptr;
+      if (adj != nullptr && env_valid) { rowp = adj + ((size_t)(env0 + e) * NODES + n) * NODES; stride = 1; }
+      else { rowp = AnT + n; stride = NODES; }
+    };
+    auto load_coefs = [&](int g, float* dst) {
+      const float* rowp; int stride;
+      row_of(g, rowp, stride);
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) {
+        const int j = (int)((nidx_packed >> (8 * d)) & 0xff) - lane_env0;
+        dst[d] = (d < cnt) ? rowp[j * stride] : 0.f;
+      }
+    };
+    const float* arow = nullptr;
+    int astride = 1;
+    // the next GEMM's small operands are pulled into L1 one GEMM ahead (no registers held across the chunk loop)
+    auto w1_src = [&](int l1, int idx) -> const float4* {
+      return (idx < 13 * 52) ? reinterpret_cast<const float4*>(P.w1[l1]) + idx
+                             : reinterpret_cast<const float4*>(P.b1[l1]) + (idx - 13 * 52);
+    };
+    for (int g = 0; g < NGEMM; ++g) {
+      PDBG_T(tg0);
+      // ---- per-GEMM setup ----
+      if (g == 1 || g == 3) {                                // g = 2 reuses gcn_l1_2's kernel
+        const int l1 = (g == 1) ? 1 : 2;
+        float4 wreg[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int idx = tid + t * NGENW * 32;
+          wreg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < 14 * 52) wreg[t] = __ldg(w1_src(l1, idx));
+        }
+        named_bar_sync(1, NGENW * 32);                       // all generators are done reading the old kernel
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int idx = tid + t * NGENW * 32;
+          if (idx < 14 * 52) reinterpret_cast<float4*>(W1s)[idx] = wreg[t];
+        }
+        named_bar_sync(1, NGENW * 32);
+      }
+      load_coefs(g, coef);
+      row_of(g, arow, astride);
+      if (g + 1 < NGEMM) {                                   // prefetch for the next GEMM
+        const float* rowp; int stride;
+        row_of(g + 1, rowp, stride);
+        if (stride == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp));
+        if (NODES == 32 && stride == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp + 16));
+        if (g == 0 || g == 2) {
+          const int l1 = (g == 0) ? 1 : 2;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int idx = tid + t * NGENW * 32;
+            if (idx < 14 * 52) asm volatile("prefetch.global.L1 [%0];" ::"l"(w1_src(l1, idx)));
+          }
+        }
+      }
+      PDBG_T(tg1);
+      if (g == 5) { ok = mbar_wait(h_ready, 0) && ok; }      // H complete (epilogue of GEMM 4)
+      PDBG_T(tg2);
+      PDBG_ACC(0, tg1 - tg0); PDBG_ACC(1, tg2 - tg1);
+      // ---- 13 chunks: generate, mix with the adjacency, split, store to tensor memory ----
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t u = (uint32_t)(g * NCH + c), sa = u % PAST;
+        PDBG_T(t0);
+        if (u >= PAST) ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok;      // chunk u-PAST consumed
+        PDBG_T(t1);
+        PDBG_ACC(2, t1 - t0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int k0 = c * KCH + KPT * kq;
+        if (k0 < KH) {                                       // warp-uniform (tail chunk: k-quarters 0 and 1 only)
+          float y[KPT] = {0.f, 0.f, 0.f, 0.f};
+          if (g <= 4) {
+            float4 x;
+            if (g <= 3) {
+              x = *reinterpret_cast<const float4*>(W1s + 13 * 208 + k0);
+              float4 wa[7], wb[6];                           // two batches of loads in flight ahead of the FMAs
+#pragma unroll
+              for (int i = 0; i < 7; ++i) wa[i] = *reinterpret_cast<const float4*>(W1s + i * 208 + k0);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) wb[i] = *reinterpret_cast<const float4*>(W1s + (7 + i) * 208 + k0);
+#pragma unroll
+              for (int i = 0; i < 7; ++i) {
+                x.x = fmaf(z[i], wa[i].x, x.x); x.y = fmaf(z[i], wa[i].y, x.y); x.z = fmaf(z[i], wa[i].z, x.z); x.w = fmaf(z[i], wa[i].w, x.w);
+              }
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                x.x = fmaf(z[7 + i], wb[i].x, x.x); x.y = fmaf(z[7 + i], wb[i].y, x.y); x.z = fmaf(z[7 + i], wb[i].z, x.z); x.w = fmaf(z[7 + i], wb[i].w, x.w);
+              }
+              x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
+            } else {
+              // the reference's stack-and-reshape scramble: x14b[b,n,h] = pooled[b,(n*200+h)/N] (truss2D_RL.py:89-95)
+              const float* pl = Pl + e * 208;
+              const int f = n * KH + k0;
+              x = make_float4(pl[f / NODES], pl[(f + 1) / NODES], pl[(f + 2) / NODES], pl[(f + 3) / NODES]);
+            }
+            PDBG_T(tx);
+            PDBG_ACC(5, tx - t1);
+            *reinterpret_cast<float4*>(xt + lane * LDX) = x;
+            __syncwarp();
+            if (!dense) {
+#pragma unroll
+              for (int d = 0; d < DMAX; ++d) {
+                if (d >= dcnt) break;                        // warp-uniform
+                const float4 t0 = *reinterpret_cast<const float4*>(xt + (int)((nidx_packed >> (8 * d)) & 0xff) * LDX);
+                y[0] = fmaf(coef[d], t0.x, y[0]); y[1] = fmaf(coef[d], t0.y, y[1]); y[2] = fmaf(coef[d], t0.z, y[2]); y[3] = fmaf(coef[d], t0.w, y[3]);
+              }
+            } else {
+#pragma unroll 1
+              for (int j = 0; j < NODES; ++j) {
+                const float a = arow[j * astride];
+                const float4 t0 = *reinterpret_cast<const float4*>(xt + (lane_env0 + j) * LDX);
+                y[0] = fmaf(a, t0.x, y[0]); y[1] = fmaf(a, t0.y, y[1]); y[2] = fmaf(a, t0.z, y[2]); y[3] = fmaf(a, t0.w, y[3]);
+              }
+            }
+            __syncwarp();                                    // the tile is rewritten by the next chunk
+          } else {
+            // layer 3: the operand rows are rows of H (shared memory), no exchange tile needed
+            const float* hb = H + (32 * q) * LDH + k0;
+            if (!dense) {
+#pragma unroll
+              for (int d = 0; d < DMAX; ++d) {
+                if (d >= dcnt) break;                        // warp-uniform
+                const float4 t0 = *reinterpret_cast<const float4*>(hb + (int)((nidx_packed >> (8 * d)) & 0xff) * LDH);
+                y[0] = fmaf(coef[d], t0.x, y[0]); y[1] = fmaf(coef[d], t0.y, y[1]); y[2] = fmaf(coef[d], t0.z, y[2]); y[3] = fmaf(coef[d], t0.w, y[3]);
+              }
+            } else {
+#pragma unroll 1
+              for (int j = 0; j < NODES; ++j) {
+                const float a = arow[j * astride];
+                const float4 t0 = *reinterpret_cast<const float4*>(hb + (lane_env0 + j) * LDH);
+                y[0] = fmaf(a, t0.x, y[0]); y[1] = fmaf(a, t0.y, y[1]); y[2] = fmaf(a, t0.z, y[2]); y[3] = fmaf(a, t0.w, y[3]);
+              }
+            }
+          }
+          PDBG_T(t2);
+          PDBG_ACC(3, t2 - t1);
+          float hi[KPT], lo[KPT];
+#pragma unroll
+          for (int t = 0; t < KPT; ++t) {
+            hi[t] = __uint_as_float(__float_as_uint(y[t]) & 0xFFFFE000u);
+            lo[t] = y[t] - hi[t];
+          }
+          const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
+          tmem_st4(tmem_base + lane_sel + (uint32_t)(TM_AHI + 16 * sa + KPT * kq), hi);
+          tmem_st4(tmem_base + lane_sel + (uint32_t)(TM_ALO + 16 * sa + KPT * kq), lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          PDBG_T(t4);
+          PDBG_ACC(6, t4 - t2);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(a_full + 8 * sa);
+          else mbar_arrive_remote(a_full + 8 * sa, 0);
+        }
+        PDBG_T(t3);
+        PDBG_ACC(4, t3 - t1);
+      }
+      if (warp == 0) { PDBG_FLUSH(0, g); }
+    }
+  } else if (warp < NGENW + NEPIW) {
+    // =================================================== epilogue =============================================
+    const int q = warp & 3;
+    const int r = 32 * q + lane;
+    const int n = r % NODES;
+    const int lane_env0 = lane & ~(NODES - 1);
+    for (int g = 0; g < NGEMM; ++g) {
+      const int b = g & 1;
+      PDBG_T(t0);
+      ok = mbar_wait(acc_full + 8 * b, (uint32_t)((g >> 1) & 1)) && ok;
+      PDBG_T(t1);
+      PDBG_ACC(0, t1 - t0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b ? TM_ACC1 : 0);
+      const float* bias = Bs + g * 208;
+      float* hrow = H + r * LDH;
+      const float* wh = Wh + (g >= 5 ? g - 5 : 0) * 201 * 4; // only used for g >= 5
+      float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+      uint32_t vr[2][8];
+      tmem_ld8_async(tacc, vr[0]);
+#pragma unroll 2
+      for (int cb = 0; cb < KH / 8; ++cb) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * cb);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * cb + 4);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(vr[cb & 1][t]);
+        if (cb + 1 < KH / 8) tmem_ld8_async(tacc + (uint32_t)(8 * (cb + 1)), vr[(cb + 1) & 1]);   // in flight while cb is processed
+        v[0] = fmaxf(v[0] + b0.x, 0.f); v[1] = fmaxf(v[1] + b0.y, 0.f); v[2] = fmaxf(v[2] + b0.z, 0.f); v[3] = fmaxf(v[3] + b0.w, 0.f);
+        v[4] = fmaxf(v[4] + b1.x, 0.f); v[5] = fmaxf(v[5] + b1.y, 0.f); v[6] = fmaxf(v[6] + b1.z, 0.f); v[7] = fmaxf(v[7] + b1.w, 0.f);
+        if (g <= 4) {
+          float4* dst = reinterpret_cast<float4*>(hrow + 8 * cb);
+          float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+          if (g > 0) { o0 = dst[0]; o1 = dst[1]; }
+          dst[0] = make_float4(v[0] + o0.x, v[1] + o0.y, v[2] + o0.z, v[3] + o0.w);
+          dst[1] = make_float4(v[4] + o1.x, v[5] + o1.y, v[6] + o1.z, v[7] + o1.w);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float4 w = *reinterpret_cast<const float4*>(wh + (8 * cb + t) * 4);
+            u0 = fmaf(v[t], w.x, u0); u1 = fmaf(v[t], w.y, u1); u2 = fmaf(v[t], w.z, u2);
+          }
+        }
+      }
+      PDBG_T(t2);
+      PDBG_ACC(1, t2 - t1);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (is_leader) mbar_arrive(acc_empty + 8 * b);
+        else mbar_arrive_remote(acc_empty + 8 * b, 0);
+        if (g == 4) mbar_arrive(h_ready);
+      }
+      if (g >= 5) {
+        // output heads (truss2D_RL.py:121-125): sigmoid(A_n (x3 W4) + b4); the 16/32 rows of an environment are
+        // lanes of this warp
+        const int hd = g - 5, nout = 2 + hd;
+        *reinterpret_cast<float4*>(Us + r * 4) = make_float4(u0, u1, u2, 0.f);
+        __syncwarp();
+        float o[3] = {wh[KH * 4 + 0], wh[KH * 4 + 1], wh[KH * 4 + 2]};
+        for (int j = 0; j < NODES; ++j) {
+          const float a = AnT[j * NODES + n];
+          const float4 uj = *reinterpret_cast<const float4*>(Us + (32 * q + lane_env0 + j) * 4);
+          o[0] = fmaf(a, uj.x, o[0]); o[1] = fmaf(a, uj.y, o[1]); o[2] = fmaf(a, uj.z, o[2]);
+        }
+        __syncwarp();
+        const int row = row0 + r;
+        if (row < M) {
+          float* dst = (hd == 0 ? P.geo : P.topo) + (size_t)row * nout;
+          for (int t = 0; t < nout; ++t) dst[t] = 1.f / (1.f + expf(-o[t]));
+        }
+      }
+      PDBG_T(t3);
+      PDBG_ACC(2, t3 - t2);
+      if (warp == NGENW) { PDBG_FLUSH(1, g); }
+    }
+  } else if (warp == W_ISSUER) {
+    // =================================================== MMA issuer / W forwarder =============================
+    if (lane == 0) {
+      if (is_leader) {
+        uint64_t db[WST][2][2];                              // [stage][k-step][hi, lo] of a full chunk
+#pragma unroll
+        for (int st = 0; st < WST; ++st)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t b_hi = smem_u32(smem + st * STAGE_BYTES) + 2 * ks * B_LBO;
+            db[st][ks][0] = make_desc(b_hi, B_LBO);
+            db[st][ks][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);
+          }
+        for (int g = 0; g < NGEMM; ++g) {
+          const int b = g & 1;
+          const uint32_t dacc = tmem_base + (uint32_t)(b ? TM_ACC1 : 0);
+          PDBG_T(ta0);
+          if (g >= 2) {                                      // the epilogue of GEMM g-2 has drained this accumulator
+            ok = mbar_wait_cluster(acc_empty + 8 * b, (uint32_t)(((g >> 1) - 1) & 1)) && ok;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          PDBG_T(ta1);
+          PDBG_ACC(3, ta1 - ta0);
+          for (int c = 0; c < NCH; ++c) {
+            const uint32_t u = (uint32_t)(g * NCH + c), sw = u % WST, sa = u % PAST;
+            PDBG_T(t0);
+            if constexpr (NCTA == 2) ok = mbar_wait_cluster(a_full + 8 * sa, (u / PAST) & 1) && ok;
+            else ok = mbar_wait(a_full + 8 * sa, (u / PAST) & 1) && ok;
+            PDBG_T(t1);
+            ok = mbar_wait(w_full + 8 * sw, (u / WST) & 1) && ok;
+            if constexpr (NCTA == 2) ok = mbar_wait_cluster(w_peer + 8 * sw, (u / WST) & 1) && ok;
+            PDBG_T(t2);
+            PDBG_ACC(0, t1 - t0); PDBG_ACC(1, t2 - t1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int kw = chunk_kw(KH, c);
+            const uint32_t a_hi = tmem_base + (uint32_t)(TM_AHI + 16 * sa), a_lo = tmem_base + (uint32_t)(TM_ALO + 16 * sa);
+#pragma unroll
+            for (int st = 0; st < WST; ++st) {
+              if (st != (int)sw) continue;                   // compile-time stage index keeps the descriptors in registers
+              if (kw == KCH) {
+                mma_tf32<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
+                mma_tf32<NCTA>(dacc, a_hi, db[st][0][1], 1);
+                mma_tf32<NCTA>(dacc, a_lo, db[st][0][0], 1);
+                mma_tf32<NCTA>(dacc, a_hi + 8, db[st][1][0], 1);
+                mma_tf32<NCTA>(dacc, a_hi + 8, db[st][1][1], 1);
+                mma_tf32<NCTA>(dacc, a_lo + 8, db[st][1][0], 1);
+              } else {                                       // tail chunk: one k-step, lo half right after hi
+                const uint64_t dbl = make_desc(smem_u32(smem + st * STAGE_BYTES) + (kw / 4) * B_LBO, B_LBO);
+                mma_tf32<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
+                mma_tf32<NCTA>(dacc, a_hi, dbl, 1);
+                mma_tf32<NCTA>(dacc, a_lo, db[st][0][0], 1);
+              }
+            }
+            mma_commit<NCTA>(w_empty + 8 * sw);
+            mma_commit<NCTA>(a_empty + 8 * sa);
+            if (c + 1 == NCH) mma_commit<NCTA>(acc_full + 8 * b);
+            PDBG_T(t3);
+            PDBG_ACC(2, t3 - t2);
+          }
+          PDBG_FLUSH(2, g);
+        }
+      } else {
+        for (int u = 0; u < NGEMM * NCH; ++u) {              // peer CTA: tell the leader that W chunk u has landed here
+          const uint32_t sw = (uint32_t)u % WST;
+          ok = mbar_wait(w_full + 8 * sw, ((uint32_t)u / WST) & 1) && ok;
+          mbar_arrive_remote(w_peer + 8 * sw, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================================== W producer ===========================================
+    if (lane == 0) {
+      for (int g = 0; g < NGEMM; ++g)
+        for (int c = 0; c < NCH; ++c) {
+          const uint32_t u = (uint32_t)(g * NCH + c), s = u % WST;
+          if (u >= WST) ok = mbar_wait(w_empty + 8 * s, ((u / WST) - 1) & 1) && ok;       // chunk u-WST consumed
+          const uint32_t bytes = 2u * (chunk_kw(KH, c) / 4) * B_LBO;                      // this CTA's half: hi then lo
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg[g]) +
+                                     (size_t)c * Cfg<NCTA>::CHUNK_IMG_BYTES + (size_t)cta_rank * bytes;
+          mbar_expect_tx(w_full + 8 * s, bytes);
+          bulk_g2s(smem_u32(smem + s * STAGE_BYTES), src, bytes, w_full + 8 * s);
+        }
+    }
+    __syncwarp();
+  }
+
+  if (!ok && P.error_flag) atomicExch(P.error_flag, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all();               // neither CTA leaves while the pair's TMEM / barriers are in use
+  if (warp == 0) {
+    if constexpr (NCTA == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+}  // namespace pipe
+}  // namespace tc
+}  // namespace tactor
