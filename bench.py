@@ -379,7 +379,7 @@ def main():
         stages = {"actor_ms": actor_ms, "fem_ms": fem_ms,
                   "fem_only_env_steps_per_s": B * world / (fem_ms * 1e-3)}
         if use_actor and actor_ms > fem_ms:
-            # dominant stage = actor_fused_kernel (tcgen05 kind::tf32 with the 3xTF32 split = float32-equivalent
+            # dominant stage = actor_pipe_kernel (tcgen05 kind::tf32 with the 3xTF32 split = float32-equivalent
             # accuracy, three MMAs per product).  achieved counts ALGORITHMIC flops (one multiply-add per
             # product) against the measured bf16 cuBLAS roof; tf32 peak is half of bf16 and the split costs 3x,
             # so 1/6 of that roof is the ceiling of this formulation.
@@ -387,7 +387,10 @@ def main():
             aflops = actor_flops(N) * B
             ach = aflops / (actor_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                        "traffic": None, "kernel": "actor_fused_kernel (1 of the 4 actor launches per step)",
+                        "traffic": (json.load(open(tpath)).get("actor_%s_B%d" % (args.family, B))
+                                    if os.path.exists(tpath) else None),
+                        "kernel": "actor_pipe_kernel (kernel_ms is the whole actor stage: + Pareto embedding and the two "
+                                  "OU-noise launches, about 3 % of it)",
                         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback",
                         "algorithmic_flops_per_env": actor_flops(N), "kernel_ms": actor_ms,
                         "note": "tcgen05 kind::tf32, 3xTF32 split (float32-equivalent); algorithmic flops vs the bf16 "

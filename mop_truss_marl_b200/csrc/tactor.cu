@@ -3,7 +3,7 @@
 //
 // Two launches per forward:
 //   pareto_kernel        Pareto-front branch (gcn_l1_4 + GlobalSumPool) -> pooled [B,208]
-//   actor_fused_kernel   everything else, one CTA per 128 rows, tcgen05 tensor cores (tactor_tc.cuh)
+//   actor_pipe_kernel    everything else, one CTA per 128 rows, tcgen05 tensor cores (tactor_pipe.cuh)
 // and two elementwise launches for the noise of tactor_act.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -96,7 +96,6 @@ struct tactor_handle_s {
   float* pooled = nullptr;             // [max_batch, 208] Pareto embedding
   float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
   int* d_error = nullptr;              // set by a kernel whose mbarrier wait timed out
-  bool pipe = true;                    // pipelined kernel (tactor_pipe.cuh); false = first fused kernel
   int ncta = 1;                        // CTAs per tcgen05 group (2 = CTA pair, cta_group::2)
   std::atomic<int64_t> launches{0};
   uint64_t calls = 0;
@@ -112,22 +111,6 @@ struct Guard {
   explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
   ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
-
-template <int NODES, int NCTA>
-cudaError_t launch_fused(const tactor::tc::fused::Params& p, int M, cudaStream_t st) {
-  using namespace tactor;
-  const int tiles = (M + tc::TCM - 1) / tc::TCM;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)((tiles + NCTA - 1) / NCTA * NCTA));   // a pair whose second tile is past M runs it empty
-  cfg.blockDim = dim3(tc::fused::FTHREADS);
-  cfg.dynamicSmemBytes = tc::fused::fused_smem_bytes<NODES, NCTA>();
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tc::fused::actor_fused_kernel<NODES, NCTA>, p);
-}
 
 template <int NODES, int NCTA>
 cudaError_t launch_pipe(const tactor::tc::fused::Params& p, int M, cudaStream_t st) {
@@ -151,12 +134,6 @@ cudaError_t set_pipe_smem() {
                               tactor::tc::pipe::pipe_smem_bytes<NODES, NCTA>());
 }
 
-template <int NODES, int NCTA>
-cudaError_t set_fused_smem() {
-  return cudaFuncSetAttribute(tactor::tc::fused::actor_fused_kernel<NODES, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              tactor::tc::fused::fused_smem_bytes<NODES, NCTA>());
-}
-
 template <int NODES>
 cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, float* geo, float* topo, cudaStream_t st) {
   using namespace tactor;
@@ -169,9 +146,7 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   for (int g = 0; g < tc::fused::NGEMM; ++g) { p.wimg[g] = h->d_wimg[4 + g]; p.bias[g] = h->d_b[4 + g]; }
   p.w_head[0] = h->d_w[11]; p.w_head[1] = h->d_w[12]; p.b_head[0] = h->d_b[11]; p.b_head[1] = h->d_b[12];
   p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error;
-  cudaError_t e;
-  if (h->pipe) e = (h->ncta == 2) ? launch_pipe<NODES, 2>(p, M, st) : launch_pipe<NODES, 1>(p, M, st);
-  else e = (h->ncta == 2) ? launch_fused<NODES, 2>(p, M, st) : launch_fused<NODES, 1>(p, M, st);
+  cudaError_t e = (h->ncta == 2) ? launch_pipe<NODES, 2>(p, M, st) : launch_pipe<NODES, 1>(p, M, st);
   h->launches.fetch_add(2);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -192,7 +167,6 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   tactor_handle_s* h = new (std::nothrow) tactor_handle_s();
   if (!h) return afail(TFEM_ERR_ARG, "out of host memory");
   h->device = device; h->nodes = nodes; h->max_batch = max_batch;
-  if (const char* v = getenv("TACTOR_KERNEL")) h->pipe = (strcmp(v, "fused") != 0);  // development switch
   if (const char* v = getenv("TACTOR_NCTA")) h->ncta = (atoi(v) == 2) ? 2 : 1;     // development switch (A/B timing)
   Guard g(device);
   cudaError_t e = cudaSuccess;
@@ -239,12 +213,8 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4096);
   if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4096);
   if (e == cudaSuccess) {
-    if (nodes == 16) e = (h->ncta == 2) ? set_fused_smem<16, 2>() : set_fused_smem<16, 1>();
-    else e = (h->ncta == 2) ? set_fused_smem<32, 2>() : set_fused_smem<32, 1>();
-    if (e == cudaSuccess) {
-      if (nodes == 16) e = (h->ncta == 2) ? set_pipe_smem<16, 2>() : set_pipe_smem<16, 1>();
-      else e = (h->ncta == 2) ? set_pipe_smem<32, 2>() : set_pipe_smem<32, 1>();
-    }
+    if (nodes == 16) e = (h->ncta == 2) ? set_pipe_smem<16, 2>() : set_pipe_smem<16, 1>();
+    else e = (h->ncta == 2) ? set_pipe_smem<32, 2>() : set_pipe_smem<32, 1>();
   }
   if (e == cudaSuccess) e = cudaMalloc(&h->pooled, (size_t)max_batch * tactor::LD * 4);
   if (e != cudaSuccess) { tactor_destroy(h); return afail(TFEM_ERR_CUDA, std::string("actor setup: ") + cudaGetErrorString(e)); }
@@ -308,7 +278,7 @@ int tactor_status(tactor_handle_t h) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(&flag, h->d_error, 4, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("actor status: ") + cudaGetErrorString(e));
-  if (flag) return afail(TFEM_ERR_CUDA, "an mbarrier wait timed out inside actor_fused_kernel");
+  if (flag) return afail(TFEM_ERR_CUDA, "an mbarrier wait timed out inside actor_pipe_kernel");
   return TFEM_OK;
 }
 

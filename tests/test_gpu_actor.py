@@ -53,6 +53,46 @@ def test_forward_matches_float64_oracle(N, B, P):
     a.check()
 
 
+def truss_mask(N):
+    """Adjacency pattern (with self loops) of the reference's num_x x 2 trusses: chords, verticals, both diagonals."""
+    nx = N // 2
+    m = np.eye(N, dtype=np.float32)
+    for i in range(nx):
+        for j in range(nx):
+            if abs(i - j) <= 1:
+                m[i, j] = m[nx + i, nx + j] = m[i, nx + j] = m[nx + j, i] = 1
+    return m
+
+
+@pytest.mark.parametrize("N,B,P,stray", [(16, 37, 3, False), (32, 21, 2, False), (16, 19, 1, True), (32, 6, 5, True)])
+def test_forward_truss_structured_adjacency(N, B, P, stray):
+    """The kernel's compacted-neighbour path (rows with <= 8 entries inside A_n's pattern), and the fall-back to the
+    full row when one environment has an entry outside that pattern (stray)."""
+    from mop_truss_marl_b200 import actor, tf_checkpoint
+    from oracle.actor_oracle import actor_forward
+    rng = np.random.RandomState(100 + N + B)
+    w = tf_checkpoint.random_actor_weights(seed=5)
+    for k in w:
+        w[k] = (w[k][0], (rng.randn(*w[k][1].shape) * 0.05).astype(np.float32))
+    inp = list(random_inputs(rng, B, N, P))
+    m = truss_mask(N)
+    off = m - np.eye(N, dtype=np.float32)
+    inp[1] = ((rng.rand(N, N) * 0.3 + 0.05) * m).astype(np.float32)
+    for i in (2, 3, 4):
+        inp[i] = (rng.rand(B, N, N) * (rng.rand(B, N, N) < 0.7) * off).astype(np.float32)
+    if stray:
+        inp[3][B // 2, 0, N - 1] = 0.37                  # outside the pattern of A_n
+        inp[2][B - 1, N - 1, 1] = 0.11
+    a = actor.BatchedActor(w, N, max_batch=B)
+    dev = [torch.from_numpy(np.ascontiguousarray(t)).cuda() for t in inp]
+    geo, topo = a.forward(*dev)
+    torch.cuda.synchronize()
+    g64, t64 = actor_forward(w, *inp)
+    assert np.abs(geo.cpu().numpy() - g64).max() <= ATOL
+    assert np.abs(topo.cpu().numpy() - t64).max() <= ATOL
+    a.check()
+
+
 def test_act_noise_statistics():
     from mop_truss_marl_b200 import actor, tf_checkpoint
     rng = np.random.RandomState(0)
