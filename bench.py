@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--e2e-pieces", type=int, default=2, help="pieces the batch is cut into on the end-to-end path")
     ap.add_argument("--no-actor", action="store_true", help="drive the env with resident uniform actions instead of the actor")
     args = ap.parse_args()
 
@@ -295,30 +296,21 @@ def main():
     if use_actor:
         # the caller holds the state tuple on the host (like the reference driver); per step it goes to the
         # device, the actor acts on it, the env steps, and the new state tuple + actions come back
-        st_host = {k: getattr(env, k).cpu().pin_memory() for k in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range")}
-        out_host["a_geo"] = torch.empty(B, N, 2).pin_memory()
-        out_host["a_topo"] = torch.empty(B, N, 3).pin_memory()
-        out_host["move_range"] = torch.empty(B, N, 2).pin_memory()
-        coin_dev = torch.empty(B, dtype=torch.uint8, device=dev)
+        from mop_truss_marl_b200.host_pipeline import HostRollout, STATE_IN
+        roll = HostRollout(env, pol, pieces=args.e2e_pieces)
+        bufs = [roll.alloc_host(), roll.alloc_host()]
+        for k in STATE_IN:
+            bufs[0][k].copy_(getattr(env, k))
+        torch.cuda.synchronize()
+        flip = [0]
 
         def e2e_step():
-            for k, v in st_host.items():
-                getattr(env, k).copy_(v, non_blocking=True)
-            coin_dev.copy_(coin_host, non_blocking=True)
-            pol.act(env.x_n, env.A_n, env.A_s, env.A_n_ts, env.A_n_cs, x_p, A_p, out=(a_geo_buf, a_topo_buf))
-            env.step(a_geo_buf, a_topo_buf, coin_dev)
-            for k, _ in f32_out:
-                out_host[k].copy_(getattr(env, k), non_blocking=True)
-            out_host["status"].copy_(env.status, non_blocking=True)
-            out_host["a_geo"].copy_(a_geo_buf, non_blocking=True)
-            out_host["a_topo"].copy_(a_topo_buf, non_blocking=True)
-            out_host["move_range"].copy_(env.move_range, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
-            for k in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range"):
-                st_host[k], out_host[k] = out_host[k], st_host[k]          # returned state = next input
-        h2d = sum(v.numel() * v.element_size() for v in st_host.values()) + B
-        d2h = sum(v.numel() * v.element_size() for v in out_host.values())
-        e2e_path = "pinned host state tuple -> device -> BatchedActor.act + BatchedTrussEnv.step -> host (state tuple, point, actions)"
+            src, dst = bufs[flip[0]], bufs[1 - flip[0]]
+            roll.step(src, coin_host, x_p, A_p, dst)           # returned state tuple = next step's input
+            flip[0] = 1 - flip[0]
+        h2d, d2h = roll.bytes_per_step()
+        e2e_path = ("pinned host state tuple -> device -> BatchedActor.act + BatchedTrussEnv.step -> host (state tuple, "
+                    "point, status, actions); host_pipeline.HostRollout, %d pieces on 3 streams" % len(roll.ranges))
     else:
         host = {
             "set_node": env.nN_x_n.cpu().pin_memory(), "set_element": env.nN_x_e.cpu().pin_memory(),

@@ -79,11 +79,12 @@ class BatchedTrussEnv:
             self.point64 = self.d = self.axial = self.ratio = self.U = self.reactions = None
         self._out = self._make_out()
 
-    def _make_out(self):
+    def _make_out(self, lo=0, hi=None):
         o = capi.StepOut()
         for name in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "point", "point64", "d", "axial",
                      "ratio", "U", "reactions", "status", "y", "y_weak"):
-            setattr(o, name, _ptr(getattr(self, name)))
+            t = getattr(self, name)
+            setattr(o, name, _ptr(t if (t is None or (lo == 0 and hi is None)) else t[lo:hi]))
         return o
 
     def _stream(self):
@@ -96,27 +97,36 @@ class BatchedTrussEnv:
         self.game_step = 1
         return self.state()
 
-    def step(self, a_geo: torch.Tensor, a_topo: torch.Tensor, coin: torch.Tensor | None = None):
+    def step(self, a_geo: torch.Tensor, a_topo: torch.Tensor, coin: torch.Tensor | None = None,
+             rows: tuple | None = None):
         """a_geo [B,N,2], a_topo [B,N,3] float32 CUDA tensors (clipped in place, like the reference);
         coin [B] uint8/bool (1 = ``random.random() >= 0.5``).  Updates the state in place and returns
-        ``point`` [B,4]."""
-        self._check(a_geo, (self.B, self.N, 2))
-        self._check(a_topo, (self.B, self.N, 3))
+        ``point`` [B,4].  ``rows=(lo, hi)`` steps only environments lo..hi-1 (the action / coin tensors then
+        hold hi-lo environments): the environments are independent, so a batch can be stepped in pieces on
+        different streams (``host_pipeline.HostRollout``)."""
+        lo, hi = (0, self.B) if rows is None else rows
+        if not (0 <= lo < hi <= self.B):
+            raise ValueError("rows must satisfy 0 <= lo < hi <= batch")
+        nb = hi - lo
+        self._check(a_geo, (nb, self.N, 2))
+        self._check(a_topo, (nb, self.N, 3))
         if coin is not None:
             if coin.dtype == torch.bool:
                 coin = coin.to(torch.uint8)
-            if coin.dtype != torch.uint8 or coin.shape != (self.B,) or coin.device != self.device or not coin.is_contiguous():
+            if coin.dtype != torch.uint8 or coin.shape != (nb,) or coin.device != self.device or not coin.is_contiguous():
                 raise ValueError("coin must be a contiguous uint8 [B] tensor on the env device")
         sin = capi.StepIn()
-        sin.set_node = _ptr(self.nN_x_n)
-        sin.set_element = _ptr(self.nN_x_e)
+        sin.set_node = _ptr(self.nN_x_n[lo:hi])
+        sin.set_element = _ptr(self.nN_x_e[lo:hi])
         sin.a_geo = _ptr(a_geo)
         sin.a_topo = _ptr(a_topo)
         sin.coin = _ptr(coin)
-        sin.move_range = _ptr(self.move_range)
-        capi.check(capi.lib.tfem_step(self.handle.ptr, self.B, C.byref(sin), C.byref(self._out), self._stream()))
-        self.game_step += 1
-        return self.point
+        sin.move_range = _ptr(self.move_range[lo:hi])
+        out = self._out if rows is None else self._make_out(lo, hi)
+        capi.check(capi.lib.tfem_step(self.handle.ptr, nb, C.byref(sin), C.byref(out), self._stream()))
+        if rows is None or hi == self.B:
+            self.game_step += 1
+        return self.point if rows is None else self.point[lo:hi]
 
     def _check(self, t, shape):
         if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and tuple(t.shape) == shape
