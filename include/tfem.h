@@ -150,6 +150,15 @@ int tfem_solve_only(tfem_handle_t h, int B, const double* y, const int32_t* sect
                     double* d, double* axial, double* ratio, double* U, double* reactions,
                     int32_t* status, void* stream);
 
+/* The solve of tfem_solve_only in the formulation BASELINE.json's north_star names for the large meshes: K assembled
+ * dense in the reference's own free-DOF order (FEM_2Dtruss.py:227-261, 310-324) and factored by a blocked (8-wide)
+ * right-looking Cholesky whose trailing updates run on the FP64 tensor cores (mma.sync.m8n8k4.f64 = DMMA), one CTA
+ * per environment.  Kept as a measured alternative to the banded production solve; d [B,ndof]
+ * in reference DOF order, status bit 0 = non-positive pivot.  Assembly uses shared-memory atomics, so the last bits
+ * of d depend on the order of the element contributions. */
+int tfem_solve_dense_dmma(tfem_handle_t h, int B, const double* y, const int32_t* section, double* d,
+                          int32_t* status, void* stream);
+
 /* Same call as tfem_step with HOST buffers (the reference's calling convention: numpy arrays in,
  * numpy arrays out).  Copies inputs host->device, runs the step, copies every non-NULL output back
  * and synchronises the stream before returning.  Scratch device memory is owned by the handle. */

@@ -157,6 +157,19 @@ class BatchedTrussEnv:
                                             _ptr(out["reactions"]), _ptr(out["status"]), self._stream()))
         return out
 
+    def solve_dense_dmma(self, y: torch.Tensor, section: torch.Tensor):
+        """the same solve as ``solve_only`` by the dense blocked Cholesky with DMMA trailing updates
+        (``tfem_solve_dense_dmma``): returns ``d`` [B,ndof] in reference DOF order and ``status`` [B]"""
+        B = y.shape[0]
+        if y.dtype != torch.float64 or section.dtype != torch.int32 or tuple(y.shape) != (B, self.N) \
+                or tuple(section.shape) != (B, self.E) or not y.is_contiguous() or not section.is_contiguous():
+            raise ValueError("y must be float64 [B,N] and section int32 [B,E], contiguous")
+        d = torch.empty(B, self.ndof, dtype=torch.float64, device=self.device)
+        status = torch.zeros(B, dtype=torch.int32, device=self.device)
+        capi.check(capi.lib.tfem_solve_dense_dmma(self.handle.ptr, B, _ptr(y), _ptr(section), _ptr(d), _ptr(status),
+                                                  self._stream()))
+        return d, status
+
     def launch_count(self) -> int:
         return self.handle.launch_count()
 

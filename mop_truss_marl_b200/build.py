@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
 ]
-SOURCES = ["tfem_family.cu", "tfem_kernels.cu", "tfem_capi.cu", "tactor.cu"]
+SOURCES = ["tfem_family.cu", "tfem_kernels.cu", "tfem_dense.cu", "tfem_capi.cu", "tactor.cu"]
 
 
 def _stale(target: str, deps) -> bool:

@@ -67,7 +67,7 @@ TABLES = {
 }
 
 EXPORTS = ("tfem_version", "tfem_last_error", "tfem_create", "tfem_destroy", "tfem_get_dims", "tfem_get_table",
-           "tfem_reset", "tfem_step", "tfem_solve_only", "tfem_step_host", "tfem_launch_count")
+           "tfem_reset", "tfem_step", "tfem_solve_only", "tfem_solve_dense_dmma", "tfem_step_host", "tfem_launch_count")
 
 
 class TfemError(RuntimeError):
@@ -89,6 +89,7 @@ def _load():
     lib.tfem_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(StepOut), C.c_void_p]
     lib.tfem_step.argtypes = [C.c_void_p, C.c_int, C.POINTER(StepIn), C.POINTER(StepOut), C.c_void_p]
     lib.tfem_solve_only.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_void_p]
+    lib.tfem_solve_dense_dmma.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     lib.tfem_step_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(StepIn), C.POINTER(StepOut), C.c_void_p]
     lib.tfem_launch_count.argtypes = [C.c_void_p]
     lib.tfem_launch_count.restype = C.c_int64

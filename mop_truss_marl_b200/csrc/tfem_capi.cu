@@ -192,6 +192,20 @@ int tfem_solve_only(tfem_handle_t h, int B, const double* y, const int32_t* sect
   return launch(h, a, stream);
 }
 
+int tfem_solve_dense_dmma(tfem_handle_t h, int B, const double* y, const int32_t* section, double* d,
+                          int32_t* status, void* stream) {
+  if (!h || !y || !section || !d) return fail(TFEM_ERR_ARG, "null argument");
+  if (B < 0) return fail(TFEM_ERR_ARG, "negative batch");
+  if (h->device < 0) return fail(TFEM_ERR_CUDA, "tables-only handle (device < 0): libtfem has no CPU path");
+  if (B == 0) return TFEM_OK;
+  DeviceGuard guard(h->device);
+  if (!guard.ok) return fail(TFEM_ERR_CUDA, "cudaSetDevice failed");
+  const int rc = tfem::dense_solve_launch(h->d_tables, B, y, section, d, status, (cudaStream_t)stream);
+  if (rc != 0) return cuda_fail((cudaError_t)rc, "dense DMMA solve");
+  h->launches.fetch_add(1);
+  return TFEM_OK;
+}
+
 int tfem_step_host(tfem_handle_t h, int B, const tfem_step_in* in, const tfem_step_out* out, void* stream_) {
   if (!h || !in || !out) return fail(TFEM_ERR_ARG, "null argument");
   if (B <= 0) return B == 0 ? TFEM_OK : fail(TFEM_ERR_ARG, "negative batch");

@@ -28,4 +28,8 @@ struct LaunchInfo {
 int step_kernel_configure(int nx, int device, int map_entries, LaunchInfo* info);
 int step_kernel_launch(int nx, const StepArgs& args, const LaunchInfo& info, cudaStream_t stream);
 
+// dense blocked Cholesky with DMMA trailing updates (tfem_dense.cu); returns cudaError_t as int
+int dense_solve_launch(const FamilyTables* d_tables, int B, const double* y, const int32_t* section, double* d,
+                       int32_t* status, cudaStream_t stream);
+
 }  // namespace tfem

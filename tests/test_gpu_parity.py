@@ -229,6 +229,31 @@ def test_solve_only_vs_oracle(envmod, name):
         assert abs(float(out["U"][i]) - want["U"]) <= FP64_TOL * abs(want["U"])
 
 
+@pytest.mark.parametrize("name", ["large_bridge", "large_roof", "small_bridge"])
+def test_dense_dmma_solve_vs_oracle_and_banded(envmod, name):
+    """the north_star's dense blocked Cholesky with DMMA trailing updates (tfem_solve_dense_dmma) against the oracle
+    and against the banded production solve, on the same geometries"""
+    from oracle.truss_oracle import TrussOracle
+    o = TrussOracle(name)
+    m = o.mesh
+    rng = np.random.RandomState(12)
+    B = 200
+    y = np.zeros((B, m.N))
+    y[:, m.N // 2:] = 1.0 + rng.rand(B, m.N // 2) * (m.y_max - 1.0)
+    y[:, 1:m.N // 2 - 1] = rng.rand(B, m.N // 2 - 2) * 0.6
+    sec = rng.randint(0, 5, size=(B, m.E)).astype(np.int32)
+    env = make_env(envmod, name, 1)
+    yt, st = torch.from_numpy(y).cuda(), torch.from_numpy(sec).cuda()
+    d, status = env.solve_dense_dmma(yt, st)
+    banded = env.solve_only(yt, st)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    for i in range(B):
+        assert nrm(cpu(d[i]), cpu(banded["d"][i])) <= FP64_TOL, i
+    for i in range(0, B, 25):
+        assert nrm(cpu(d[i]), o.solve_only(y[i], sec[i])["d"]) <= FP64_TOL, i
+
+
 def test_degenerate_geometry_sets_status(envmod):
     """zero-length vertical: the reference divides by zero (python float) / raises; we flag the env"""
     from oracle.truss_oracle import TrussOracle
