@@ -301,16 +301,17 @@ def main():
         bufs = [roll.alloc_host(), roll.alloc_host()]
         for k in STATE_IN:
             bufs[0][k].copy_(getattr(env, k))
+        x_p_host, A_p_host = x_p.cpu().pin_memory(), A_p.cpu().pin_memory()
         torch.cuda.synchronize()
         flip = [0]
 
         def e2e_step():
             src, dst = bufs[flip[0]], bufs[1 - flip[0]]
-            roll.step(src, coin_host, x_p, A_p, dst)           # returned state tuple = next step's input
+            roll.step(src, coin_host, x_p_host, A_p_host, dst)  # returned state tuple = next step's input
             flip[0] = 1 - flip[0]
         h2d, d2h = roll.bytes_per_step()
-        e2e_path = ("pinned host state tuple -> device -> BatchedActor.act + BatchedTrussEnv.step -> host (state tuple, "
-                    "point, status, actions); host_pipeline.HostRollout, %d pieces on 3 streams" % len(roll.ranges))
+        e2e_path = ("pinned host state tuple + Pareto graph -> device -> tactor_act + tfem_step -> host (state tuple, point, "
+                    "status, actions); trollout_step_host (host_pipeline.HostRollout), %d pieces on 3 streams" % len(roll.ranges))
     else:
         host = {
             "set_node": env.nN_x_n.cpu().pin_memory(), "set_element": env.nN_x_e.cpu().pin_memory(),

@@ -2,36 +2,76 @@
 driver does (``master_DDPG_truss2D_MO.py:167-260``), and every step moves it to the GPU, lets the actor act, steps
 the environments and brings the new state tuple, the objective point and the actions back.
 
-The environments are independent, so the batch is cut into pieces and the three legs -- host->device copies, the
-two C-ABI calls (``tactor_act``, ``tfem_step``) and device->host copies -- run on three CUDA streams: piece i+1 is
-uploading while piece i computes and piece i-1 downloads (PCIe is full duplex).  PyTorch provides the streams,
-events and pinned buffers only.
+The work is done by ``trollout_step_host`` (``include/trollout.h``): the environments are independent, so the batch
+is cut into pieces and the three legs -- host->device copies, the two kernels-with-C-ABI (``tactor_act``,
+``tfem_step``) and device->host copies -- run on three CUDA streams: piece i+1 is uploading while piece i computes
+and piece i-1 downloads (PCIe is full duplex).  PyTorch only provides the pinned host buffers here.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
+
+from . import capi
 
 STATE_IN = ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range")
 STATE_OUT = ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range", "point", "status")
+ROLLOUT_EXPORTS = ("trollout_last_error", "trollout_create", "trollout_destroy", "trollout_step_host",
+                   "trollout_bytes_per_env")
+
+
+class _State(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in STATE_IN]
+
+
+class _IO(C.Structure):
+    _fields_ = [("inp", _State), ("coin", C.c_void_p), ("x_p", C.c_void_p), ("A_p", C.c_void_p), ("n_pf", C.c_void_p),
+                ("P", C.c_int32), ("out", _State), ("point", C.c_void_p), ("status", C.c_void_p),
+                ("a_geo", C.c_void_p), ("a_topo", C.c_void_p)]
+
+
+_lib = capi.lib
+_lib.trollout_last_error.restype = C.c_char_p
+_lib.trollout_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+_lib.trollout_destroy.argtypes = [C.c_void_p]
+_lib.trollout_step_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(_IO), C.c_float, C.c_float, C.c_float, C.c_uint64]
+_lib.trollout_bytes_per_env.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+
+
+def _check(rc):
+    if rc != 0:
+        raise capi.TfemError("libtfem rollout error %d: %s" % (rc, _lib.trollout_last_error().decode()))
+
+
+def _hp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
 class HostRollout:
-    """``env``: BatchedTrussEnv, ``actor``: BatchedActor of the same batch; ``pieces``: how many pieces the batch
-    is cut into (each should still fill the GPU: >= 148 tiles of 128 rows, i.e. >= ~1184 small / 592 large envs)."""
+    """``env``: BatchedTrussEnv (family, device), ``actor``: BatchedActor on the same device; ``pieces``: how many
+    pieces the batch is cut into (each should still fill the GPU: about 148 tiles of 128 actor rows, i.e. ~1000
+    small / ~500 large environments)."""
 
     def __init__(self, env, actor, pieces: int = 2):
         self.env, self.actor = env, actor
-        B, dev = env.B, env.device
-        pieces = max(1, min(int(pieces), B))
-        step = -(-B // pieces)
-        step = -(-step // 32) * 32                 # piece boundaries on 32 environments: every sub-array stays 16-byte aligned
-        self.ranges = [(lo, min(lo + step, B)) for lo in range(0, B, step)]
-        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
-        self.ev_in = [torch.cuda.Event() for _ in self.ranges]
-        self.ev_run = [torch.cuda.Event() for _ in self.ranges]
-        self.a_geo = torch.empty(B, env.N, 2, device=dev)
-        self.a_topo = torch.empty(B, env.N, 3, device=dev)
-        self.coin = torch.empty(B, dtype=torch.uint8, device=dev)
+        self._h = C.c_void_p()
+        with torch.cuda.device(env.device):
+            _check(_lib.trollout_create(env.handle.ptr, actor._h, env.B, int(pieces), C.byref(self._h)))
+        step = -(-env.B // max(1, int(pieces)))
+        step = -(-step // 32) * 32
+        self.ranges = [(lo, min(lo + step, env.B)) for lo in range(0, env.B, step)]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.trollout_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def alloc_host(self):
         """pinned host buffers for one state tuple (+ point, status, actions)"""
@@ -41,41 +81,38 @@ class HostRollout:
         h["a_topo"] = torch.empty(env.B, env.N, 3).pin_memory()
         return h
 
-    def bytes_per_step(self):
-        env = self.env
-        nbytes = lambda t: t.numel() * t.element_size()  # noqa: E731
-        h2d = sum(nbytes(getattr(env, k)) for k in STATE_IN) + env.B
-        d2h = sum(nbytes(getattr(env, k)) for k in STATE_OUT) + nbytes(self.a_geo) + nbytes(self.a_topo)
-        return h2d, d2h
+    def bytes_per_step(self, P: int = 1):
+        a, b = C.c_size_t(), C.c_size_t()
+        _check(_lib.trollout_bytes_per_env(self._h, int(P), C.byref(a), C.byref(b)))
+        return a.value * self.env.B, b.value * self.env.B
 
-    def step(self, state_host: dict, coin_host: torch.Tensor, x_p: torch.Tensor, A_p: torch.Tensor, out_host: dict,
-             n_pf=None):
-        """state_host[k] for k in STATE_IN and coin_host [B] uint8: pinned host tensors; x_p/A_p/n_pf: the Pareto-front
-        graph (device, [B,P,4] / [B,P,P] / [B]).  Fills out_host (STATE_OUT + a_geo, a_topo) and returns it after the
-        last piece has landed."""
-        env, actor = self.env, self.actor
-        cur = torch.cuda.current_stream(env.device)
-        for s in (self.s_in, self.s_run, self.s_out):
-            s.wait_stream(cur)
-        for i, (lo, hi) in enumerate(self.ranges):
-            with torch.cuda.stream(self.s_in):
-                for k in STATE_IN:
-                    getattr(env, k)[lo:hi].copy_(state_host[k][lo:hi], non_blocking=True)
-                self.coin[lo:hi].copy_(coin_host[lo:hi], non_blocking=True)
-                self.ev_in[i].record(self.s_in)
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(self.ev_in[i])
-                actor.act(env.x_n[lo:hi], env.A_n, env.A_s[lo:hi], env.A_n_ts[lo:hi], env.A_n_cs[lo:hi],
-                          x_p[lo:hi], A_p[lo:hi], n_pf=None if n_pf is None else n_pf[lo:hi],
-                          out=(self.a_geo[lo:hi], self.a_topo[lo:hi]))
-                env.step(self.a_geo[lo:hi], self.a_topo[lo:hi], self.coin[lo:hi], rows=(lo, hi))
-                self.ev_run[i].record(self.s_run)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.ev_run[i])
-                for k in STATE_OUT:
-                    out_host[k][lo:hi].copy_(getattr(env, k)[lo:hi], non_blocking=True)
-                out_host["a_geo"][lo:hi].copy_(self.a_geo[lo:hi], non_blocking=True)
-                out_host["a_topo"][lo:hi].copy_(self.a_topo[lo:hi], non_blocking=True)
-        self.s_out.synchronize()
-        cur.wait_stream(self.s_run)
+    def step(self, state_host: dict, coin_host, x_p_host: torch.Tensor, A_p_host: torch.Tensor, out_host: dict,
+             n_pf_host=None):
+        """state_host[k] for k in STATE_IN, coin_host [B] uint8 (or None), x_p_host [B,P,4], A_p_host [B,P,P] and
+        n_pf_host [B] int32 (or None): contiguous HOST tensors (pinned for overlap).  Fills out_host (STATE_OUT +
+        a_geo, a_topo) and returns it once the last piece has landed."""
+        env, act = self.env, self.actor
+        B, N, E = env.B, env.N, env.E
+        P = int(x_p_host.shape[1])
+        shapes = {"x_n": (B, N, 13), "A_s": (B, N, N), "A_n_ts": (B, N, N), "A_n_cs": (B, N, N), "nN_x_n": (B, N, 12),
+                  "nN_x_e": (B, E, 21), "move_range": (B, N, 2), "point": (B, 4), "a_geo": (B, N, 2), "a_topo": (B, N, 3)}
+
+        def chk(t, shape, dtype=torch.float32):
+            if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == dtype
+                    and tuple(t.shape) == shape and t.is_contiguous()):
+                raise ValueError("expected a contiguous host %s tensor of shape %s" % (dtype, shape))
+            return _hp(t)
+        io = _IO()
+        for k in STATE_IN:
+            setattr(io.inp, k, chk(state_host[k], shapes[k]))
+            setattr(io.out, k, chk(out_host[k], shapes[k]))
+        io.coin = chk(coin_host, (B,), torch.uint8) if coin_host is not None else C.c_void_p(0)
+        io.x_p, io.A_p, io.P = chk(x_p_host, (B, P, 4)), chk(A_p_host, (B, P, P)), P
+        io.n_pf = chk(n_pf_host, (B,), torch.int32) if n_pf_host is not None else C.c_void_p(0)
+        io.point = chk(out_host["point"], shapes["point"])
+        io.status = chk(out_host["status"], (B,), torch.int32)
+        io.a_geo, io.a_topo = chk(out_host["a_geo"], shapes["a_geo"]), chk(out_host["a_topo"], shapes["a_topo"])
+        with torch.cuda.device(env.device):
+            _check(_lib.trollout_step_host(self._h, B, C.byref(io), act.mu, act.theta, act.sigma, act.seed))
+        act.update_num += 1
         return out_host

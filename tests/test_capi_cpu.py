@@ -27,6 +27,12 @@ def test_exports_match_header():
                          "tactor_launch_count", "tactor_status"}
     for name in declared2:
         assert hasattr(capi.lib, name), name
+    hdr3 = open(os.path.join(ROOT, "include", "trollout.h")).read()
+    declared3 = set(re.findall(r"\b(trollout_[a-z_0-9]+)\s*\(", hdr3))
+    from mop_truss_marl_b200 import host_pipeline
+    assert declared3 == set(host_pipeline.ROLLOUT_EXPORTS)
+    for name in declared3:
+        assert hasattr(capi.lib, name), name
 
 
 def test_struct_sizes():

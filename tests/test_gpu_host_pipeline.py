@@ -1,4 +1,4 @@
-"""GPU: host_pipeline.HostRollout (state tuple resident on the host, batch cut into pieces on three streams) gives
+"""GPU: host_pipeline.HostRollout / trollout_step_host (state tuple resident on the host, batch cut into pieces on three streams) gives
 exactly what the resident path gives: environments are independent, so cutting the batch must not change a bit."""
 import numpy as np
 import pytest
@@ -21,6 +21,7 @@ def test_host_rollout_equals_resident_path(family, B, pieces):
     g = torch.Generator(device=dev).manual_seed(3)
     x_p = torch.rand(B, 2, 4, device=dev, generator=g)
     A_p = torch.rand(B, 2, 2, device=dev, generator=g)
+    x_p_host, A_p_host = x_p.cpu().pin_memory(), A_p.cpu().pin_memory()
     roll = HostRollout(envs[1], pols[1], pieces=pieces)
     assert len(roll.ranges) == pieces and roll.ranges[0][0] == 0 and roll.ranges[-1][1] == B
     bufs = [roll.alloc_host(), roll.alloc_host()]
@@ -36,7 +37,7 @@ def test_host_rollout_equals_resident_path(family, B, pieces):
         envs[0].step(a_geo, a_topo, coin.to(dev))
         # host-resident, pipelined path
         src, dst = bufs[it & 1], bufs[1 - (it & 1)]
-        roll.step(src, coin.pin_memory(), x_p, A_p, dst)
+        roll.step(src, coin.pin_memory(), x_p_host, A_p_host, dst)
         torch.cuda.synchronize()
         for k in STATE_OUT:
             assert torch.equal(dst[k], getattr(envs[0], k).cpu()), (it, k)
