@@ -50,6 +50,10 @@ const char* tactor_last_error(void);
 int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device, tactor_handle_t* out);
 int tactor_destroy(tactor_handle_t h);
 
+/* actor_model.set_weights / load_weights on a live handle (truss2D_RL.py:368-379, master...:795): replaces all 13
+ * layers (same layout as tactor_create) after the device has finished the forwards already queued. */
+int tactor_set_weights(tactor_handle_t h, const tactor_weights* w);
+
 /* geo [B,N,2], topo [B,N,3] = sigmoid outputs of gcn_l4_1 / gcn_l4_2 (no noise). */
 int tactor_forward(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, void* stream);
 

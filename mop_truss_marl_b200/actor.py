@@ -22,13 +22,14 @@ class _Inputs(C.Structure):
                 ("P", C.c_int32)]
 
 
-ACTOR_EXPORTS = ("tactor_last_error", "tactor_create", "tactor_destroy", "tactor_forward", "tactor_act",
+ACTOR_EXPORTS = ("tactor_last_error", "tactor_create", "tactor_destroy", "tactor_set_weights", "tactor_forward", "tactor_act",
                  "tactor_launch_count", "tactor_status")
 
 _lib = capi.lib
 _lib.tactor_last_error.restype = C.c_char_p
 _lib.tactor_create.argtypes = [C.POINTER(_Weights), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
 _lib.tactor_destroy.argtypes = [C.c_void_p]
+_lib.tactor_set_weights.argtypes = [C.c_void_p, C.POINTER(_Weights)]
 _lib.tactor_forward.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.tactor_act.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                             C.c_float, C.c_uint64, C.c_void_p]
@@ -60,6 +61,12 @@ class BatchedActor:
         self.device = torch.device("cuda", index)
         self.nodes, self.max_batch = int(nodes), int(max_batch)
         self.mu, self.theta, self.sigma, self.seed = float(mu), float(theta), float(sigma), int(seed)
+        w = self._pack(weights)
+        self._h = C.c_void_p()
+        _check(_lib.tactor_create(C.byref(w), self.nodes, self.max_batch, index, C.byref(self._h)))
+        self.update_num = 0                        # multimodals_OneAgent.update_num (:352)
+
+    def _pack(self, weights):
         w = _Weights()
         self._keep = []
         for i, name in enumerate(ACTOR_LAYERS):
@@ -68,9 +75,12 @@ class BatchedActor:
             self._keep += [k, b]
             w.kernel[i] = k.ctypes.data
             w.bias[i] = b.ctypes.data
-        self._h = C.c_void_p()
-        _check(_lib.tactor_create(C.byref(w), self.nodes, self.max_batch, index, C.byref(self._h)))
-        self.update_num = 0                        # multimodals_OneAgent.update_num (:352)
+        return w
+
+    def set_weights(self, weights):
+        """replace all 13 layers (``actor_model.set_weights`` / ``load_weights`` on a live actor)"""
+        w = self._pack(weights)
+        _check(_lib.tactor_set_weights(self._h, C.byref(w)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -121,10 +121,42 @@ class MADDPG:
         self.temprp[0].append([state, a0_g, a0_t, a1_g, a1_t, a2_g, a2_t, reward, next_state1, next_state2,
                                next_state3, done])
 
+    # ---- learner: PyTorch-level restatement of MADDPG.train / update (mop_truss_marl_b200/learner.py) ----
+    def _learner(self):
+        if getattr(self, "_lrn", None) is None:
+            import torch
+            from mop_truss_marl_b200.learner import MADDPGLearner
+            dev = "cuda" if torch.cuda.is_available() else "cpu"
+            self._lrn = MADDPGLearner(lr=self.lr, gamma=self.gamma, hidden=self.a_nn, n_q=self.c_nn,
+                                      max_mem=self.temprp[0].maxlen, batch_size=self.batch_size, device=dev, seed=seedThis)
+            for k, a in enumerate(self.agents):              # carry over loaded checkpoints (critic weights do not exist)
+                self._lrn.agents[k].actor.import_weights(a.actor_model.weights)
+                self._lrn.agents[k].update_init()
+            self._seen = 0
+        return self._lrn
+
     def train(self):
-        raise NotImplementedError("the DDPG learner (critic, replay sampling, actor update) is outside the "
-                                  "accelerated hot path (SURVEY.md section 8f-4)")
+        lrn = self._learner()
+        mem = self.temprp[0]
+        # move the transitions remembered since the last call into the learner's replay
+        fresh = list(mem)[self._seen:] if self._seen <= len(mem) else list(mem)
+        for t in fresh:
+            state = [t[0][i] for i in (0, 1, 2, 3, 4, 6, 7)]                      # the reference's tuple carries mask at [5]
+            nxt = [[ns[i] for i in (0, 1, 2, 3, 4, 6, 7)] for ns in (t[8], t[9], t[10])]
+            lrn.remember(state, [(t[1], t[2]), (t[3], t[4]), (t[5], t[6])], np.asarray(t[7], dtype=np.float32), nxt,
+                         1 if t[11] == 1 else 0)
+        self._seen = len(mem)
+        if not lrn.train():
+            return
+        for k, a in enumerate(self.agents):                  # the rollout acts with the updated online actor (:340)
+            a.actor_model.weights = lrn.actor_weights(k)
+            for dev_actor in a.actor_model._device_actor.values():
+                dev_actor.set_weights(a.actor_model.weights)
 
     def update(self):
-        for a in self.agents:
-            a.update_num += 0
+        interval = len(self.agents) * 100                    # (:692-697)
+        if self.agents[0].update_num % interval == 0 and getattr(self, "_lrn", None) is not None:
+            for k, a in enumerate(self.agents):
+                self._lrn.agents[k].update_num = a.update_num
+                if self._lrn.agents[k].update():
+                    a.update_num = 0

@@ -134,6 +134,52 @@ cudaError_t set_pipe_smem() {
                               tactor::tc::pipe::pipe_smem_bytes<NODES, NCTA>());
 }
 
+// (re)builds the device copies of the weights: packed [Kpad,208] kernels / [208] biases and the tcgen05 operand
+// images of the seven [200,200] layers.  Buffers are allocated on first use and overwritten afterwards.
+cudaError_t upload_weights(tactor_handle_s* h, const tactor_weights* w) {
+  cudaError_t e = cudaSuccess;
+  for (int l = 0; l < TACTOR_NLAYERS && e == cudaSuccess; ++l) {
+    const int kin = kIn[l], kout = kOut[l];
+    const int kpad = (kin + tactor::KC - 1) / tactor::KC * tactor::KC;
+    std::vector<float> wp((size_t)kpad * tactor::LD, 0.f), bp(tactor::LD, 0.f);
+    for (int i = 0; i < kin; ++i)
+      for (int o = 0; o < kout; ++o) wp[(size_t)i * tactor::LD + o] = w->kernel[l][(size_t)i * kout + o];
+    for (int o = 0; o < kout; ++o) bp[o] = w->bias[l][o];
+    if (!h->d_w[l]) e = cudaMalloc(&h->d_w[l], wp.size() * 4);
+    if (e == cudaSuccess && !h->d_b[l]) e = cudaMalloc(&h->d_b[l], bp.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_w[l], wp.data(), wp.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_b[l], bp.data(), bp.size() * 4, cudaMemcpyHostToDevice);
+  }
+  // tcgen05 operand images of the [200,200] layers: per 16-wide K chunk, per CTA of the pair (its half of the
+  // 208 columns), [hi|lo][kb][n][4 floats]
+  const int bn = tactor::tc::TCN / h->ncta;
+  for (int l = 4; l <= 10 && e == cudaSuccess; ++l) {
+    const int K = kIn[l], kout = kOut[l];
+    std::vector<float> img;
+    for (int c = 0; c * tactor::tc::KCH < K; ++c) {
+      const int kw = tactor::tc::chunk_kw(K, c), nkb = kw / 4;
+      for (int half = 0; half < h->ncta; ++half)
+      for (int part = 0; part < 2; ++part)
+        for (int kb = 0; kb < nkb; ++kb)
+          for (int nl = 0; nl < bn; ++nl)
+            for (int t = 0; t < 4; ++t) {
+              const int n = half * bn + nl;
+              const int k = c * tactor::tc::KCH + 4 * kb + t;
+              float v = (n < kout && k < K) ? w->kernel[l][(size_t)k * kout + n] : 0.f;
+              uint32_t bits;
+              memcpy(&bits, &v, 4);
+              bits &= 0xFFFFE000u;
+              float hi;
+              memcpy(&hi, &bits, 4);
+              img.push_back(part == 0 ? hi : v - hi);
+            }
+    }
+    if (!h->d_wimg[l]) e = cudaMalloc(&h->d_wimg[l], img.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size() * 4, cudaMemcpyHostToDevice);
+  }
+  return e;
+}
+
 template <int NODES>
 cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, float* geo, float* topo, cudaStream_t st) {
   using namespace tactor;
@@ -169,47 +215,9 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   h->device = device; h->nodes = nodes; h->max_batch = max_batch;
   if (const char* v = getenv("TACTOR_NCTA")) h->ncta = (atoi(v) == 2) ? 2 : 1;     // development switch (A/B timing)
   Guard g(device);
-  cudaError_t e = cudaSuccess;
-  for (int l = 0; l < TACTOR_NLAYERS && e == cudaSuccess; ++l) {
+  for (int l = 0; l < TACTOR_NLAYERS; ++l)
     if (!w->kernel[l] || !w->bias[l]) { tactor_destroy(h); return afail(TFEM_ERR_ARG, "missing layer weights"); }
-    const int kin = kIn[l], kout = kOut[l];
-    const int kpad = (kin + tactor::KC - 1) / tactor::KC * tactor::KC;
-    std::vector<float> wp((size_t)kpad * tactor::LD, 0.f), bp(tactor::LD, 0.f);
-    for (int i = 0; i < kin; ++i)
-      for (int o = 0; o < kout; ++o) wp[(size_t)i * tactor::LD + o] = w->kernel[l][(size_t)i * kout + o];
-    for (int o = 0; o < kout; ++o) bp[o] = w->bias[l][o];
-    e = cudaMalloc(&h->d_w[l], wp.size() * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_b[l], bp.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(h->d_w[l], wp.data(), wp.size() * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(h->d_b[l], bp.data(), bp.size() * 4, cudaMemcpyHostToDevice);
-  }
-  // tcgen05 operand images of the [200,200] layers: per 16-wide K chunk, per CTA of the pair (its half of the
-  // 208 columns), [hi|lo][kb][n][4 floats]
-  const int bn = tactor::tc::TCN / h->ncta;
-  for (int l = 4; l <= 10 && e == cudaSuccess; ++l) {
-    const int K = kIn[l], kout = kOut[l];
-    std::vector<float> img;
-    for (int c = 0; c * tactor::tc::KCH < K; ++c) {
-      const int kw = tactor::tc::chunk_kw(K, c), nkb = kw / 4;
-      for (int half = 0; half < h->ncta; ++half)
-      for (int part = 0; part < 2; ++part)
-        for (int kb = 0; kb < nkb; ++kb)
-          for (int nl = 0; nl < bn; ++nl)
-            for (int t = 0; t < 4; ++t) {
-              const int n = half * bn + nl;
-              const int k = c * tactor::tc::KCH + 4 * kb + t;
-              float v = (n < kout && k < K) ? w->kernel[l][(size_t)k * kout + n] : 0.f;
-              uint32_t bits;
-              memcpy(&bits, &v, 4);
-              bits &= 0xFFFFE000u;
-              float hi;
-              memcpy(&hi, &bits, 4);
-              img.push_back(part == 0 ? hi : v - hi);
-            }
-    }
-    e = cudaMalloc(&h->d_wimg[l], img.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size() * 4, cudaMemcpyHostToDevice);
-  }
+  cudaError_t e = upload_weights(h, w);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4096);
   if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4096);
   if (e == cudaSuccess) {
@@ -219,6 +227,17 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   if (e == cudaSuccess) e = cudaMalloc(&h->pooled, (size_t)max_batch * tactor::LD * 4);
   if (e != cudaSuccess) { tactor_destroy(h); return afail(TFEM_ERR_CUDA, std::string("actor setup: ") + cudaGetErrorString(e)); }
   *out = h;
+  return TFEM_OK;
+}
+
+int tactor_set_weights(tactor_handle_t h, const tactor_weights* w) {
+  if (!h || !w) return afail(TFEM_ERR_ARG, "null argument");
+  for (int l = 0; l < TACTOR_NLAYERS; ++l)
+    if (!w->kernel[l] || !w->bias[l]) return afail(TFEM_ERR_ARG, "missing layer weights");
+  Guard g(h->device);
+  cudaError_t e = cudaDeviceSynchronize();                  // no forward of this handle may still read the old weights
+  if (e == cudaSuccess) e = upload_weights(h, w);
+  if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("actor weights: ") + cudaGetErrorString(e));
   return TFEM_OK;
 }
 

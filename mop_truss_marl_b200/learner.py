@@ -1,0 +1,276 @@
+"""PyTorch-level DDPG learner of the three node agents: the consumer on the far side of the hot path
+(BASELINE.json configs[4]; SURVEY.md section 2 keeps it "PyTorch-level", only the gradient all-reduce is named).
+
+Restates ``train/code/truss2D_RL.py``:
+  * ``multimodes_actor``  (:49-127)  -> :class:`ActorNet`   (same parameters / names as the checkpoint and as
+    ``tactor_create``; the rollout uses the CUDA kernel, this module is the differentiable twin for the update)
+  * ``multimodes_critic`` (:130-266) -> :class:`CriticNet`  (10 + 11 GCNConv, sum-pool, concat, 3 Dense)
+  * ``MADDPG.remember / train / update`` (:458-700) -> :class:`MADDPGLearner`
+
+``GCNConv`` = ``A . (X . W) + b`` (spektral 1.2.0), ``GlobalSumPool`` = sum over nodes.  Quirks kept on purpose:
+the Pareto embedding is tiled and ``tf.reshape``-d, not transposed (:89-95, :190-195); the critic target averages the
+three per-agent next states (:611-618); the actor step builds a NEW Adam every call (:625, so every step is Adam's
+first step) with ``lr * 0.1`` and ``clipnorm=1``; targets move by ``tau = 0.005`` only every 1000 calls (:392-398).
+
+When the replay / learner is partitioned over ranks, gradients are averaged with ONE flat-buffer all-reduce per model
+update (:func:`allreduce_flat`): the only collective in the system (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import random
+from collections import deque
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from .tf_checkpoint import ACTOR_LAYERS
+
+ACTOR_SHAPES = {"gcn_l1_1": 13, "gcn_l1_2": 13, "gcn_l1_3": 13, "gcn_l1_4": 4}
+CRITIC_L1_IN = (13, 13, 13, 4, 2, 3, 2, 3, 2, 3)          # gcn_l1_1 .. gcn_l1_10 (:176-213)
+
+
+def _glorot_normal(fan_in, fan_out, gen):
+    std = float(np.sqrt(2.0 / (fan_in + fan_out)))
+    return torch.randn(fan_in, fan_out, generator=gen) * std
+
+
+class _GCN(nn.Module):
+    def __init__(self, fan_in, fan_out, gen):
+        super().__init__()
+        self.kernel = nn.Parameter(_glorot_normal(fan_in, fan_out, gen))
+        self.bias = nn.Parameter(torch.zeros(fan_out))
+
+    def forward(self, x, a):
+        return torch.matmul(a, torch.matmul(x, self.kernel)) + self.bias
+
+
+def _tile_reshape(pooled, n):
+    """tf.ragged.stack([pooled]*N, axis=-1) -> [B,H,N]; tf.reshape(..., (B,N,H)) (not a transpose)"""
+    b, h = pooled.shape
+    return pooled.unsqueeze(-1).expand(b, h, n).reshape(b, n, h)
+
+
+class ActorNet(nn.Module):
+    """``multimodes_actor`` (truss2D_RL.py:49-127).  ``forward`` returns (geo [B,N,2], topo [B,N,3])."""
+
+    def __init__(self, hidden=200, n_geo=2, n_topo=3, seed=20):
+        super().__init__()
+        gen = torch.Generator().manual_seed(seed)
+        fan = lambda name: ACTOR_SHAPES.get(name, hidden)  # noqa: E731
+        out = {"gcn_l4_1": n_geo, "gcn_l4_2": n_topo}
+        self.layers = nn.ModuleDict({name: _GCN(fan(name), out.get(name, hidden), gen) for name in ACTOR_LAYERS})
+
+    def forward(self, x_n, A_n, A_s, A_n_ts, A_n_cs, x_p, A_p):
+        L, relu = self.layers, torch.relu
+        if A_n.dim() == 2:
+            A_n = A_n.unsqueeze(0).expand(x_n.shape[0], -1, -1)
+        x11, x12, x13 = (relu(L[k](x_n, A_n)) for k in ("gcn_l1_1", "gcn_l1_2", "gcn_l1_3"))
+        x14 = _tile_reshape(relu(L["gcn_l1_4"](x_p, A_p)).sum(dim=1), x_n.shape[1])
+        s = (relu(L["gcn_l2_1"](x11, A_n)) + relu(L["gcn_l2_2"](x12, A_n_ts)) + relu(L["gcn_l2_3"](x12, A_n_cs))
+             + relu(L["gcn_l2_4"](x13, A_s)) + relu(L["gcn_l2_5"](x14, A_n)))
+        x31, x32 = relu(L["gcn_l3_1"](s, A_n)), relu(L["gcn_l3_2"](s, A_s))
+        return torch.sigmoid(L["gcn_l4_1"](x31, A_n)), torch.sigmoid(L["gcn_l4_2"](x32, A_n))
+
+    # ---- exchange with the CUDA actor / the TF checkpoint: {layer: (kernel [in,out], bias [out])} float32 numpy ----
+    def export_weights(self):
+        return {k: (m.kernel.detach().cpu().numpy().astype(np.float32).copy(),
+                    m.bias.detach().cpu().numpy().astype(np.float32).copy()) for k, m in self.layers.items()}
+
+    def import_weights(self, weights):
+        with torch.no_grad():
+            for k, m in self.layers.items():
+                m.kernel.copy_(torch.as_tensor(np.asarray(weights[k][0]), dtype=m.kernel.dtype))
+                m.bias.copy_(torch.as_tensor(np.asarray(weights[k][1]), dtype=m.bias.dtype))
+
+
+class CriticNet(nn.Module):
+    """``multimodes_critic`` (truss2D_RL.py:130-266): Q(state, own action, the two other agents' actions) [B,1]."""
+
+    def __init__(self, hidden=200, n_q=200, seed=21):
+        super().__init__()
+        gen = torch.Generator().manual_seed(seed)
+        self.l1 = nn.ModuleList([_GCN(f, hidden, gen) for f in CRITIC_L1_IN])
+        self.l2 = nn.ModuleList([_GCN(hidden, hidden, gen) for _ in range(11)])
+        self.dense_1, self.dense_2, self.dense_out = nn.Linear(11 * hidden, n_q), nn.Linear(n_q, n_q), nn.Linear(n_q, 1)
+        with torch.no_grad():
+            for d in (self.dense_1, self.dense_2):
+                d.weight.copy_(_glorot_normal(d.in_features, d.out_features, gen).t())
+                d.bias.zero_()
+            lim = float(np.sqrt(6.0 / (n_q + 1)))            # Dense(1): keras default glorot_uniform
+            self.dense_out.weight.copy_((torch.rand(1, n_q, generator=gen) * 2 - 1) * lim)
+            self.dense_out.bias.zero_()
+
+    def forward(self, x_n, A_n, A_s, A_n_ts, A_n_cs, x_p, A_p, self_g, self_t, o1_g, o1_t, o2_g, o2_t):
+        relu = torch.relu
+        if A_n.dim() == 2:
+            A_n = A_n.unsqueeze(0).expand(x_n.shape[0], -1, -1)
+        n = x_n.shape[1]
+        x1 = [relu(self.l1[i](x_n, A_n)) for i in range(3)]
+        x14 = _tile_reshape(relu(self.l1[3](x_p, A_p)).sum(dim=1), n)
+        acts = [relu(self.l1[4 + i](a, A_n)) for i, a in enumerate((self_g, self_t, o1_g, o1_t, o2_g, o2_t))]
+        x2 = [relu(self.l2[0](x1[0], A_n)), relu(self.l2[1](x1[1], A_n_ts)), relu(self.l2[2](x1[1], A_n_cs)),
+              relu(self.l2[3](x1[2], A_s))]
+        x2 += [relu(self.l2[4 + i](a, A_n)) for i, a in enumerate(acts)]
+        x2.append(relu(self.l2[10](x14, A_n)))
+        q = torch.cat([t.sum(dim=1) for t in x2], dim=-1)     # GlobalSumPool + Concatenate -> [B, 11*hidden]
+        return self.dense_out(relu(self.dense_2(relu(self.dense_1(q)))))
+
+
+def allreduce_flat(params, group=None):
+    """Average the gradients of ``params`` over the process group with ONE all-reduce on a flat buffer."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return flat.numel()
+
+
+def _clip_global_norm(params, max_norm=1.0):
+    """keras ``clipnorm``: every gradient tensor is clipped to ``max_norm`` on its OWN norm"""
+    for p in params:
+        if p.grad is not None:
+            nrm = p.grad.norm()
+            if nrm > max_norm:
+                p.grad.mul_(max_norm / nrm)
+
+
+class _Agent:
+    def __init__(self, lr, hidden, n_q, seed, device):
+        self.actor, self.target_actor = ActorNet(hidden, seed=seed).to(device), ActorNet(hidden, seed=seed).to(device)
+        self.critic, self.target_critic = CriticNet(hidden, n_q, seed=seed + 1).to(device), CriticNet(hidden, n_q, seed=seed + 1).to(device)
+        self.lr, self.tau, self.update_num = lr, 0.005, 0
+        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=lr, eps=1e-7)
+        self.update_init()
+
+    @staticmethod
+    def _blend(dst, src, tau):
+        with torch.no_grad():
+            for d, s in zip(dst.parameters(), src.parameters()):
+                d.copy_(s if tau >= 1.0 else s * tau + d * (1.0 - tau))
+
+    def update_init(self):
+        self._blend(self.target_actor, self.actor, 1.0)
+        self._blend(self.target_critic, self.critic, 1.0)
+
+    def update(self):
+        """``multimodals_OneAgent.update`` (:392-400): soft update only when ``update_num == 1000``"""
+        if self.update_num == 1000:
+            self._blend(self.target_actor, self.actor, self.tau)
+            self._blend(self.target_critic, self.critic, self.tau)
+            self.update_num = 0
+            return True
+        return False
+
+
+STATE_KEYS = ("x_n", "A_n", "A_s", "A_n_ts", "A_n_cs", "x_p", "A_p")
+
+
+class MADDPGLearner:
+    """Replay + update of the three agents (``MADDPG.remember / train / update``).
+
+    A transition is ``(state, [(geo_k, topo_k)]*3, rewards[3], [next_state_k]*3, done)`` where a state is the tuple
+    ``(x_n, A_n, A_s, A_n_ts, A_n_cs, x_p, A_p)`` of one environment; ``remember_batch`` takes the same with a leading
+    batch axis (what the batched environment produces).  ``train()`` samples ``batch_size`` transitions and does, per
+    agent, the critic regression and the actor ascent; gradients are all-reduced when a process group is initialised.
+    """
+
+    def __init__(self, lr=1e-7, gamma=0.99, hidden=200, n_q=200, max_mem=100000, batch_size=32, device="cpu", seed=20):
+        self.device = torch.device(device)
+        self.gamma, self.batch_size = gamma, batch_size
+        self.agents = [_Agent(lr, hidden, n_q, seed + 10 * k, self.device) for k in range(3)]
+        self.memory = deque(maxlen=max_mem)
+        self.rng = random.Random(seed)
+        self.allreduced_elements = 0
+        self.last_losses = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _to(self, a):
+        return torch.as_tensor(np.asarray(a), dtype=torch.float32)
+
+    def remember(self, state, actions, rewards, next_states, done):
+        st = tuple(self._to(s) for s in state)
+        self.memory.append((st, tuple((self._to(g), self._to(t)) for g, t in actions), self._to(rewards),
+                            tuple(tuple(self._to(s) for s in ns) for ns in next_states), float(done)))
+
+    def remember_batch(self, state, actions, rewards, next_states, done):
+        b = len(np.asarray(rewards))
+        for i in range(b):
+            pick = lambda tup: tuple((np.asarray(s) if np.asarray(s).ndim == 2 and k == 1 else np.asarray(s)[i])  # noqa: E731
+                                     for k, s in enumerate(tup))
+            self.remember(pick(state), [(np.asarray(g)[i], np.asarray(t)[i]) for g, t in actions], np.asarray(rewards)[i],
+                          [pick(ns) for ns in next_states], np.asarray(done).reshape(-1)[i] if np.ndim(done) else done)
+
+    # ------------------------------------------------------------------------------------------------
+    def _stack_state(self, states):
+        return tuple(torch.stack([s[j] for s in states]).to(self.device) for j in range(len(STATE_KEYS)))
+
+    def train(self):
+        """one ``MADDPG.train()`` call (:463-689); returns False while the replay holds fewer than ``batch_size``"""
+        if len(self.memory) < self.batch_size:
+            return False
+        samples = self.rng.sample(list(self.memory), self.batch_size)
+        S = self._stack_state([m[0] for m in samples])
+        NS = [self._stack_state([m[3][k] for m in samples]) for k in range(3)]
+        A = [(torch.stack([m[1][k][0] for m in samples]).to(self.device),
+              torch.stack([m[1][k][1] for m in samples]).to(self.device)) for k in range(3)]
+        R = torch.stack([m[2] for m in samples]).to(self.device)                    # [B,3]
+        done = torch.tensor([m[4] for m in samples], device=self.device)
+        order = {0: (0, 1, 2), 1: (1, 0, 2), 2: (2, 0, 1)}                           # own action first (:560-562)
+        with torch.no_grad():
+            # next actions of every target actor on every agent's next state, then the target critics (:564-606)
+            nxt = [[self.agents[j].target_actor(*NS[f]) for j in range(3)] for f in range(3)]
+            q_next = []
+            for k in range(3):
+                o = order[k]
+                qs = [self.agents[k].target_critic(*NS[f], *nxt[f][o[0]], *nxt[f][o[1]], *nxt[f][o[2]]) for f in range(3)]
+                q_next.append((qs[0] + qs[1] + qs[2]) / 3.0)
+        losses = []
+        for k, ag in enumerate(self.agents):
+            o = order[k]
+            y = torch.where(done.view(-1, 1) == 1.0, R[:, k:k + 1], R[:, k:k + 1] + self.gamma * q_next[k])
+            # critic: train_on_batch with mse, Adam(lr, clipnorm=1) (:619)
+            ag.critic_opt.zero_grad(set_to_none=True)
+            q = ag.critic(*S, *A[o[0]], *A[o[1]], *A[o[2]])
+            c_loss = torch.mean((q - y) ** 2)
+            c_loss.backward()
+            self.allreduced_elements += allreduce_flat(list(ag.critic.parameters()))
+            _clip_global_norm(ag.critic.parameters(), 1.0)
+            ag.critic_opt.step()
+            # actor: maximise the critic's value of the three CURRENT actors' actions; gradient to agent k only (:620-625)
+            for p in ag.actor.parameters():
+                p.grad = None
+            pred = [self.agents[j].actor(*S) for j in range(3)]
+            a_loss = -ag.critic(*S, *pred[o[0]], *pred[o[1]], *pred[o[2]]).mean()
+            grads = torch.autograd.grad(a_loss, list(ag.actor.parameters()), allow_unused=True)
+            for p, g in zip(ag.actor.parameters(), grads):
+                p.grad = g if g is not None else torch.zeros_like(p)
+            self.allreduced_elements += allreduce_flat(list(ag.actor.parameters()))
+            _clip_global_norm(ag.actor.parameters(), 1.0)
+            # a NEW Adam every call (:625): its first step is lr * g / (|g| + eps)
+            with torch.no_grad():
+                for p in ag.actor.parameters():
+                    p.add_(-(ag.lr * 0.1) * p.grad / (p.grad.abs() + 1e-7))
+            losses.append((float(c_loss.detach()), float(a_loss.detach())))
+        self.last_losses = losses
+        return True
+
+    def update(self):
+        """``MADDPG.update`` (:692-697): every 300 actor calls let each agent check its own counter"""
+        interval = len(self.agents) * 100
+        if self.agents[0].update_num % interval == 0:
+            return [a.update() for a in self.agents]
+        return None
+
+    def actor_weights(self, k):
+        """weights of agent k's online actor -- the model ``act`` uses (:340) -- for ``BatchedActor.set_weights``"""
+        return self.agents[k].actor.export_weights()

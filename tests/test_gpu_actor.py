@@ -111,3 +111,36 @@ def test_act_noise_statistics():
     assert abs(np.mean(z ** 3)) < 0.05 and abs(np.mean(z ** 4) - 3.0) < 0.1
     assert not torch.equal(geo1, geo2)               # a new call draws new noise
     assert a.update_num == 2
+
+
+def test_set_weights_and_learner_round_trip():
+    """tactor_set_weights on a live handle; the PyTorch learner's ActorNet (the differentiable twin used for the DDPG
+    update) and the CUDA kernel agree before and after a training step."""
+    from mop_truss_marl_b200 import actor, learner, tf_checkpoint
+    rng = np.random.RandomState(7)
+    N, B = 16, 24
+    inp = random_inputs(rng, B, N, 2)
+    dev = [torch.from_numpy(t).cuda() for t in inp]
+    w0 = tf_checkpoint.random_actor_weights(seed=1)
+    a = actor.BatchedActor(w0, N, max_batch=B)
+    g0, t0 = a.forward(*dev)
+    lrn = learner.MADDPGLearner(lr=1e-2, batch_size=8, device="cuda", seed=9)
+    net = lrn.agents[0].actor
+    a.set_weights(net.export_weights())
+    g1, t1 = a.forward(*dev)
+    with torch.no_grad():
+        gn, tn = net(*dev)
+    assert (g1 - gn).abs().max() <= ATOL and (t1 - tn).abs().max() <= ATOL
+    assert (g1 - g0).abs().max() > 1e-3                  # the weights really changed
+    for _ in range(12):
+        s = [t if t.ndim == 2 else t[0] for t in inp]
+        lrn.remember(s, [(rng.rand(N, 2).astype(np.float32), rng.rand(N, 3).astype(np.float32)) for _ in range(3)],
+                     rng.randn(3).astype(np.float32), [s, s, s], 0)
+    assert lrn.train()
+    a.set_weights(lrn.actor_weights(0))
+    g2, t2 = a.forward(*dev)
+    with torch.no_grad():
+        gn2, tn2 = net(*dev)
+    assert (g2 - gn2).abs().max() <= ATOL and (t2 - tn2).abs().max() <= ATOL
+    assert not torch.equal(g2, g1)
+    a.check()

@@ -116,6 +116,23 @@ def test_dropin_actor_act(mods):
     assert maddpg.agents[0].update_num == 1
     point, S = game._game_modify(st[8], st[9], st[10], [geo, topo])
     assert len(point) == 4 and geo.max() <= 1 and geo.min() >= 0            # clipped in place
-    with pytest.raises(NotImplementedError):
-        maddpg.train()
     assert maddpg.agents[1].critic_model.load_weights("nowhere").expect_partial() is not None
+    # the learner side of the drop-in: remember / train / update as the driver calls them (master...:612-649)
+    maddpg.train()                                           # fewer than 32 transitions: returns silently (:491-494)
+    state8 = list(st[:8])                                    # (x_n, A_n, A_s, A_n_ts, A_n_cs, mask, x_pf, A_pf)
+    child8 = list(S[:5]) + [st[5], st[6], st[7]]
+    for i in range(33):
+        acts = []
+        for k in range(3):
+            acts += [np.random.rand(16, 2).astype(np.float32), np.random.rand(16, 3).astype(np.float32)]
+        maddpg.remember(state8, *acts, [0.1 * i, -0.2, 0.3], child8, child8, child8, 1 if i == 5 else 0, 16)
+    w_before = maddpg.agents[0].actor_model.weights["gcn_l3_1"][0].copy()
+    geo_b, _ = maddpg.agents[0].act(st[0], st[1], st[2], st[3], st[4], st[6], st[7])
+    maddpg.train()
+    w_after = maddpg.agents[0].actor_model.weights["gcn_l3_1"][0]
+    # Adam's first step at lr * 0.1 = 1e-8 (:625): one float32 ulp of a 0.07-sized weight is 7.5e-9, so a weight moves
+    # by 0, 1 or 2 ulps
+    assert 0 < np.abs(w_after - w_before).max() <= 2e-8
+    maddpg.update()
+    geo_a, _ = maddpg.agents[0].act(st[0], st[1], st[2], st[3], st[4], st[6], st[7])
+    assert geo_a.shape == geo_b.shape
