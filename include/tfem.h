@@ -65,7 +65,7 @@ typedef struct tfem_family_desc {
 typedef struct tfem_dims {
   int32_t N, E, ndof, nres;           /* nres = 2N - ndof restrained DOFs */
   int32_t num_x, n_internal, band;    /* internal banded system: n_internal = 4*num_x, half-bandwidth */
-  int32_t reserved;
+  int32_t device;                     /* CUDA device of the handle, -1 for a tables-only handle */
 } tfem_dims;
 
 /* constant tables (tfem_get_table): what the reference recomputes on every call although it never

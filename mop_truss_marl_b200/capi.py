@@ -31,7 +31,7 @@ class FamilyDesc(C.Structure):
 
 class Dims(C.Structure):
     _fields_ = [("N", C.c_int32), ("E", C.c_int32), ("ndof", C.c_int32), ("nres", C.c_int32),
-                ("num_x", C.c_int32), ("n_internal", C.c_int32), ("band", C.c_int32), ("reserved", C.c_int32)]
+                ("num_x", C.c_int32), ("n_internal", C.c_int32), ("band", C.c_int32), ("device", C.c_int32)]
 
 
 class StepIn(C.Structure):

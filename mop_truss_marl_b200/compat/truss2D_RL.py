@@ -118,8 +118,10 @@ class MADDPG:
 
     def remember(self, state, a0_g, a0_t, a1_g, a1_t, a2_g, a2_t, reward, next_state1, next_state2, next_state3,
                  done, n_node):
-        self.temprp[0].append([state, a0_g, a0_t, a1_g, a1_t, a2_g, a2_t, reward, next_state1, next_state2,
-                               next_state3, done])
+        t = [state, a0_g, a0_t, a1_g, a1_t, a2_g, a2_t, reward, next_state1, next_state2, next_state3, done]
+        self.temprp[0].append(t)
+        self._pending = getattr(self, "_pending", [])
+        self._pending.append(t)                              # handed to the learner's replay at the next train()
 
     # ---- learner: PyTorch-level restatement of MADDPG.train / update (mop_truss_marl_b200/learner.py) ----
     def _learner(self):
@@ -132,20 +134,17 @@ class MADDPG:
             for k, a in enumerate(self.agents):              # carry over loaded checkpoints (critic weights do not exist)
                 self._lrn.agents[k].actor.import_weights(a.actor_model.weights)
                 self._lrn.agents[k].update_init()
-            self._seen = 0
         return self._lrn
 
     def train(self):
         lrn = self._learner()
-        mem = self.temprp[0]
         # move the transitions remembered since the last call into the learner's replay
-        fresh = list(mem)[self._seen:] if self._seen <= len(mem) else list(mem)
+        fresh, self._pending = getattr(self, "_pending", []), []
         for t in fresh:
             state = [t[0][i] for i in (0, 1, 2, 3, 4, 6, 7)]                      # the reference's tuple carries mask at [5]
             nxt = [[ns[i] for i in (0, 1, 2, 3, 4, 6, 7)] for ns in (t[8], t[9], t[10])]
             lrn.remember(state, [(t[1], t[2]), (t[3], t[4]), (t[5], t[6])], np.asarray(t[7], dtype=np.float32), nxt,
                          1 if t[11] == 1 else 0)
-        self._seen = len(mem)
         if not lrn.train():
             return
         for k, a in enumerate(self.agents):                  # the rollout acts with the updated online actor (:340)

@@ -108,7 +108,7 @@ int tfem_get_dims(tfem_handle_t h, tfem_dims* out) {
   if (!h || !out) return fail(TFEM_ERR_ARG, "null argument");
   const tfem::FamilyTables& t = h->fam.t;
   out->N = t.N; out->E = t.E; out->ndof = t.ndof; out->nres = t.nres;
-  out->num_x = t.nx; out->n_internal = 4 * t.nx; out->band = 7; out->reserved = 0;
+  out->num_x = t.nx; out->n_internal = 4 * t.nx; out->band = 7; out->device = h->device;
   return TFEM_OK;
 }
 

@@ -3,7 +3,7 @@
 // BASELINE.json's north_star names this variant for the large meshes (ndof = 60).  The production path
 // (tfem_kernels.cu) instead renumbers the DOFs by chord column, which makes K banded with half-bandwidth 7 for
 // every num_x, and factors the band.  This file builds the named variant so that the choice rests on a
-// measurement and not on an argument (bench.py --solver-compare, profiles/): K is assembled DENSE in the
+// measurement and not on an argument (scripts/solver_compare.py, profiles/): K is assembled DENSE in the
 // reference's own free-DOF order (FEM_2Dtruss.py:227-261, 310-324) and factored by a right-looking blocked
 // Cholesky, block size 8:
 //
@@ -148,13 +148,9 @@ dense_dmma_solve_kernel(const FamilyTables* __restrict__ fam, int B, const doubl
 
 int dense_solve_launch(const FamilyTables* d_tables, int B, const double* y, const int32_t* section, double* d,
                        int32_t* status, cudaStream_t stream) {
-  static bool configured = false;
   const int smem = (DN * DLD + DN) * (int)sizeof(double);
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dense_dmma_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(dense_dmma_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;                       // per call: the attribute is per device
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

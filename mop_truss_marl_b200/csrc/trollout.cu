@@ -55,7 +55,11 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
   if (tfem_get_dims(env, &h->dims) != TFEM_OK) { delete h; return rfail(TFEM_ERR_ARG, "bad env handle"); }
   int piece = (max_batch + pieces - 1) / pieces;
   h->piece = (piece + 31) / 32 * 32;               // piece boundaries on 32 environments: every sub-array stays 16-byte aligned
-  cudaError_t e = cudaGetDevice(&h->device);
+  h->device = h->dims.device;
+  if (h->device < 0) { delete h; return rfail(TFEM_ERR_CUDA, "tables-only env handle: libtfem has no CPU path"); }
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  cudaError_t e = cudaSetDevice(h->device);
   const size_t B = (size_t)max_batch, N = h->dims.N, E = h->dims.E;
   if (e == cudaSuccess) e = dalloc(h, &h->d.x_n, B * N * 13);
   if (e == cudaSuccess) e = dalloc(h, &h->d.A_s, B * N * N);
@@ -88,6 +92,7 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
     if (e == cudaSuccess) { h->ev_in.push_back(a); e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming); }
     if (e == cudaSuccess) h->ev_run.push_back(b);
   }
+  if (prev_dev >= 0) cudaSetDevice(prev_dev);
   if (e != cudaSuccess) {
     trollout_destroy(h);
     return rfail(TFEM_ERR_CUDA, std::string("rollout setup: ") + cudaGetErrorString(e));
@@ -128,7 +133,10 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
   if (io->P < 1 || io->P > PMAX) return rfail(TFEM_ERR_ARG, "P must be in 1..50");
   const size_t N = h->dims.N, E = h->dims.E, P = (size_t)io->P;
   const Dev& d = h->d;
-  cudaError_t e = cudaSuccess;
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  cudaError_t e = (prev_dev == h->device) ? cudaSuccess : cudaSetDevice(h->device);
+  struct Restore { int dev; ~Restore() { if (dev >= 0) cudaSetDevice(dev); } } restore{prev_dev == h->device ? -1 : prev_dev};
   auto up = [&](void* dst, const void* src, size_t bytes) {
     if (e == cudaSuccess && src) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->s_in);
   };

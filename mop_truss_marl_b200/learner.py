@@ -203,12 +203,15 @@ class MADDPGLearner:
                             tuple(tuple(self._to(s) for s in ns) for ns in next_states), float(done)))
 
     def remember_batch(self, state, actions, rewards, next_states, done):
-        b = len(np.asarray(rewards))
-        for i in range(b):
-            pick = lambda tup: tuple((np.asarray(s) if np.asarray(s).ndim == 2 and k == 1 else np.asarray(s)[i])  # noqa: E731
-                                     for k, s in enumerate(tup))
-            self.remember(pick(state), [(np.asarray(g)[i], np.asarray(t)[i]) for g, t in actions], np.asarray(rewards)[i],
-                          [pick(ns) for ns in next_states], np.asarray(done).reshape(-1)[i] if np.ndim(done) else done)
+        """the same with a leading batch axis on every array (``A_n`` may stay [N,N]): what the batched environment
+        and actor produce; ``rewards`` [B,3], ``done`` [B] or a scalar"""
+        rewards = np.asarray(rewards)
+
+        def row(tup, i):
+            return tuple(np.asarray(s) if (k == 1 and np.asarray(s).ndim == 2) else np.asarray(s)[i] for k, s in enumerate(tup))
+        for i in range(rewards.shape[0]):
+            self.remember(row(state, i), [(np.asarray(g)[i], np.asarray(t)[i]) for g, t in actions], rewards[i],
+                          [row(ns, i) for ns in next_states], np.asarray(done).reshape(-1)[i] if np.ndim(done) else done)
 
     # ------------------------------------------------------------------------------------------------
     def _stack_state(self, states):
