@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
 ]
-SOURCES = ["tfem_family.cu", "tfem_kernels.cu", "tfem_dense.cu", "tfem_capi.cu", "tactor.cu", "trollout.cu"]
+SOURCES = ["tfem_family.cu", "tfem_kernels.cu", "tfem_dense.cu", "tfem_capi.cu", "tactor.cu", "trollout.cu", "tpareto.cu"]
 
 
 def _stale(target: str, deps) -> bool:
@@ -31,6 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps.append(os.path.join(os.path.dirname(HERE), "include", "tfem.h"))
     deps.append(os.path.join(os.path.dirname(HERE), "include", "tactor.h"))
     deps.append(os.path.join(os.path.dirname(HERE), "include", "trollout.h"))
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "tpareto.h"))
     if force or _stale(LIB_PATH, deps):
         nvcc = os.environ.get("NVCC", "nvcc")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs

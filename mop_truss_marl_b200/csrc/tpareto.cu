@@ -1,0 +1,199 @@
+// Batched Pareto front + spread statistics + hypervolume (include/tpareto.h): one warp per environment, points in
+// shared memory, every step O(P^2) or a warp reduction -- P <= 64, so an environment costs a few thousand
+// instructions and the kernel is bound by the load of its 16 P bytes.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/tfem.h"
+#include "../../include/tpareto.h"
+
+namespace {
+thread_local std::string g_pareto_err;
+int pfail(int code, const std::string& m) { g_pareto_err = m; return code; }
+
+constexpr int MAXP = TPARETO_MAX_POINTS;
+constexpr int WARPS = 4;
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+  for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+pareto_front_hv_kernel(int B, int P, const float* __restrict__ points, const int32_t* __restrict__ counts, double rx,
+                       double ry, int32_t* __restrict__ front_idx, int32_t* __restrict__ front_len,
+                       double* __restrict__ stats, double* __restrict__ hv) {
+  __shared__ float4 pt[WARPS][MAXP];       // the environment's points
+  __shared__ int order[WARPS][MAXP];       // front members in sorted order
+  __shared__ double fx[WARPS][MAXP], fy[WARPS][MAXP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * WARPS + warp; b < B; b += gridDim.x * WARPS) {
+    const int n = counts ? min(max(counts[b], 0), P) : P;
+    for (int i = lane; i < n; i += 32) pt[warp][i] = reinterpret_cast<const float4*>(points)[(size_t)b * P + i];
+    __syncwarp();
+    // ---- feasibility, duplicates, dominance (utils.py:17-54) ----
+    bool on_front[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int i = lane + 32 * s;
+      bool keep = false;
+      if (i < n) {
+        const float4 p = pt[warp][i];
+        keep = !(p.z > 1.f || p.w > 1.f);
+        for (int j = 0; j < n && keep; ++j) {
+          const float4 q = pt[warp][j];
+          if (q.z > 1.f || q.w > 1.f) continue;
+          if (q.x < p.x && q.y < p.y) keep = false;                                      // dominated
+          if (j < i && q.x == p.x && q.y == p.y && q.z == p.z && q.w == p.w) keep = false;   // same tuple: kept once
+        }
+      }
+      on_front[s] = keep;
+    }
+    // ---- rank among the front members by (obj1 ascending, obj2 descending, index) (:57) ----
+    const unsigned m0 = __ballot_sync(0xffffffffu, on_front[0]), m1 = __ballot_sync(0xffffffffu, on_front[1]);
+    const int F = __popc(m0) + __popc(m1);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int i = lane + 32 * s;
+      if (on_front[s]) {
+        const float4 p = pt[warp][i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+          const bool member = (j < 32 ? (m0 >> j) : (m1 >> (j - 32))) & 1u;
+          if (!member || j == i) continue;
+          const float4 q = pt[warp][j];
+          if (q.x < p.x || (q.x == p.x && (q.y > p.y || (q.y == p.y && j < i)))) ++rank;
+        }
+        order[warp][rank] = i;
+        fx[warp][rank] = (double)p.x;
+        fy[warp][rank] = (double)p.y;
+      }
+    }
+    __syncwarp();
+    if (front_len && lane == 0) front_len[b] = F;
+    if (front_idx)
+      for (int i = lane; i < P; i += 32) front_idx[(size_t)b * P + i] = (i < F) ? order[warp][i] : -1;
+    // ---- spread statistics (:159-195) ----
+    double dsum = 0.0, dmax = 0.0, d[2] = {0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int k = lane + 32 * s;
+      if (k + 1 < F) {
+        const double ax = fx[warp][k] - fx[warp][k + 1], ay = fy[warp][k] - fy[warp][k + 1];
+        d[s] = sqrt(ax * ax + ay * ay);
+        dsum += d[s];
+        dmax = fmax(dmax, d[s]);
+      }
+    }
+    dsum = warp_sum(dsum);
+    dmax = warp_max(dmax);
+    double max_d = 0.0, dis_d = 1.0, sum_d = 0.0;
+    if (F >= 2) {
+      const double nd = (double)(F - 1), centre = dmax / nd;
+      double acc = 0.0;
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+        if (lane + 32 * s + 1 < F) acc += (d[s] - centre) * (d[s] - centre);
+      acc = warp_sum(acc);
+      max_d = dmax; sum_d = dsum; dis_d = sqrt(acc / nd);
+    }
+    double std_cd = 1.0, p_inv = 0.0;
+    if (F > 3) {
+      double c[2] = {0.0, 0.0}, csum = 0.0, cmax = 0.0;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int k = lane + 32 * s;                        // interior point k+1
+        if (k + 2 < F) {
+          c[s] = fabs(fx[warp][k] - fx[warp][k + 2]) + fabs(fy[warp][k] - fy[warp][k + 2]);
+          csum += c[s];
+          cmax = fmax(cmax, c[s]);
+        }
+      }
+      csum = warp_sum(csum);
+      cmax = warp_max(cmax);
+      if (csum != 0.0) {
+        const double nc = (double)(F - 2);
+        double mean = 0.0, p10 = 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (lane + 32 * s + 2 < F) { c[s] /= cmax; mean += c[s]; const double c2 = c[s] * c[s], c4 = c2 * c2; p10 += c4 * c4 * c2; }
+        mean = warp_sum(mean) / nc;
+        p10 = warp_sum(p10);
+        double var = 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          if (lane + 32 * s + 2 < F) var += (c[s] - mean) * (c[s] - mean);
+        var = warp_sum(var);
+        std_cd = sqrt(var / nc);
+        p_inv = pow(p10, 0.1);
+      }
+    }
+    if (stats && lane == 0) {
+      double* o = stats + (size_t)b * 5;
+      o[0] = max_d; o[1] = dis_d; o[2] = p_inv; o[3] = sum_d; o[4] = std_cd;
+    }
+    // ---- hypervolume of the front (:463-530): integral of the running maximum height over the sorted x ----
+    if (hv) {
+      double area = 0.0, minx = INFINITY, miny = INFINITY;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int k = lane + 32 * s;
+        if (k < F) {
+          double h = 0.0;
+          for (int j = 0; j <= k; ++j) h = fmax(h, 1.0 - fmin(fy[warp][j], 1.0));      // the front is sorted by x
+          const double x0 = fmin(fx[warp][k], 1.0), x1 = (k + 1 < F) ? fmin(fx[warp][k + 1], 1.0) : 1.0;
+          area += (x1 - x0) * h;
+          minx = fmin(minx, fx[warp][k]);
+          miny = fmin(miny, fy[warp][k]);
+        }
+      }
+      area = warp_sum(area);
+      minx = warp_min(minx);
+      miny = warp_min(miny);
+      double out = 0.0;
+      if (F > 0 && !(F == 1 && fx[warp][0] == 1.0 && fy[warp][0] == 1.0))
+        out = area - ((1.0 - rx) * (1.0 - minx) + (1.0 - ry) * (1.0 - miny) - (1.0 - rx) * (1.0 - ry));
+      if (lane == 0) hv[b] = out;
+    }
+    __syncwarp();
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char* tpareto_last_error(void) { return g_pareto_err.c_str(); }
+
+int tpareto_front_hv(int B, int P, const float* points, const int32_t* counts, const double* ref_point,
+                     int32_t* front_idx, int32_t* front_len, double* stats, double* hv, void* stream) {
+  if (!points) return pfail(TFEM_ERR_ARG, "null argument");
+  if (B < 0) return pfail(TFEM_ERR_ARG, "negative batch");
+  if (P < 1 || P > TPARETO_MAX_POINTS) return pfail(TFEM_ERR_ARG, "P must be in 1..64");
+  if (reinterpret_cast<uintptr_t>(points) & 15u) return pfail(TFEM_ERR_ALIGN, "points must be 16-byte aligned");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pfail(TFEM_ERR_CUDA, "no CUDA device: no CPU path");
+  if (B == 0) return TFEM_OK;
+  const double rx = ref_point ? ref_point[0] : 1.0, ry = ref_point ? ref_point[1] : 1.0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int need = (B + WARPS - 1) / WARPS;
+  const int grid = need < sms * 8 ? need : sms * 8;
+  pareto_front_hv_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(B, P, points, counts, rx, ry, front_idx, front_len,
+                                                                        stats, hv);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(TFEM_ERR_CUDA, std::string("pareto kernel: ") + cudaGetErrorString(e));
+  return TFEM_OK;
+}
+
+}  // extern "C"

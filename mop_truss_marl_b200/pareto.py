@@ -1,0 +1,46 @@
+"""Batched Pareto-front bookkeeping on the GPU (C ABI in ``include/tpareto.h``): ``utils.simple_cull`` and
+``utils.union_rectangles_fastest`` of the reference (``test/*/code/utils.py:11-217, 463-530``) for B environments at
+once.  PyTorch only provides the device buffers and the stream."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import capi
+
+PARETO_EXPORTS = ("tpareto_last_error", "tpareto_front_hv")
+MAX_POINTS = 64
+
+_lib = capi.lib
+_lib.tpareto_last_error.restype = C.c_char_p
+_lib.tpareto_front_hv.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 8
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def front_hv(points: torch.Tensor, counts: torch.Tensor | None = None, ref_point=(1.0, 1.0)):
+    """points [B,P,4] float32 CUDA (obj1, obj2, con1, con2), counts [B] int32 (valid points per environment).
+    Returns ``front_idx`` [B,P] (front members in the reference's order, -1 padded), ``front_len`` [B],
+    ``stats`` [B,5] = (max_distance, dis_distance, p_norm_inv_cd, sum_distance, std_cd) and ``hv`` [B]."""
+    if not (points.is_cuda and points.dtype == torch.float32 and points.dim() == 3 and points.shape[2] == 4
+            and points.is_contiguous()):
+        raise ValueError("points must be a contiguous float32 CUDA tensor [B,P,4]")
+    B, P = int(points.shape[0]), int(points.shape[1])
+    if counts is not None and not (counts.is_cuda and counts.dtype == torch.int32 and tuple(counts.shape) == (B,)):
+        raise ValueError("counts must be an int32 CUDA tensor [B]")
+    dev = points.device
+    front_idx = torch.empty(B, P, dtype=torch.int32, device=dev)
+    front_len = torch.empty(B, dtype=torch.int32, device=dev)
+    stats = torch.empty(B, 5, dtype=torch.float64, device=dev)
+    hv = torch.empty(B, dtype=torch.float64, device=dev)
+    ref = (C.c_double * 2)(float(ref_point[0]), float(ref_point[1]))
+    with torch.cuda.device(dev):
+        rc = _lib.tpareto_front_hv(B, P, _ptr(points), _ptr(counts), C.cast(ref, C.c_void_p), _ptr(front_idx),
+                                   _ptr(front_len), _ptr(stats), _ptr(hv),
+                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc != 0:
+        raise capi.TfemError("libtfem pareto error %d: %s" % (rc, _lib.tpareto_last_error().decode()))
+    return {"front_idx": front_idx, "front_len": front_len, "stats": stats, "hv": hv}

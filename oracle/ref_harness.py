@@ -78,6 +78,22 @@ def _install_stubs() -> None:
         su.degree_power = degree_power
 
 
+def load_utils(run: str = "small_bridge"):
+    """the reference's ``utils.py`` (Pareto filter, hypervolume) of one run directory, imported in isolation"""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    code_dir = os.path.join(REF_ROOT, RUN_DIRS[run])
+    saved = {k: sys.modules.pop(k) for k in ("utils", "set_seed_global") if k in sys.modules}
+    sys.path.insert(0, code_dir)
+    try:
+        return importlib.import_module("utils")
+    finally:
+        sys.path.remove(code_dir)
+        for k in ("utils", "set_seed_global"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+
+
 class RefModules:
     """The reference modules of one run directory, imported in isolation."""
 

@@ -27,6 +27,12 @@ def test_exports_match_header():
     assert declared2 == set(actor.ACTOR_EXPORTS)
     for name in declared2:
         assert hasattr(capi.lib, name), name
+    hdr4 = open(os.path.join(ROOT, "include", "tpareto.h")).read()
+    declared4 = set(re.findall(r"\b(tpareto_[a-z_0-9]+)\s*\(", hdr4))
+    from mop_truss_marl_b200 import pareto
+    assert declared4 == set(pareto.PARETO_EXPORTS)
+    for name in declared4:
+        assert hasattr(capi.lib, name), name
     hdr3 = open(os.path.join(ROOT, "include", "trollout.h")).read()
     declared3 = set(re.findall(r"\b(trollout_[a-z_0-9]+)\s*\(", hdr3))
     from mop_truss_marl_b200 import host_pipeline

@@ -1,0 +1,74 @@
+"""GPU: tpareto_front_hv against the golden vectors recorded from the reference's utils.py and against the CPU oracle
+on random batches (front membership and order exact, statistics and hypervolume to 1e-12 in float64)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run(points64, counts, ref):
+    from mop_truss_marl_b200 import pareto
+    pts = torch.from_numpy(np.nan_to_num(points64, nan=0.0).astype(np.float32)).cuda()
+    out = pareto.front_hv(pts, torch.from_numpy(counts.astype(np.int32)).cuda(), ref)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}, pts.cpu().numpy().astype(np.float64)
+
+
+def check_against_oracle(out, pts32, counts, ref):
+    from oracle import pareto_oracle
+    for b in range(len(counts)):
+        p = pts32[b, :counts[b]]
+        try:
+            idx = pareto_oracle.front_indices(p)
+        except IndexError:
+            assert out["front_len"][b] == 0 and out["hv"][b] == 0.0
+            assert np.array_equal(out["stats"][b], [0.0, 1.0, 0.0, 0.0, 1.0])
+            continue
+        F = len(idx)
+        assert out["front_len"][b] == F
+        assert np.array_equal(out["front_idx"][b, :F], idx) and (out["front_idx"][b, F:] == -1).all()
+        _, max_d, dis_d, p_cd, sum_d, std_cd = pareto_oracle.front_stats(p)
+        assert np.allclose(out["stats"][b], [max_d, dis_d, p_cd, sum_d, std_cd], rtol=1e-12, atol=1e-14), b
+        assert abs(out["hv"][b] - pareto_oracle.hypervolume(p[idx], ref)) <= 1e-12, b
+
+
+def test_golden_from_reference():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pareto.npz"))
+    for r, ref in enumerate(g["refs"]):
+        out, pts32 = run(g["points"], g["counts"], ref)
+        # the kernel sees the float32-rounded points: same front (the golden sets have no near-ties), statistics within
+        # float32 rounding of the inputs
+        assert np.array_equal(out["front_len"], g["front_len"])
+        for b in range(len(g["counts"])):
+            F = g["front_len"][b]
+            got = pts32[b][out["front_idx"][b, :F]][:, :2]
+            assert np.allclose(got, g["fronts"][b, :F], rtol=0, atol=1e-7)
+        assert np.allclose(out["stats"], g["stats"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(out["hv"], g["hv"][:, r], rtol=0, atol=1e-6)
+        check_against_oracle(out, pts32, g["counts"], ref)          # and exactly what the oracle gives on those inputs
+
+
+@pytest.mark.parametrize("B,P", [(1, 1), (257, 50), (4096, 64), (33, 7)])
+def test_random_batches_vs_oracle(B, P):
+    rng = np.random.RandomState(B + P)
+    pts = rng.rand(B, P, 4)
+    pts[:, :, 2:] *= 1.4
+    counts = rng.randint(1, P + 1, size=B)
+    if B > 8:
+        pts[3, :, 2] = 5.0                                    # an environment with no feasible point
+        pts[5, 1] = pts[5, 0]                                 # an exact duplicate
+        pts[6, :, :2] = np.round(pts[6, :, :2], 1)            # many ties in both objectives
+        counts[3:7] = P
+    ref = (0.95, 0.85)
+    out, pts32 = run(pts, counts, ref)
+    step = max(1, B // 200)
+    sel = np.unique(np.concatenate([np.arange(0, B, step), np.arange(min(B, 8))]))
+    sub = {k: v[sel] for k, v in out.items()}
+    check_against_oracle(sub, pts32[sel], counts[sel], ref)
