@@ -159,6 +159,31 @@ int tfem_solve_only(tfem_handle_t h, int B, const double* y, const int32_t* sect
 int tfem_solve_dense_dmma(tfem_handle_t h, int B, const double* y, const int32_t* section, double* d,
                           int32_t* status, void* stream);
 
+/* Gene-vector objective of the MOEA/D benchmark: gen_model.read_genes(genes, int_obj1, int_obj2)
+ * (test/benchmarks/MOEAD/<family>.zip:<family>/truss2D_GEN.py:117-228, one call per individual from
+ * MOEAD_master.py:103-121) for B individuals in ONE launch of the env-step kernel (gene decode, forced symmetry,
+ * FEM, objectives).  genes [B,N+E] float64 in [0,1]: the first N scale to node heights (x max_height: 8 in the small
+ * zips, 6 in the large ones, truss2D_GEN.py:127), the last E to section numbers min(4, round(4 g)).  Everything is
+ * float64 like the reference (python floats); point [B,4] float32 is what read_genes returns.  int_obj1/int_obj2 <= 0
+ * select the family's own initial objectives (what MOEAD_master.py:53-64 computes).  The reference keeps one
+ * persistent model, but every node read_genes does not assign ends each call at its generated height, so the call
+ * is pure.  Genes outside [0,1] clamp the section to 0..4 (the reference would index the catalogue from the end).
+ * Any output may be NULL. */
+typedef struct tfem_genes_out {
+  float* point;      /* [B,4]   obj1/int_obj1, obj2/int_obj2, con1, con2 */
+  double* point64;   /* [B,4]   the same four without float32 rounding, not normalised */
+  double* y;         /* [B,N]   decoded node heights */
+  int32_t* section;  /* [B,E]   decoded section numbers */
+  double* d;         /* [B,ndof] */
+  double* axial;     /* [B,E] */
+  double* ratio;     /* [B,E] */
+  double* U;         /* [B] */
+  double* reactions; /* [B,nres] */
+  int32_t* status;   /* [B] */
+} tfem_genes_out;
+int tfem_read_genes(tfem_handle_t h, int B, const double* genes, double max_height, float int_obj1, float int_obj2,
+                    const tfem_genes_out* out, void* stream);
+
 /* Same call as tfem_step with HOST buffers (the reference's calling convention: numpy arrays in,
  * numpy arrays out).  Copies inputs host->device, runs the step, copies every non-NULL output back
  * and synchronises the stream before returning.  Scratch device memory is owned by the handle. */

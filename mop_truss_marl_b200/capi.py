@@ -66,8 +66,12 @@ TABLES = {
     "scalars": (16, np.float64, lambda d: (8,)),
 }
 
+class GenesOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("point", "point64", "y", "section", "d", "axial", "ratio", "U", "reactions", "status")]
+
+
 EXPORTS = ("tfem_version", "tfem_last_error", "tfem_create", "tfem_destroy", "tfem_get_dims", "tfem_get_table",
-           "tfem_reset", "tfem_step", "tfem_solve_only", "tfem_solve_dense_dmma", "tfem_step_host", "tfem_launch_count")
+           "tfem_reset", "tfem_step", "tfem_solve_only", "tfem_read_genes", "tfem_solve_dense_dmma", "tfem_step_host", "tfem_launch_count")
 
 
 class TfemError(RuntimeError):
@@ -89,6 +93,8 @@ def _load():
     lib.tfem_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(StepOut), C.c_void_p]
     lib.tfem_step.argtypes = [C.c_void_p, C.c_int, C.POINTER(StepIn), C.POINTER(StepOut), C.c_void_p]
     lib.tfem_solve_only.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_void_p]
+    lib.tfem_read_genes.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_float, C.c_float,
+                                    C.POINTER(GenesOut), C.c_void_p]
     lib.tfem_solve_dense_dmma.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
     lib.tfem_step_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(StepIn), C.POINTER(StepOut), C.c_void_p]
     lib.tfem_launch_count.argtypes = [C.c_void_p]

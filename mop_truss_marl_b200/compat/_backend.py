@@ -84,6 +84,28 @@ class Backend:
         for n in model.nodes:
             n.set_target()
 
+    # ---- gene-vector objective ------------------------------------------------------------------------
+    def read_genes(self, genes, max_height, int_obj1, int_obj2):
+        torch = self.torch
+        g = torch.from_numpy(np.ascontiguousarray(genes, dtype=np.float64).reshape(1, -1)).to(self.dev)
+        if g.shape[1] != self.N + self.E:
+            raise ValueError("expected %d genes" % (self.N + self.E))
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        out = {"point": torch.empty(1, 4, dtype=torch.float32, device=self.dev), "y": torch.empty(1, self.N, **f64),
+               "section": torch.empty(1, self.E, dtype=torch.int32, device=self.dev),
+               "d": torch.empty(1, self.ndof, **f64), "axial": torch.empty(1, self.E, **f64),
+               "ratio": torch.empty(1, self.E, **f64), "U": torch.empty(1, **f64),
+               "reactions": torch.empty(1, self.nres, **f64),
+               "status": torch.zeros(1, dtype=torch.int32, device=self.dev)}
+        o = capi.GenesOut()
+        for k, v in out.items():
+            setattr(o, k, C.c_void_p(v.data_ptr()))
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        capi.check(capi.lib.tfem_read_genes(self.handle.ptr, 1, C.c_void_p(g.data_ptr()), float(max_height),
+                                            float(int_obj1), float(int_obj2), C.byref(o), st))
+        self.analyses += 1
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
     # ---- full env step -------------------------------------------------------------------------------
     def game_modify(self, set_node, set_element, move_range, a_geo, a_topo, coin):
         out = step_host(self.handle, np.ascontiguousarray(set_node, dtype=np.float32)[None],

@@ -151,6 +151,22 @@ class gen_model:
                 n.max_up = abs(pair_y - n.coord[1] - self.d_min)
                 n.max_down = abs(n.coord[1] - self.y_min)
 
+    # ---- gene-vector objective of the MOEA/D benchmark (zip truss2D_GEN.py:117-228) -----------------------------
+    def read_genes(self, genes, int_obj1, int_obj2):
+        """one individual: decodes the genes onto ``self.model`` (heights, sections), analyses it and returns
+        ``[obj1/int_obj1, obj2/int_obj2, con1, con2]`` like the reference; the population-sized entry is
+        ``mop_truss_marl_b200.genes.GeneEvaluator.read_genes``"""
+        max_height = 8 if self.num_x == 8 else (6 if self.num_x == 16 else self.y_max)
+        res = self._tfem.read_genes(np.asarray(genes, dtype=np.float64), max_height, float(int_obj1), float(int_obj2))
+        for n, yv in zip(self.model.nodes, res["y"][0]):
+            n.coord[1] = int(yv) if float(yv) == 0.0 else float(yv)
+        for el, s in zip(self.model.elements, res["section"][0]):
+            el.section_no = int(s)
+            el.area = self.truss[el.section_no][0] * 1e-4
+            el.set_i(self.truss[el.section_no][1] * 1e-8)
+        self._tfem.fill_results(self.model, res)
+        return [np.float32(v) for v in res["point"][0]]
+
     # ---- structure text format (truss2D_GEN.py:193-211; parsed by render/truss2D_READ.py:136-172) --------
     def savetxt(self, name):
         with open(name, "w+") as f:

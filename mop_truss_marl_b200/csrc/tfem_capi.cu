@@ -192,6 +192,21 @@ int tfem_solve_only(tfem_handle_t h, int B, const double* y, const int32_t* sect
   return launch(h, a, stream);
 }
 
+int tfem_read_genes(tfem_handle_t h, int B, const double* genes, double max_height, float int_obj1, float int_obj2,
+                    const tfem_genes_out* out, void* stream) {
+  if (!h || !genes || !out) return fail(TFEM_ERR_ARG, "null argument");
+  if (B < 0) return fail(TFEM_ERR_ARG, "negative batch");
+  if (!(max_height > 0.0)) return fail(TFEM_ERR_ARG, "max_height must be positive");
+  if (out->point && !aligned16(out->point)) return fail(TFEM_ERR_ALIGN, "point must be 16-byte aligned");
+  if (B == 0) return TFEM_OK;
+  tfem::StepArgs a{};
+  a.B = B; a.mode = tfem::MODE_GENES; a.genes = genes; a.max_height = max_height; a.sec_out = out->section;
+  a.int_obj1 = int_obj1; a.int_obj2 = int_obj2;
+  a.out.point = out->point; a.out.point64 = out->point64; a.out.y = out->y; a.out.d = out->d; a.out.axial = out->axial;
+  a.out.ratio = out->ratio; a.out.U = out->U; a.out.reactions = out->reactions; a.out.status = out->status;
+  return launch(h, a, stream);
+}
+
 int tfem_solve_dense_dmma(tfem_handle_t h, int B, const double* y, const int32_t* section, double* d,
                           int32_t* status, void* stream) {
   if (!h || !y || !section || !d) return fail(TFEM_ERR_ARG, "null argument");

@@ -290,6 +290,45 @@ tfem_step_kernel(const StepArgs args) {
       yp = W(fam->y0[fam->pair[node]]);
 #pragma unroll
       for (int p = 0; p < EPL; ++p) sec[p] = TFEM_NSEC - 1;
+    } else if (mode == MODE_GENES) {
+      // gene-vector decode: read_genes of the MOEA/D benchmark zips (<family>/truss2D_GEN.py:126-195); all float64
+      const double* gp = args.genes + (size_t)b * (N + E);
+      const double dmin = fam->d_min, ymin = fam->y_min;
+      const bool roof = fam->truss_type == TFEM_ROOF;
+      const int pr = fam->pair[node];
+      double yy = fam->y0[node];
+      const double hgt = __dmul_rn(gp[node], args.max_height);
+      if (roof ? !(res_bits & 2) : is_top) yy = (dmin > hgt) ? dmin : hgt;        // max([h, d_min])
+      if (roof && node == N - 1) yy = 0.0;                                        // the loop's for-else (:141-142)
+      const double ytop = __shfl_sync(0xffffffffu, yy, pr);
+      if (!is_top && (__dsub_rn(ytop, dmin) < yy)) yy = __dsub_rn(ytop, dmin);    // fix the vertical pair (:155-159)
+      const int low = (!is_top && yy < ymin) ? 1 : 0;                             // below y_min (:162-167)
+      const int pair_low = __shfl_sync(0xffffffffu, low, pr);
+      if (low) yy = ymin;
+      if (is_top && pair_low) yy = dmin;
+      yy = __shfl_sync(0xffffffffu, yy, fam->sym_src[fam->symmetry == TFEM_SYM_SMALL ? 0 : 1][node]);
+      y = W(yy);
+      yp = W(__shfl_sync(0xffffffffu, yy, pr));
+#pragma unroll
+      for (int p = 0; p < EPL; ++p) {
+        const int e = lane + 32 * p;
+        sec[p] = 0;
+        if (e < E) {
+          sec[p] = min(max(__double2int_rn(__dmul_rn(gp[N + e], 4.0)), 0), TFEM_NSEC - 1);   // min([4, round(g*4)])
+          sec_s[e] = sec[p];
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < EPL; ++p) {
+        const int e = lane + 32 * p;
+        if (e < E) {
+          const int partner = fam->sym_elem[e];
+          if (partner > e) sec[p] = sec_s[partner];                               // low index <- its mirror
+          if (args.sec_out) args.sec_out[(size_t)b * E + e] = sec[p];
+        }
+      }
+      __syncwarp();
     } else {
       y = W(args.so_y[(size_t)b * N + node]);
       yp = W(args.so_y[(size_t)b * N + fam->pair[node]]);
@@ -477,7 +516,45 @@ tfem_step_kernel(const StepArgs args) {
       if (args.out.U) args.out.U[b] = U;
       if (args.out.status) args.out.status[b] = status;
     }
-    if (mode == MODE_SOLVE_ONLY) { __syncwarp(); continue; }
+    // objectives (truss2D_ENV.py:566-587)
+    float* sum_s = reinterpret_cast<float*>(z);               // z is dead: scratch for the pairwise sums
+#pragma unroll
+    for (int p = 0; p < EPL; ++p) { const int e = lane + 32 * p; if (e < E) sum_s[e] = allv[p]; }
+    __syncwarp();
+    const float obj1 = pairwise_sum_warp(sum_s, E, lane);
+    __syncwarp();
+    float dt32 = 0.f;
+    double dt64 = 0.0;
+    if (is_top) {
+      const TS dt = ts_abs(ts_sub(W(fam->target[node]), y));
+      dt32 = f32(dt);
+      dt64 = fabs(fam->target[node] - y.v);
+    }
+    if (node_lane) sum_s[node] = dt32;
+    __syncwarp();
+    const float obj2 = pairwise_sum_warp(sum_s, N, lane);
+    float con1 = 0.f;
+#pragma unroll
+    for (int p = 0; p < EPL; ++p) con1 = fmaxf(con1, __double2float_rn(ratio[p]));
+    con1 = warp_max_f32(con1);
+    const float alld = is_top ? 0.f : fabsf(__double2float_rn(__ddiv_rn(ddy, fam->max_def)));
+    const float con2 = warp_max_f32(alld);
+    if (lane == 0 && args.out.point) {
+      reinterpret_cast<float4*>(args.out.point)[b] =
+          make_float4(__fdiv_rn(obj1, args.int_obj1 > 0.f ? args.int_obj1 : fam->int_obj1),
+                      __fdiv_rn(obj2, args.int_obj2 > 0.f ? args.int_obj2 : fam->int_obj2), con1, con2);
+    }
+    if (args.out.point64) {
+      const double s1 = warp_sum(v64);
+      const double s2 = warp_sum(node_lane ? dt64 : 0.0);
+      const double m1 = warp_max(c1);
+      const double m2 = warp_max((node_lane && !is_top) ? fabs(ddy) / fam->max_def : 0.0);
+      if (lane == 0) {
+        double* p64 = args.out.point64 + (size_t)b * 4;
+        p64[0] = s1; p64[1] = s2; p64[2] = m1; p64[3] = m2;
+      }
+    }
+    if (mode >= MODE_SOLVE_ONLY) { __syncwarp(); continue; }
 
     // ======================================= observations ======================================
     // node features (state_data / state_data_not_norm, truss2D_ENV.py:65-82, 137-149)
@@ -504,43 +581,6 @@ tfem_step_kernel(const StepArgs args) {
         float* rawd = dyn + 7 * N;
         rawd[0 * N + node] = y32o; rawd[1 * N + node] = up32; rawd[2 * N + node] = down32;
         rawd[3 * N + node] = x9; rawd[4 * N + node] = dy32; rawd[5 * N + node] = raw11;
-      }
-    }
-    // objectives (truss2D_ENV.py:566-587)
-    float* sum_s = reinterpret_cast<float*>(z);               // z is dead: scratch for the pairwise sums
-#pragma unroll
-    for (int p = 0; p < EPL; ++p) { const int e = lane + 32 * p; if (e < E) sum_s[e] = allv[p]; }
-    __syncwarp();
-    const float obj1 = pairwise_sum_warp(sum_s, E, lane);
-    __syncwarp();
-    float dt32 = 0.f;
-    double dt64 = 0.0;
-    if (is_top) {
-      const TS dt = ts_abs(ts_sub(W(fam->target[node]), y));
-      dt32 = f32(dt);
-      dt64 = fabs(fam->target[node] - y.v);
-    }
-    if (node_lane) sum_s[node] = dt32;
-    __syncwarp();
-    const float obj2 = pairwise_sum_warp(sum_s, N, lane);
-    float con1 = 0.f;
-#pragma unroll
-    for (int p = 0; p < EPL; ++p) con1 = fmaxf(con1, __double2float_rn(ratio[p]));
-    con1 = warp_max_f32(con1);
-    const float alld = is_top ? 0.f : fabsf(__double2float_rn(__ddiv_rn(ddy, fam->max_def)));
-    const float con2 = warp_max_f32(alld);
-    if (lane == 0 && args.out.point) {
-      reinterpret_cast<float4*>(args.out.point)[b] =
-          make_float4(__fdiv_rn(obj1, fam->int_obj1), __fdiv_rn(obj2, fam->int_obj2), con1, con2);
-    }
-    if (args.out.point64) {
-      const double s1 = warp_sum(v64);
-      const double s2 = warp_sum(node_lane ? dt64 : 0.0);
-      const double m1 = warp_max(c1);
-      const double m2 = warp_max((node_lane && !is_top) ? fabs(ddy) / fam->max_def : 0.0);
-      if (lane == 0) {
-        double* p64 = args.out.point64 + (size_t)b * 4;
-        p64[0] = s1; p64[1] = s2; p64[2] = m1; p64[3] = m2;
       }
     }
     // element columns of the pool (state_data :84-100, state_data_not_norm :151-172)

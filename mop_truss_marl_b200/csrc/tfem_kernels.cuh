@@ -5,7 +5,7 @@
 
 namespace tfem {
 
-enum StepMode { MODE_STEP = 0, MODE_RESET = 1, MODE_SOLVE_ONLY = 2 };
+enum StepMode { MODE_STEP = 0, MODE_RESET = 1, MODE_SOLVE_ONLY = 2, MODE_GENES = 3 };
 
 struct StepArgs {
   const FamilyTables* fam;     // device copy
@@ -18,6 +18,10 @@ struct StepArgs {
   const double* so_y;          // MODE_SOLVE_ONLY: [B,N]
   const int32_t* so_sec;       // MODE_SOLVE_ONLY: [B,E]
   float* reset_move_range;     // MODE_RESET: [B,N,2]
+  const double* genes;         // MODE_GENES: [B,N+E]
+  double max_height;           // MODE_GENES
+  int32_t* sec_out;            // MODE_GENES: decoded sections [B,E] (optional)
+  float int_obj1, int_obj2;    // > 0: normalisers of point[0], point[1] instead of the family's
 };
 
 struct LaunchInfo {

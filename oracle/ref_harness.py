@@ -212,3 +212,74 @@ class RefGame:
 def seed_all(seed: int) -> None:
     random.seed(seed)
     np.random.seed(seed)
+
+
+# ----------------------------------------------------------------------------------------------------
+# MOEA/D benchmark: read_genes of test/benchmarks/MOEAD/<family>.zip
+# ----------------------------------------------------------------------------------------------------
+MOEAD_ZIPS = {
+    "small_bridge": "test/benchmarks/MOEAD/00_small_bridge.zip",
+    "small_roof": "test/benchmarks/MOEAD/01_small_roof.zip",
+    "large_bridge": "test/benchmarks/MOEAD/02_large_bridge.zip",
+    "large_roof": "test/benchmarks/MOEAD/03_large_roof.zip",
+}
+
+
+class RefMoead:
+    """The unmodified ``truss2D_GEN.py`` / ``FEM_2Dtruss.py`` of one MOEA/D benchmark zip, extracted to a temporary
+    directory (never into the repo) and imported in isolation; ``read_genes`` is the call of
+    ``MOEAD_master.py:104`` with ``int_obj1 / int_obj2`` computed as ``MOEAD_master.py:53-64`` does."""
+
+    def __init__(self, run: str):
+        import tempfile
+        import zipfile
+        if not available():
+            raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+        self.run = run
+        self._tmp = tempfile.TemporaryDirectory(prefix="moead_ref_")
+        with zipfile.ZipFile(os.path.join(REF_ROOT, MOEAD_ZIPS[run])) as z:
+            top = MOEAD_ZIPS[run].rsplit("/", 1)[1][:-4]
+            z.extractall(self._tmp.name, [n for n in z.namelist() if n.startswith(top + "/") and
+                                          (n.endswith(".py") or "section_data/" in n)])
+        self.code_dir = os.path.join(self._tmp.name, top)
+        _install_stubs()
+        names = ("FEM_2Dtruss", "truss2D_GEN", "set_seed_global")
+        saved = {k: sys.modules.pop(k) for k in names if k in sys.modules}
+        sys.path.insert(0, self.code_dir)
+        old = os.getcwd()
+        os.chdir(self.code_dir)
+        try:
+            self.GEN = importlib.import_module("truss2D_GEN")
+            with contextlib.redirect_stdout(io.StringIO()):
+                self.gen = self.GEN.gen_model(*DRIVER_ARGS[run])
+        finally:
+            os.chdir(old)
+            sys.path.remove(self.code_dir)
+            for k in names:
+                sys.modules.pop(k, None)
+            sys.modules.update(saved)
+        m = self.gen.model
+        all_v = np.zeros(len(m.elements), dtype=np.float32)
+        for i, e in enumerate(m.elements):
+            all_v[i] = e.area * e.length
+        all_dt = np.zeros(len(m.nodes), dtype=np.float32)
+        for i, n in enumerate(m.nodes):
+            if n.top_node == 1:
+                all_dt[i] = abs(n.target - n.coord[1])
+        self.int_obj1, self.int_obj2 = np.sum(all_v), np.sum(all_dt)
+
+    def read_genes(self, genes):
+        with np.errstate(all="ignore"), contextlib.redirect_stdout(io.StringIO()):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                point = self.gen.read_genes(genes, self.int_obj1, self.int_obj2)
+        m = self.gen.model
+        return {
+            "point": np.array(point, dtype=np.float32),
+            "y": np.array([float(n.coord[1]) for n in m.nodes], dtype=np.float64),
+            "section": np.array([e.section_no for e in m.elements], dtype=np.int32),
+            "d": np.array(m.d, dtype=np.float64).reshape(-1),
+            "axial": np.array([float(e.e_q[0][0]) for e in m.elements], dtype=np.float64),
+            "ratio": np.array([float(e.prop_yeield) for e in m.elements], dtype=np.float64),
+        }

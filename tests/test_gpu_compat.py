@@ -136,3 +136,21 @@ def test_dropin_actor_act(mods):
     maddpg.update()
     geo_a, _ = maddpg.agents[0].act(st[0], st[1], st[2], st[3], st[4], st[6], st[7])
     assert geo_a.shape == geo_b.shape
+
+
+@pytest.mark.parametrize("name", ["small_roof", "large_bridge"])
+def test_dropin_read_genes_matches_golden(mods, name):
+    """gen_model.read_genes (MOEA/D zips, truss2D_GEN.py:117-228) as MOEAD_master.py:104 calls it"""
+    GEN = mods[0]
+    g = load_golden("genes")
+    gm = quiet(GEN.gen_model, *ARGS[name])
+    int_obj1, int_obj2 = g[name + "_int_obj"]
+    for t in (0, 1, 2, 3, 4, 7):
+        point = gm.read_genes(g[name + "_genes"][t], int_obj1, int_obj2)
+        assert_f32_close("point", np.array(point, dtype=np.float32), g[name + "_point"][t])
+        m = gm.model
+        assert np.array_equal(np.array([float(n.coord[1]) for n in m.nodes]), g[name + "_y"][t])
+        assert [e.section_no for e in m.elements] == g[name + "_section"][t].tolist()
+        assert nrm(np.array(m.d).ravel(), g[name + "_d"][t]) <= 1e-9
+        assert nrm(np.array([e.prop_yeield for e in m.elements]), g[name + "_ratio"][t]) <= 1e-9
+        assert m.elements[0].area == gm.truss[m.elements[0].section_no][0] * 1e-4
