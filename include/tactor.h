@@ -63,6 +63,15 @@ int tactor_forward(tactor_handle_t h, int B, const tactor_inputs* in, float* geo
 int tactor_act(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo,
                float mu, float theta, float sigma, uint64_t seed, void* stream);
 
+/* tactor_act for work that is captured once into a CUDA graph and replayed (trollout_step_host): the noise stream is
+ * chosen when the kernels RUN, from device memory: seed = seed_call_dev[0], call index = seed_call_dev[1] + call_offset.
+ * Does not advance the handle's call counter; tactor_reserve_calls(h, n, launches) returns the counter, advances it by n
+ * calls and books `launches` replayed kernel launches, so that replayed and directly launched steps draw the same
+ * noise and tactor_launch_count stays truthful. */
+int tactor_act_dev(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, float mu, float theta,
+                   float sigma, const uint64_t* seed_call_dev, uint32_t call_offset, void* stream);
+uint64_t tactor_reserve_calls(tactor_handle_t h, uint32_t n, int64_t replayed_launches);
+
 int64_t tactor_launch_count(tactor_handle_t h);
 
 /* Synchronises the device and returns 0, or TFEM_ERR_CUDA if a kernel of this handle reported a

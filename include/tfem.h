@@ -190,8 +190,10 @@ int tfem_read_genes(tfem_handle_t h, int B, const double* genes, double max_heig
 int tfem_step_host(tfem_handle_t h, int B, const tfem_step_in* in_host, const tfem_step_out* out_host,
                    void* stream);
 
-/* number of kernels this library launched on behalf of the handle since creation */
+/* number of kernels this library launched on behalf of the handle since creation; tfem_book_launches adds kernel
+ * launches that were replayed from a CUDA graph captured around tfem_step (trollout_step_host) */
 int64_t tfem_launch_count(tfem_handle_t h);
+void tfem_book_launches(tfem_handle_t h, int64_t n);
 
 #ifdef __cplusplus
 }

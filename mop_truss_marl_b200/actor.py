@@ -23,7 +23,7 @@ class _Inputs(C.Structure):
 
 
 ACTOR_EXPORTS = ("tactor_last_error", "tactor_create", "tactor_destroy", "tactor_set_weights", "tactor_forward", "tactor_act",
-                 "tactor_launch_count", "tactor_status")
+                 "tactor_act_dev", "tactor_reserve_calls", "tactor_launch_count", "tactor_status")
 
 _lib = capi.lib
 _lib.tactor_last_error.restype = C.c_char_p

@@ -71,7 +71,7 @@ class GenesOut(C.Structure):
 
 
 EXPORTS = ("tfem_version", "tfem_last_error", "tfem_create", "tfem_destroy", "tfem_get_dims", "tfem_get_table",
-           "tfem_reset", "tfem_step", "tfem_solve_only", "tfem_read_genes", "tfem_solve_dense_dmma", "tfem_step_host", "tfem_launch_count")
+           "tfem_reset", "tfem_step", "tfem_solve_only", "tfem_read_genes", "tfem_solve_dense_dmma", "tfem_step_host", "tfem_launch_count", "tfem_book_launches")
 
 
 class TfemError(RuntimeError):

@@ -71,10 +71,12 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+// seed_call != nullptr (CUDA-graph replay, tactor_act_dev): seed = seed_call[0], call index = seed_call[1] + call
 __global__ void ou_noise_kernel(float* __restrict__ a, size_t n, float mu, float theta, float sigma,
-                                uint64_t seed, uint64_t call, uint64_t stream_id) {
+                                uint64_t seed, uint64_t call, uint64_t stream_id, const uint64_t* __restrict__ seed_call) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (seed_call) { seed = seed_call[0]; call += seed_call[1]; }
   const uint64_t h = mix64(mix64(seed ^ (call * 0xD1342543DE82EF95ull)) + stream_id * 0x632BE59BD9B4E019ull + i);
   const float u1 = ((uint32_t)(h >> 32) + 1.0f) * 2.3283064365386963e-10f;    // (0, 1]
   const float u2 = (uint32_t)h * 2.3283064365386963e-10f;
@@ -274,19 +276,39 @@ int tactor_forward(tactor_handle_t h, int B, const tactor_inputs* in, float* geo
   return TFEM_OK;
 }
 
-int tactor_act(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, float mu, float theta,
-               float sigma, uint64_t seed, void* stream) {
-  if (int rc = tactor_forward(h, B, in, geo, topo, stream)) return rc;
+static int ou_noise(tactor_handle_t h, int B, float* geo, float* topo, float mu, float theta, float sigma, uint64_t seed,
+                    uint64_t call, const uint64_t* seed_call_dev, void* stream) {
   if (B == 0 || (sigma == 0.f && theta == 0.f)) return TFEM_OK;
   Guard g(h->device);
   const size_t ng = (size_t)B * h->nodes * 2, nt = (size_t)B * h->nodes * 3;
-  const uint64_t call = h->calls++;
-  tactor::ou_noise_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, (cudaStream_t)stream>>>(geo, ng, mu, theta, sigma, seed, call, 1);
-  tactor::ou_noise_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(topo, nt, mu, theta, sigma, seed, call, 2);
+  tactor::ou_noise_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, (cudaStream_t)stream>>>(geo, ng, mu, theta, sigma, seed, call, 1, seed_call_dev);
+  tactor::ou_noise_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(topo, nt, mu, theta, sigma, seed, call, 2, seed_call_dev);
   h->launches.fetch_add(2);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("ou noise: ") + cudaGetErrorString(e));
   return TFEM_OK;
+}
+
+int tactor_act(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, float mu, float theta,
+               float sigma, uint64_t seed, void* stream) {
+  if (int rc = tactor_forward(h, B, in, geo, topo, stream)) return rc;
+  if (B == 0 || (sigma == 0.f && theta == 0.f)) return TFEM_OK;
+  return ou_noise(h, B, geo, topo, mu, theta, sigma, seed, h->calls++, nullptr, stream);
+}
+
+int tactor_act_dev(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, float mu, float theta,
+                   float sigma, const uint64_t* seed_call_dev, uint32_t call_offset, void* stream) {
+  if (!seed_call_dev) return afail(TFEM_ERR_ARG, "null argument");
+  if (int rc = tactor_forward(h, B, in, geo, topo, stream)) return rc;
+  return ou_noise(h, B, geo, topo, mu, theta, sigma, 0, call_offset, seed_call_dev, stream);
+}
+
+uint64_t tactor_reserve_calls(tactor_handle_t h, uint32_t n, int64_t replayed_launches) {
+  if (!h) return 0;
+  const uint64_t base = h->calls;
+  h->calls += n;
+  h->launches.fetch_add(replayed_launches);
+  return base;
 }
 
 int64_t tactor_launch_count(tactor_handle_t h) { return h ? h->launches.load() : 0; }

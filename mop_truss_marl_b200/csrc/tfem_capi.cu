@@ -304,5 +304,6 @@ int tfem_step_host(tfem_handle_t h, int B, const tfem_step_in* in, const tfem_st
 }
 
 int64_t tfem_launch_count(tfem_handle_t h) { return h ? h->launches.load() : 0; }
+void tfem_book_launches(tfem_handle_t h, int64_t n) { if (h) h->launches.fetch_add(n); }
 
 }  // extern "C"

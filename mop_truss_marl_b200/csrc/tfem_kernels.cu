@@ -142,7 +142,9 @@ __host__ __device__ constexpr int align16(int v) { return (v + 15) & ~15; }
 #ifndef TFEM_MINB_LARGE
 #define TFEM_MINB_LARGE 2
 #endif
-template <int NX>
+// GM = false: env-step / reset / solve-only (args.mode); GM = true: the gene-vector objective (MODE_GENES) -- a separate
+// instantiation so that the env-step keeps its register allocation
+template <int NX, bool GM>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (NX == 8) ? TFEM_MINB_SMALL : TFEM_MINB_LARGE)
 tfem_step_kernel(const StepArgs args) {
   using D = Dims<NX>;
@@ -152,7 +154,7 @@ tfem_step_kernel(const StepArgs args) {
   uint16_t* maps = reinterpret_cast<uint16_t*>(smem_raw + align16((int)sizeof(FamilyTables)));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int mode = args.mode;
+  const int mode = GM ? (int)MODE_GENES : args.mode;
   const int warps_total = gridDim.x * WARPS_PER_CTA;
   const int node = lane % N;                 // lanes >= N mirror a node so warp reductions stay exact
   // ---- per-env inputs are fetched one environment ahead (the first batch overlaps the table staging) ----
@@ -215,7 +217,46 @@ tfem_step_kernel(const StepArgs args) {
     TS y, yp;                                // this node's height and its vertical pair's
     int sec[EPL];
     // ======================================= geometry =======================================
-    if (mode == MODE_STEP) {
+    if constexpr (GM) {
+      // gene-vector decode: read_genes of the MOEA/D benchmark zips (<family>/truss2D_GEN.py:126-195); all float64
+      const double* gp = args.genes + (size_t)b * (N + E);
+      const double dmin = fam->d_min, ymin = fam->y_min;
+      const bool roof = fam->truss_type == TFEM_ROOF;
+      const int pr = fam->pair[node];
+      double yy = fam->y0[node];
+      const double hgt = __dmul_rn(gp[node], args.max_height);
+      if (roof ? !(res_bits & 2) : is_top) yy = (dmin > hgt) ? dmin : hgt;        // max([h, d_min])
+      if (roof && node == N - 1) yy = 0.0;                                        // the loop's for-else (:141-142)
+      const double ytop = __shfl_sync(0xffffffffu, yy, pr);
+      if (!is_top && (__dsub_rn(ytop, dmin) < yy)) yy = __dsub_rn(ytop, dmin);    // fix the vertical pair (:155-159)
+      const int low = (!is_top && yy < ymin) ? 1 : 0;                             // below y_min (:162-167)
+      const int pair_low = __shfl_sync(0xffffffffu, low, pr);
+      if (low) yy = ymin;
+      if (is_top && pair_low) yy = dmin;
+      yy = __shfl_sync(0xffffffffu, yy, fam->sym_src[fam->symmetry == TFEM_SYM_SMALL ? 0 : 1][node]);
+      y = W(yy);
+      yp = W(__shfl_sync(0xffffffffu, yy, pr));
+#pragma unroll
+      for (int p = 0; p < EPL; ++p) {
+        const int e = lane + 32 * p;
+        sec[p] = 0;
+        if (e < E) {
+          sec[p] = min(max(__double2int_rn(__dmul_rn(gp[N + e], 4.0)), 0), TFEM_NSEC - 1);   // min([4, round(g*4)])
+          sec_s[e] = sec[p];
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < EPL; ++p) {
+        const int e = lane + 32 * p;
+        if (e < E) {
+          const int partner = fam->sym_elem[e];
+          if (partner > e) sec[p] = sec_s[partner];                               // low index <- its mirror
+          if (args.sec_out) args.sec_out[(size_t)b * E + e] = sec[p];
+        }
+      }
+      __syncwarp();
+    } else if (mode == MODE_STEP) {
       const float y32 = in_y;
       const float2 mr = in_mr;
       float2 ag = in_ag;
@@ -290,45 +331,6 @@ tfem_step_kernel(const StepArgs args) {
       yp = W(fam->y0[fam->pair[node]]);
 #pragma unroll
       for (int p = 0; p < EPL; ++p) sec[p] = TFEM_NSEC - 1;
-    } else if (mode == MODE_GENES) {
-      // gene-vector decode: read_genes of the MOEA/D benchmark zips (<family>/truss2D_GEN.py:126-195); all float64
-      const double* gp = args.genes + (size_t)b * (N + E);
-      const double dmin = fam->d_min, ymin = fam->y_min;
-      const bool roof = fam->truss_type == TFEM_ROOF;
-      const int pr = fam->pair[node];
-      double yy = fam->y0[node];
-      const double hgt = __dmul_rn(gp[node], args.max_height);
-      if (roof ? !(res_bits & 2) : is_top) yy = (dmin > hgt) ? dmin : hgt;        // max([h, d_min])
-      if (roof && node == N - 1) yy = 0.0;                                        // the loop's for-else (:141-142)
-      const double ytop = __shfl_sync(0xffffffffu, yy, pr);
-      if (!is_top && (__dsub_rn(ytop, dmin) < yy)) yy = __dsub_rn(ytop, dmin);    // fix the vertical pair (:155-159)
-      const int low = (!is_top && yy < ymin) ? 1 : 0;                             // below y_min (:162-167)
-      const int pair_low = __shfl_sync(0xffffffffu, low, pr);
-      if (low) yy = ymin;
-      if (is_top && pair_low) yy = dmin;
-      yy = __shfl_sync(0xffffffffu, yy, fam->sym_src[fam->symmetry == TFEM_SYM_SMALL ? 0 : 1][node]);
-      y = W(yy);
-      yp = W(__shfl_sync(0xffffffffu, yy, pr));
-#pragma unroll
-      for (int p = 0; p < EPL; ++p) {
-        const int e = lane + 32 * p;
-        sec[p] = 0;
-        if (e < E) {
-          sec[p] = min(max(__double2int_rn(__dmul_rn(gp[N + e], 4.0)), 0), TFEM_NSEC - 1);   // min([4, round(g*4)])
-          sec_s[e] = sec[p];
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int p = 0; p < EPL; ++p) {
-        const int e = lane + 32 * p;
-        if (e < E) {
-          const int partner = fam->sym_elem[e];
-          if (partner > e) sec[p] = sec_s[partner];                               // low index <- its mirror
-          if (args.sec_out) args.sec_out[(size_t)b * E + e] = sec[p];
-        }
-      }
-      __syncwarp();
     } else {
       y = W(args.so_y[(size_t)b * N + node]);
       yp = W(args.so_y[(size_t)b * N + fam->pair[node]]);
@@ -516,6 +518,37 @@ tfem_step_kernel(const StepArgs args) {
       if (args.out.U) args.out.U[b] = U;
       if (args.out.status) args.out.status[b] = status;
     }
+    if (!GM && mode == MODE_SOLVE_ONLY) { __syncwarp(); continue; }
+
+    // ======================================= observations ======================================
+    // node features (state_data / state_data_not_norm, truss2D_ENV.py:65-82, 137-149)
+    if constexpr (!GM) {
+    const float y32o = f32(y);
+    float x9 = 0.f;
+    if (is_top) {
+      const TS den = ts_add(y, W(1e-6));
+      x9 = den.weak ? __double2float_rn(__ddiv_rn(fam->target[node], den.v))
+                    : __fdiv_rn(__double2float_rn(fam->target[node]), (float)den.v);
+    }
+    const float dy32 = __double2float_rn(fabs(ddy));
+    const float r = __fdiv_rn(dy32, fam->maxdef32);
+    const float x11 = (r > 1.f) ? 1.f : __fmul_rn(r, 0.5f);
+    const float x12 = (r > 1.f) ? 1.f : 0.f;
+    const float raw11 = (r >= 1.f) ? 1.f : 0.f;
+    {
+      const float cols[7] = {y32o, up32, down32, x9, dy32, x11, x12};
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const float mn = warp_min_f32(cols[k]), mx = warp_max_f32(cols[k]);
+        if (node_lane) dyn[k * N + node] = norm_f32(cols[k], mn, mx);
+      }
+      if (node_lane) {
+        float* rawd = dyn + 7 * N;
+        rawd[0 * N + node] = y32o; rawd[1 * N + node] = up32; rawd[2 * N + node] = down32;
+        rawd[3 * N + node] = x9; rawd[4 * N + node] = dy32; rawd[5 * N + node] = raw11;
+      }
+    }
+    }  // !GM
     // objectives (truss2D_ENV.py:566-587)
     float* sum_s = reinterpret_cast<float*>(z);               // z is dead: scratch for the pairwise sums
 #pragma unroll
@@ -554,35 +587,7 @@ tfem_step_kernel(const StepArgs args) {
         p64[0] = s1; p64[1] = s2; p64[2] = m1; p64[3] = m2;
       }
     }
-    if (mode >= MODE_SOLVE_ONLY) { __syncwarp(); continue; }
-
-    // ======================================= observations ======================================
-    // node features (state_data / state_data_not_norm, truss2D_ENV.py:65-82, 137-149)
-    const float y32o = f32(y);
-    float x9 = 0.f;
-    if (is_top) {
-      const TS den = ts_add(y, W(1e-6));
-      x9 = den.weak ? __double2float_rn(__ddiv_rn(fam->target[node], den.v))
-                    : __fdiv_rn(__double2float_rn(fam->target[node]), (float)den.v);
-    }
-    const float dy32 = __double2float_rn(fabs(ddy));
-    const float r = __fdiv_rn(dy32, fam->maxdef32);
-    const float x11 = (r > 1.f) ? 1.f : __fmul_rn(r, 0.5f);
-    const float x12 = (r > 1.f) ? 1.f : 0.f;
-    const float raw11 = (r >= 1.f) ? 1.f : 0.f;
-    {
-      const float cols[7] = {y32o, up32, down32, x9, dy32, x11, x12};
-#pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        const float mn = warp_min_f32(cols[k]), mx = warp_max_f32(cols[k]);
-        if (node_lane) dyn[k * N + node] = norm_f32(cols[k], mn, mx);
-      }
-      if (node_lane) {
-        float* rawd = dyn + 7 * N;
-        rawd[0 * N + node] = y32o; rawd[1 * N + node] = up32; rawd[2 * N + node] = down32;
-        rawd[3 * N + node] = x9; rawd[4 * N + node] = dy32; rawd[5 * N + node] = raw11;
-      }
-    }
+    if (GM) { __syncwarp(); continue; }
     // element columns of the pool (state_data :84-100, state_data_not_norm :151-172)
     __syncwarp();
 #pragma unroll
@@ -633,23 +638,28 @@ int smem_bytes_for(int map_entries) {
 
 }  // namespace
 
+namespace {
+template <int NX, bool GM>
+cudaError_t configure_one(int smem, int* ctas) {
+  cudaError_t err = cudaFuncSetAttribute(tfem_step_kernel<NX, GM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(tfem_step_kernel<NX, GM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (err != cudaSuccess) return err;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, tfem_step_kernel<NX, GM>, WARPS_PER_CTA * 32, smem);
+}
+}  // namespace
+
 int step_kernel_configure(int nx, int device, int map_entries, LaunchInfo* info) {
   cudaError_t err;
-  int smem = 0, ctas = 0, sms = 0;
+  int smem = 0, ctas = 0, ctas_g = 0, sms = 0;
   if (nx == 8) {
     smem = smem_bytes_for<8>(map_entries);
-    err = cudaFuncSetAttribute(tfem_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaFuncSetAttribute(tfem_step_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tfem_step_kernel<8>, WARPS_PER_CTA * 32, smem);
+    err = configure_one<8, false>(smem, &ctas);
+    if (err == cudaSuccess) err = configure_one<8, true>(smem, &ctas_g);
   } else if (nx == 16) {
     smem = smem_bytes_for<16>(map_entries);
-    err = cudaFuncSetAttribute(tfem_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaFuncSetAttribute(tfem_step_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, tfem_step_kernel<16>, WARPS_PER_CTA * 32, smem);
+    err = configure_one<16, false>(smem, &ctas);
+    if (err == cudaSuccess) err = configure_one<16, true>(smem, &ctas_g);
   } else {
     return (int)cudaErrorInvalidValue;
   }
@@ -657,19 +667,25 @@ int step_kernel_configure(int nx, int device, int map_entries, LaunchInfo* info)
   err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return (int)err;
   if (ctas < 1) ctas = 1;
+  if (ctas_g < 1) ctas_g = 1;
   info->block = WARPS_PER_CTA * 32;
   info->smem_bytes = smem;
   info->ctas_per_sm = ctas;
   info->grid = sms * ctas;          // persistent: a multiple of the SM count, warps stride over envs
+  info->grid_genes = sms * ctas_g;
   return 0;
 }
 
 int step_kernel_launch(int nx, const StepArgs& args, const LaunchInfo& info, cudaStream_t stream) {
   if (args.B <= 0) return 0;
+  const bool gm = args.mode == MODE_GENES;
   const int needed = (args.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  const int grid = needed < info.grid ? needed : info.grid;
-  if (nx == 8) tfem_step_kernel<8><<<grid, info.block, info.smem_bytes, stream>>>(args);
-  else if (nx == 16) tfem_step_kernel<16><<<grid, info.block, info.smem_bytes, stream>>>(args);
+  const int full = gm ? info.grid_genes : info.grid;
+  const int grid = needed < full ? needed : full;
+  if (nx == 8 && !gm) tfem_step_kernel<8, false><<<grid, info.block, info.smem_bytes, stream>>>(args);
+  else if (nx == 8) tfem_step_kernel<8, true><<<grid, info.block, info.smem_bytes, stream>>>(args);
+  else if (nx == 16 && !gm) tfem_step_kernel<16, false><<<grid, info.block, info.smem_bytes, stream>>>(args);
+  else if (nx == 16) tfem_step_kernel<16, true><<<grid, info.block, info.smem_bytes, stream>>>(args);
   else return (int)cudaErrorInvalidValue;
   return (int)cudaGetLastError();
 }

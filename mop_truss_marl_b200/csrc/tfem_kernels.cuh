@@ -25,7 +25,7 @@ struct StepArgs {
 };
 
 struct LaunchInfo {
-  int grid, block, smem_bytes, ctas_per_sm;
+  int grid, block, smem_bytes, ctas_per_sm, grid_genes;
 };
 
 // one-time per-handle setup (opt-in shared memory, occupancy query); returns cudaError_t as int

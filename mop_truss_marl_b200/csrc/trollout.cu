@@ -2,6 +2,9 @@
 // PCIe upload, the two kernels-with-C-ABI (tactor_act, tfem_step) and the PCIe download overlap.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -16,6 +19,7 @@ struct Dev {
   uint8_t* coin = nullptr;
 };
 constexpr int PMAX = 50;
+constexpr size_t MAX_GRAPHS = 4, MAX_SEEN = 8;
 }  // namespace
 
 struct trollout_handle_s {
@@ -26,7 +30,26 @@ struct trollout_handle_s {
   Dev d;
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_run;
+  cudaEvent_t ev_join = nullptr;
   std::vector<void*> allocs;
+  // CUDA graphs of one whole step (every copy and kernel of every piece), replayed while the caller keeps passing the
+  // same pinned buffers (a driver that ping-pongs two state tuples alternates between two graphs); a buffer set is
+  // captured the second time it is seen.  The OU-noise seed / call index travel through h_ctr -> d_ctr.
+  struct Graph {
+    std::vector<uintptr_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int64_t env_launches = 0, actor_launches = 0;
+    int pieces = 0;
+    uint64_t last_use = 0;
+  };
+  std::vector<Graph> graphs;                       // at most MAX_GRAPHS, least recently used one is replaced
+  std::vector<std::vector<uintptr_t>> seen_once;   // at most MAX_SEEN
+  uint64_t tick = 0;
+  uint64_t* h_ctr = nullptr;      // pinned: [seed, first call index]
+  uint64_t* d_ctr = nullptr;
+  bool use_graph = true;
+  bool timeline = false;                           // TROLLOUT_TIMELINE=1: print per-piece event times (direct path)
+  std::vector<cudaEvent_t> tl;
 };
 
 namespace {
@@ -82,6 +105,11 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
     if (tfem_get_table(env, TFEM_TAB_A_N, an.data(), an.size() * 4) != TFEM_OK) e = cudaErrorInvalidValue;
     else e = cudaMemcpy(h->d.A_n, an.data(), an.size() * 4, cudaMemcpyHostToDevice);
   }
+  if (e == cudaSuccess) e = dalloc(h, &h->d_ctr, 2);
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->h_ctr), 16, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  if (const char* v = getenv("TROLLOUT_NO_GRAPH")) h->use_graph = (v[0] == '0');
+  if (const char* v = getenv("TROLLOUT_TIMELINE")) { h->timeline = (v[0] == '1'); if (h->timeline) h->use_graph = false; }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
@@ -103,6 +131,9 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
 
 int trollout_destroy(trollout_handle_t h) {
   if (!h) return TFEM_OK;
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
   for (cudaEvent_t ev : h->ev_in) cudaEventDestroy(ev);
   for (cudaEvent_t ev : h->ev_run) cudaEventDestroy(ev);
   if (h->s_in) cudaStreamDestroy(h->s_in);
@@ -122,27 +153,27 @@ int trollout_bytes_per_env(trollout_handle_t h, int P, size_t* h2d, size_t* d2h)
   return TFEM_OK;
 }
 
-int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float mu, float theta, float sigma,
-                       uint64_t seed) {
-  if (!h || !io) return rfail(TFEM_ERR_ARG, "null argument");
-  if (B < 0 || B > h->max_batch) return rfail(TFEM_ERR_ARG, "batch exceeds max_batch");
-  if (B == 0) return TFEM_OK;
+// Enqueues every copy and kernel of one step on the three streams.  ctr_dev == nullptr: the noise call index is taken
+// from the actor handle (tactor_act); otherwise from device memory (tactor_act_dev, graph capture).  join: make s_in
+// wait for the last download (needed to close a capture).
+static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, float mu, float theta, float sigma,
+                        uint64_t seed, const uint64_t* ctr_dev, bool join, int* pieces_out) {
   const trollout_state &si = io->in, &so = io->out;
-  if (!si.x_n || !si.A_s || !si.A_n_ts || !si.A_n_cs || !si.nN_x_n || !si.nN_x_e || !si.move_range || !io->x_p || !io->A_p)
-    return rfail(TFEM_ERR_ARG, "the parent state tuple, x_p and A_p are required");
-  if (io->P < 1 || io->P > PMAX) return rfail(TFEM_ERR_ARG, "P must be in 1..50");
   const size_t N = h->dims.N, E = h->dims.E, P = (size_t)io->P;
   const Dev& d = h->d;
-  int prev_dev = -1;
-  cudaGetDevice(&prev_dev);
-  cudaError_t e = (prev_dev == h->device) ? cudaSuccess : cudaSetDevice(h->device);
-  struct Restore { int dev; ~Restore() { if (dev >= 0) cudaSetDevice(dev); } } restore{prev_dev == h->device ? -1 : prev_dev};
+  cudaError_t e = cudaSuccess;
   auto up = [&](void* dst, const void* src, size_t bytes) {
     if (e == cudaSuccess && src) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->s_in);
   };
   auto down = [&](void* dst, const void* src, size_t bytes) {
     if (e == cudaSuccess && dst) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->s_out);
   };
+  if (ctr_dev) up(h->d_ctr, h->h_ctr, 16);
+  if (h->timeline && !ctr_dev) {
+    const size_t need = 1 + 4 * h->ev_in.size();
+    while (h->tl.size() < need) { cudaEvent_t ev; cudaEventCreate(&ev); h->tl.push_back(ev); }
+    cudaEventRecord(h->tl[0], h->s_in);
+  }
   int piece_idx = 0;
   for (int lo = 0; lo < B && e == cudaSuccess; lo += h->piece, ++piece_idx) {
     const size_t l = (size_t)lo, nb = (size_t)((lo + h->piece <= B) ? h->piece : (B - lo));
@@ -159,6 +190,7 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
     if (io->coin) up(d.coin + l, io->coin + l, nb);
     if (io->n_pf) up(d.n_pf + l, io->n_pf + l, nb * 4);
     if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[piece_idx], h->s_in);
+    if (h->timeline && !ctr_dev) cudaEventRecord(h->tl[1 + 4 * piece_idx + 0], h->s_in);
     // ---- act + step ----
     if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_run, h->ev_in[piece_idx], 0);
     if (e != cudaSuccess) break;
@@ -166,7 +198,10 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
     ai.x_n = d.x_n + l * N * 13; ai.A_n = d.A_n; ai.A_s = d.A_s + l * N * N; ai.A_n_ts = d.A_ts + l * N * N;
     ai.A_n_cs = d.A_cs + l * N * N; ai.x_p = d.x_p + l * P * 4; ai.A_p = d.A_p + l * P * P;
     ai.n_pf = io->n_pf ? d.n_pf + l : nullptr; ai.P = io->P;
-    int rc = tactor_act(h->actor, (int)nb, &ai, d.a_geo + l * N * 2, d.a_topo + l * N * 3, mu, theta, sigma, seed, h->s_run);
+    int rc = ctr_dev ? tactor_act_dev(h->actor, (int)nb, &ai, d.a_geo + l * N * 2, d.a_topo + l * N * 3, mu, theta, sigma,
+                                      ctr_dev, (uint32_t)piece_idx, h->s_run)
+                     : tactor_act(h->actor, (int)nb, &ai, d.a_geo + l * N * 2, d.a_topo + l * N * 3, mu, theta, sigma, seed,
+                                  h->s_run);
     if (rc != TFEM_OK) return rfail(rc, std::string("rollout: ") + tactor_last_error());
     tfem_step_in in{};
     in.set_node = d.raw_n + l * N * 12; in.set_element = d.raw_e + l * E * 21; in.a_geo = d.a_geo + l * N * 2;
@@ -177,6 +212,7 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
     rc = tfem_step(h->env, (int)nb, &in, &o, h->s_run);
     if (rc != TFEM_OK) return rfail(rc, std::string("rollout: ") + tfem_last_error());
     e = cudaEventRecord(h->ev_run[piece_idx], h->s_run);
+    if (h->timeline && !ctr_dev) cudaEventRecord(h->tl[1 + 4 * piece_idx + 1], h->s_run);
     // ---- download ----
     if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_out, h->ev_run[piece_idx], 0);
     down(so.x_n ? so.x_n + l * N * 13 : nullptr, d.x_n + l * N * 13, nb * N * 13 * 4);
@@ -190,9 +226,120 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
     down(io->status ? io->status + l : nullptr, d.status + l, nb * 4);
     down(io->a_geo ? io->a_geo + l * N * 2 : nullptr, d.a_geo + l * N * 2, nb * N * 2 * 4);
     down(io->a_topo ? io->a_topo + l * N * 3 : nullptr, d.a_topo + l * N * 3, nb * N * 3 * 4);
+    if (h->timeline && !ctr_dev) cudaEventRecord(h->tl[1 + 4 * piece_idx + 2], h->s_out);
   }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_out);
+  if (join) {
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev_join, h->s_out);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_in, h->ev_join, 0);
+  }
+  if (pieces_out) *pieces_out = piece_idx;
+  if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout step: ") + cudaGetErrorString(e));
+  return TFEM_OK;
+}
+
+static bool pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float mu, float theta, float sigma,
+                       uint64_t seed) {
+  if (!h || !io) return rfail(TFEM_ERR_ARG, "null argument");
+  if (B < 0 || B > h->max_batch) return rfail(TFEM_ERR_ARG, "batch exceeds max_batch");
+  if (B == 0) return TFEM_OK;
+  const trollout_state &si = io->in, &so = io->out;
+  if (!si.x_n || !si.A_s || !si.A_n_ts || !si.A_n_cs || !si.nN_x_n || !si.nN_x_e || !si.move_range || !io->x_p || !io->A_p)
+    return rfail(TFEM_ERR_ARG, "the parent state tuple, x_p and A_p are required");
+  if (io->P < 1 || io->P > PMAX) return rfail(TFEM_ERR_ARG, "P must be in 1..50");
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  cudaError_t e = (prev_dev == h->device) ? cudaSuccess : cudaSetDevice(h->device);
+  struct Restore { int dev; ~Restore() { if (dev >= 0) cudaSetDevice(dev); } } restore{prev_dev == h->device ? -1 : prev_dev};
+  if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout step: ") + cudaGetErrorString(e));
+
+  // ---- graph path: same pinned buffers as the captured step -> one cudaGraphLaunch instead of ~30 API calls a piece ----
+  const void* ptrs[] = {si.x_n, si.A_s, si.A_n_ts, si.A_n_cs, si.nN_x_n, si.nN_x_e, si.move_range, io->coin, io->x_p, io->A_p,
+                        io->n_pf, so.x_n, so.A_s, so.A_n_ts, so.A_n_cs, so.nN_x_n, so.nN_x_e, so.move_range, io->point,
+                        io->status, io->a_geo, io->a_topo};
+  const bool noise = !(sigma == 0.f && theta == 0.f);
+  if (h->use_graph) {
+    std::vector<uintptr_t> key;
+    for (const void* p : ptrs) key.push_back(reinterpret_cast<uintptr_t>(p));
+    uint32_t fb[3];
+    memcpy(&fb[0], &mu, 4); memcpy(&fb[1], &theta, 4); memcpy(&fb[2], &sigma, 4);
+    key.push_back((uintptr_t)B); key.push_back((uintptr_t)io->P);
+    key.push_back(fb[0]); key.push_back(fb[1]); key.push_back(fb[2]);
+    trollout_handle_s::Graph* hit = nullptr;
+    for (auto& g : h->graphs) if (g.key == key) hit = &g;
+    if (!hit) {
+      bool second = false;
+      for (auto& k : h->seen_once) second = second || (k == key);
+      if (!second) {
+        if (h->seen_once.size() >= MAX_SEEN) h->seen_once.erase(h->seen_once.begin());
+        h->seen_once.push_back(key);
+      } else {
+        bool all_pinned = true;
+        for (const void* p : ptrs) all_pinned = all_pinned && pinned(p);
+        if (all_pinned) {
+          trollout_handle_s::Graph ng;
+          const int64_t env0 = tfem_launch_count(h->env), act0 = tactor_launch_count(h->actor);
+          e = cudaStreamBeginCapture(h->s_in, cudaStreamCaptureModeRelaxed);
+          if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout capture: ") + cudaGetErrorString(e));
+          const int rc = enqueue_step(h, B, io, mu, theta, sigma, seed, h->d_ctr, true, &ng.pieces);
+          cudaGraph_t g = nullptr;
+          e = cudaStreamEndCapture(h->s_in, &g);
+          // the kernels were recorded, not run: take their bookings back (every replay books them)
+          ng.env_launches = tfem_launch_count(h->env) - env0;
+          ng.actor_launches = tactor_launch_count(h->actor) - act0;
+          tfem_book_launches(h->env, -ng.env_launches);
+          tactor_reserve_calls(h->actor, 0, -ng.actor_launches);
+          if (rc != TFEM_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+          if (e == cudaSuccess) e = cudaGraphInstantiate(&ng.exec, g, 0);
+          if (g) cudaGraphDestroy(g);
+          if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout capture: ") + cudaGetErrorString(e));
+          ng.key = key;
+          if (h->graphs.size() >= MAX_GRAPHS) {
+            size_t lru = 0;
+            for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+            cudaGraphExecDestroy(h->graphs[lru].exec);
+            h->graphs[lru] = ng;
+            hit = &h->graphs[lru];
+          } else {
+            h->graphs.push_back(ng);
+            hit = &h->graphs.back();
+          }
+        }
+      }
+    }
+    if (hit) {
+      hit->last_use = ++h->tick;
+      h->h_ctr[0] = seed;
+      h->h_ctr[1] = tactor_reserve_calls(h->actor, noise ? (uint32_t)hit->pieces : 0u, hit->actor_launches);
+      tfem_book_launches(h->env, hit->env_launches);
+      e = cudaGraphLaunch(hit->exec, h->s_in);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_in);
+      if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout step: ") + cudaGetErrorString(e));
+      return TFEM_OK;
+    }
+  }
+  // ---- direct path (pageable buffers, or TROLLOUT_NO_GRAPH=1) ----
+  int np_done = 0;
+  if (int rc = enqueue_step(h, B, io, mu, theta, sigma, seed, nullptr, false, &np_done)) return rc;
+  e = cudaStreamSynchronize(h->s_out);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_in);
+  if (h->timeline && e == cudaSuccess) {
+    fprintf(stderr, "[trollout timeline, ms since first upload]");
+    for (int i = 0; i < np_done; ++i) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, h->tl[0], h->tl[1 + 4 * i + 0]);
+      cudaEventElapsedTime(&b, h->tl[0], h->tl[1 + 4 * i + 1]);
+      cudaEventElapsedTime(&c, h->tl[0], h->tl[1 + 4 * i + 2]);
+      fprintf(stderr, " | piece %d: up %.3f run %.3f down %.3f", i, a, b, c);
+    }
+    fprintf(stderr, "\n");
+  }
   if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout step: ") + cudaGetErrorString(e));
   return TFEM_OK;
 }

@@ -10,6 +10,16 @@ from oracle.truss_oracle import TrussOracle
 from util import FAMILY_NAMES, FP64_TOL, assert_f32_close, load_golden, nrm
 
 pytestmark = pytest.mark.gpu
+
+
+def fp64_tol(o, y, sec):
+    """1e-9 (north_star) for cond(K) <= 1e6; beyond that (gene vectors with heights scaled to the d_min floor give
+    0.3 m deep trusses, cond up to ~1e8) the reference's own LU answer is only good to eps*cond, so the tolerance grows
+    linearly with cond -- the rule of tests/test_gpu_parity.py::fp64_tol"""
+    cond = float(np.linalg.cond(o.solve_only(y, sec)["K"]))
+    return FP64_TOL * max(1.0, cond / 1e6)
+
+
 ALL = ("point", "point64", "y", "section", "d", "axial", "ratio", "U", "reactions", "status")
 
 
@@ -23,6 +33,7 @@ def genesmod():
 def test_read_genes_vs_golden(genesmod, name):
     g = load_golden("genes")
     ev = genesmod.GeneEvaluator(name)
+    o = TrussOracle(name)
     point = ev.read_genes(g[name + "_genes"], fields=ALL)
     torch.cuda.synchronize()
     out = {k: v.cpu().numpy() for k, v in ev.out.items()}
@@ -30,8 +41,9 @@ def test_read_genes_vs_golden(genesmod, name):
     assert np.array_equal(out["y"], g[name + "_y"])                      # float64 bit patterns
     assert np.array_equal(out["section"], g[name + "_section"])
     for t in range(out["d"].shape[0]):
+        tol = fp64_tol(o, out["y"][t], out["section"][t])
         for k in ("d", "axial", "ratio"):
-            assert nrm(out[k][t], g["%s_%s" % (name, k)][t]) <= FP64_TOL, (t, k)
+            assert nrm(out[k][t], g["%s_%s" % (name, k)][t]) <= tol, (t, k, tol)
     assert_f32_close("point", point.cpu().numpy(), g[name + "_point"])   # <= 2 ulp(float32)
     assert ev.handle.launch_count() == 1
 
@@ -51,11 +63,12 @@ def test_read_genes_vs_oracle_random(genesmod, name):
     for b in range(B):
         want = genes_oracle.read_genes(o, genes[b])
         assert np.array_equal(out["y"][b], want["y"]) and np.array_equal(out["section"][b], want["section"])
+        tol = fp64_tol(o, want["y"], want["section"])
         for k in ("d", "axial", "ratio"):
-            assert nrm(out[k][b], want[k]) <= FP64_TOL, (b, k)
-        assert abs(out["U"][b] - want["U"]) <= FP64_TOL * abs(want["U"])
+            assert nrm(out[k][b], want[k]) <= tol, (b, k, tol)
+        assert abs(out["U"][b] - want["U"]) <= tol * abs(want["U"])
         assert_f32_close("point", out["point"][b], want["point"])
-        assert nrm(out["point64"][b], want["point64"]) <= FP64_TOL
+        assert nrm(out["point64"][b], want["point64"]) <= tol
 
 
 def test_read_genes_custom_normalisers_and_errors(genesmod):
@@ -88,10 +101,14 @@ def test_population_size_properties(genesmod, name, B):
     # (2) strain energy = half the work of the loads; reactions balance the load
     P = torch.from_numpy(ev.handle.table("loadvec")).cuda()
     work = 0.5 * (o["d"] @ P)
-    assert float(((o["U"] - work).abs() / work.abs()).max()) <= 1e-9
+    rel = (o["U"] - work).abs() / work.abs()
+    deep = (y[:, nx:] - y[:, :nx]).min(dim=1).values >= 1.0        # at least 1 m deep everywhere: cond(K) < 1e6
+    assert int(deep.sum()) > B // 20
+    assert float(rel[deep].max()) <= 1e-9 and float(rel.max()) <= 1e-6   # 0.3 m deep individuals: eps * cond
     tnsc = ev.handle.table("tnsc"); ndof = ev.ndof
     ry = sum(o["reactions"][:, tnsc[i, 1] - 1 - ndof] for i in range(N) if tnsc[i, 1] > ndof)
-    assert float(((ry + P.sum()).abs() / P.sum().abs()).max()) <= 1e-9
+    bal = (ry + P.sum()).abs() / P.sum().abs()
+    assert float(bal[deep].max()) <= 1e-9 and float(bal.max()) <= 1e-6
     # (3) idempotence: the plain solve of the decoded geometry gives the same bits; so does the other half alone
     from mop_truss_marl_b200 import capi
     import ctypes as C

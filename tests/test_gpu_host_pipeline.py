@@ -46,3 +46,43 @@ def test_host_rollout_equals_resident_path(family, B, pieces):
         assert a_geo_in.shape == a_geo.shape
     h2d, d2h = roll.bytes_per_step()
     assert h2d > 0 and d2h > h2d
+
+
+@pytest.mark.parametrize("family,B,pieces", [("small_bridge", 200, 4), ("large_bridge", 96, 2)])
+def test_graph_replay_equals_direct_enqueue(family, B, pieces, monkeypatch):
+    """trollout_step_host captures a buffer set into a CUDA graph the second time it sees it and replays it afterwards;
+    replayed steps (OU noise included: seed and call index reach the kernels through device memory) must give the bits
+    of the directly enqueued steps, and the launch counters must count the replayed kernels"""
+    from mop_truss_marl_b200 import actor, batched_env, tf_checkpoint
+    from mop_truss_marl_b200.host_pipeline import HostRollout, STATE_IN, STATE_OUT
+    w = tf_checkpoint.random_actor_weights(seed=5)
+    rolls, bufs, envs, pols = [], [], [], []
+    for use_graph in (True, False):
+        monkeypatch.setenv("TROLLOUT_NO_GRAPH", "0" if use_graph else "1")
+        env = batched_env.BatchedTrussEnv(family, B)
+        env.reset()
+        pol = actor.BatchedActor(w, env.N, B, seed=123)          # default OU noise on
+        roll = HostRollout(env, pol, pieces=pieces)
+        b = [roll.alloc_host(), roll.alloc_host()]
+        for k in STATE_IN:
+            b[0][k].copy_(getattr(env, k))
+        rolls.append(roll); bufs.append(b); envs.append(env); pols.append(pol)
+    torch.cuda.synchronize()
+    x_p = torch.tensor([1.0, 1.0, 1.0, 1.0 / 50]).repeat(B, 1, 1).contiguous().pin_memory()
+    A_p = torch.ones(B, 1, 1).pin_memory()
+    coin = (torch.rand(B, generator=torch.Generator().manual_seed(1)) >= 0.5).to(torch.uint8).pin_memory()
+    counts = []
+    for it in range(8):
+        for r in range(2):
+            src, dst = bufs[r][it & 1], bufs[r][1 - (it & 1)]
+            rolls[r].step(src, coin, x_p, A_p, dst)
+        torch.cuda.synchronize()
+        for k in STATE_OUT + ("a_geo", "a_topo"):
+            assert torch.equal(bufs[0][1 - (it & 1)][k], bufs[1][1 - (it & 1)][k]), (it, k)
+        counts.append((envs[0].launch_count(), pols[0].launch_count(), envs[1].launch_count(), pols[1].launch_count()))
+    # both arms launched the same number of kernels every step (1 env-step + 4 actor kernels per piece)
+    assert counts[-1][0] == counts[-1][2] and counts[-1][1] == counts[-1][3]
+    per_step = [(b[0] - a[0], b[1] - a[1]) for a, b in zip(counts, counts[1:])]
+    assert all(p == (pieces, 4 * pieces) for p in per_step), per_step
+    assert int(bufs[0][0]["status"].abs().max()) == 0
+    pols[0].check()
