@@ -5,6 +5,7 @@
 //   pareto_kernel        Pareto-front branch (gcn_l1_4 + GlobalSumPool) -> pooled [B,208]
 //   actor_pipe_kernel    everything else, one CTA per 128 rows, tcgen05 tensor cores (tactor_pipe.cuh)
 // and two elementwise launches for the noise of tactor_act.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -99,6 +100,8 @@ struct tactor_handle_s {
   float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
   int* d_error = nullptr;              // set by a kernel whose mbarrier wait timed out
   int ncta = 1;                        // CTAs per tcgen05 group (2 = CTA pair, cta_group::2)
+  int sms = 0;                         // SM count of the device (tile splitting of the last wave); TACTOR_NO_SPLIT=1 disables
+  float wscale_inv[TACTOR_NLAYERS] = {};  // 1 / power-of-two scale folded into d_wimg[l] (f16 split), 1 otherwise
   std::atomic<int64_t> launches{0};
   uint64_t calls = 0;
 };
@@ -115,11 +118,20 @@ struct Guard {
 };
 
 template <int NODES, int NCTA>
-cudaError_t launch_pipe(const tactor::tc::fused::Params& p, int M, cudaStream_t st) {
+cudaError_t launch_pipe(tactor::tc::fused::Params& p, int M, int sms, cudaStream_t st) {
   using namespace tactor;
   const int tiles = (M + tc::TCM - 1) / tc::TCM;
+  // wave quantisation: one CTA per SM, so `tiles % sms` tiles would run as a last wave that leaves most SMs idle.
+  // Cut those tiles into 2 or 4 row pieces (one CTA each) when the pieces still fit one wave.
+  int grid = (tiles + NCTA - 1) / NCTA * NCTA;
+  p.split_from = grid; p.split_f = 1;
+  if (NCTA == 1 && sms > 0) {
+    const int rem = tiles % sms, full = tiles - rem;
+    const int f = (rem > 0 && 4 * rem <= sms) ? 4 : (rem > 0 && 2 * rem <= sms) ? 2 : 1;
+    if (f > 1) { p.split_from = full; p.split_f = f; grid = full + f * rem; }
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)((tiles + NCTA - 1) / NCTA * NCTA));
+  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(tc::pipe::PTHREADS);
   cfg.dynamicSmemBytes = tc::pipe::pipe_smem_bytes<NODES, NCTA>();
   cfg.stream = st;
@@ -153,31 +165,58 @@ cudaError_t upload_weights(tactor_handle_s* h, const tactor_weights* w) {
     if (e == cudaSuccess) e = cudaMemcpy(h->d_b[l], bp.data(), bp.size() * 4, cudaMemcpyHostToDevice);
   }
   // tcgen05 operand images of the [200,200] layers: per 16-wide K chunk, per CTA of the pair (its half of the
-  // 208 columns), [hi|lo][kb][n][4 floats]
+  // 208 columns), [hi|lo][kb][n][16 bytes].  tf32: 4 floats per 16 bytes, hi = 10-bit-mantissa truncation.  f16: 8 halfs
+  // per 16 bytes, W scaled by S = 2^s (largest s with max|W| S <= 2^14, so that hi and lo stay normal fp16 numbers),
+  // hi = fp16(W S), lo = fp16(W S - hi); the kernel's epilogue multiplies the accumulator by 1/S (exact).  Row k = 200
+  // of the image (inside the zero-padded tail chunk) holds the bias: the generators feed a constant 1 in column 200 of A.
   const int bn = tactor::tc::TCN / h->ncta;
+  for (int l = 0; l < TACTOR_NLAYERS; ++l) h->wscale_inv[l] = 1.f;
   for (int l = 4; l <= 10 && e == cudaSuccess; ++l) {
     const int K = kIn[l], kout = kOut[l];
-    std::vector<float> img;
+    std::vector<unsigned char> img;
+    auto push = [&](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); img.insert(img.end(), b, b + n); };
+    float scale = 1.f;
+    if (tactor::tc::F16) {
+      float wmax = 0.f;
+      for (size_t i = 0; i < (size_t)K * kout; ++i) wmax = fmaxf(wmax, fabsf(w->kernel[l][i]));
+      for (int i = 0; i < kout; ++i) wmax = fmaxf(wmax, fabsf(w->bias[l][i]));      // row K of the image is the bias
+      if (!(wmax < INFINITY)) return cudaErrorInvalidValue;
+      int ex = 0;
+      if (wmax > 0.f) { frexpf(wmax, &ex); ex = 14 - ex; }         // wmax in [2^(e-1), 2^e): wmax * 2^(14-e) < 2^14
+      ex = ex > 24 ? 24 : (ex < -24 ? -24 : ex);
+      scale = ldexpf(1.f, ex);
+      h->wscale_inv[l] = ldexpf(1.f, -ex);
+    }
+    const int kpc = tactor::tc::KPC;
     for (int c = 0; c * tactor::tc::KCH < K; ++c) {
-      const int kw = tactor::tc::chunk_kw(K, c), nkb = kw / 4;
+      const int kw = tactor::tc::F16 ? tactor::tc::KCH : tactor::tc::chunk_kw(K, c), nkb = kw / kpc;
       for (int half = 0; half < h->ncta; ++half)
       for (int part = 0; part < 2; ++part)
         for (int kb = 0; kb < nkb; ++kb)
           for (int nl = 0; nl < bn; ++nl)
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < kpc; ++t) {
               const int n = half * bn + nl;
-              const int k = c * tactor::tc::KCH + 4 * kb + t;
-              float v = (n < kout && k < K) ? w->kernel[l][(size_t)k * kout + n] : 0.f;
-              uint32_t bits;
-              memcpy(&bits, &v, 4);
-              bits &= 0xFFFFE000u;
-              float hi;
-              memcpy(&hi, &bits, 4);
-              img.push_back(part == 0 ? hi : v - hi);
+              const int k = c * tactor::tc::KCH + kpc * kb + t;
+              float v = (n < kout && k < K) ? w->kernel[l][(size_t)k * kout + n] * scale : 0.f;
+              if (tactor::tc::F16 && n < kout && k == K) v = w->bias[l][n] * scale;   // A's column K is the constant 1
+              if (tactor::tc::F16) {
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                const __half pick = part == 0 ? hi : lo;
+                push(&pick, 2);
+              } else {
+                uint32_t bits;
+                memcpy(&bits, &v, 4);
+                bits &= 0xFFFFE000u;
+                float hi;
+                memcpy(&hi, &bits, 4);
+                const float pick = part == 0 ? hi : v - hi;
+                push(&pick, 4);
+              }
             }
     }
-    if (!h->d_wimg[l]) e = cudaMalloc(&h->d_wimg[l], img.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size() * 4, cudaMemcpyHostToDevice);
+    if (!h->d_wimg[l]) e = cudaMalloc(&h->d_wimg[l], img.size());
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size(), cudaMemcpyHostToDevice);
   }
   return e;
 }
@@ -191,10 +230,10 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   tc::fused::Params p{};
   p.x_n = in->x_n; p.A_n = in->A_n; p.A_s = in->A_s; p.A_ts = in->A_n_ts; p.A_cs = in->A_n_cs; p.pooled = pooled;
   for (int k = 0; k < 3; ++k) { p.w1[k] = h->d_w[k]; p.b1[k] = h->d_b[k]; }
-  for (int g = 0; g < tc::fused::NGEMM; ++g) { p.wimg[g] = h->d_wimg[4 + g]; p.bias[g] = h->d_b[4 + g]; }
+  for (int g = 0; g < tc::fused::NGEMM; ++g) { p.wimg[g] = h->d_wimg[4 + g]; p.bias[g] = h->d_b[4 + g]; p.wscale_inv[g] = h->wscale_inv[4 + g]; }
   p.w_head[0] = h->d_w[11]; p.w_head[1] = h->d_w[12]; p.b_head[0] = h->d_b[11]; p.b_head[1] = h->d_b[12];
   p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error;
-  cudaError_t e = (h->ncta == 2) ? launch_pipe<NODES, 2>(p, M, st) : launch_pipe<NODES, 1>(p, M, st);
+  cudaError_t e = (h->ncta == 2) ? launch_pipe<NODES, 2>(p, M, h->sms, st) : launch_pipe<NODES, 1>(p, M, h->sms, st);
   h->launches.fetch_add(2);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -220,6 +259,8 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   for (int l = 0; l < TACTOR_NLAYERS; ++l)
     if (!w->kernel[l] || !w->bias[l]) { tactor_destroy(h); return afail(TFEM_ERR_ARG, "missing layer weights"); }
   cudaError_t e = upload_weights(h, w);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
+  if (const char* v = getenv("TACTOR_NO_SPLIT")) { if (v[0] == '1') h->sms = 0; }
   if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4096);
   if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4096);
   if (e == cudaSuccess) {
@@ -322,7 +363,8 @@ int tactor_status(tactor_handle_t h) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(&flag, h->d_error, 4, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("actor status: ") + cudaGetErrorString(e));
-  if (flag) return afail(TFEM_ERR_CUDA, "an mbarrier wait timed out inside actor_pipe_kernel");
+  if (flag & 1) return afail(TFEM_ERR_CUDA, "an mbarrier wait timed out inside actor_pipe_kernel");
+  if (flag & 2) return afail(TFEM_ERR_UNSUPPORTED, "an activation left the fp16 range of the split tensor-core product (|A.X| > 65504 or NaN input)");
   return TFEM_OK;
 }
 

@@ -21,8 +21,11 @@
 //   epilogue    warps 16-19  tcgen05.ld the finished accumulator while the next GEMM is already running:
 //                            relu(D + b) -> H (+)= (g <= 4), or the sigmoid heads gcn_l4_1/2 (g = 5, 6)
 //
-// TMEM map (512 columns): [0,208) acc0 | [208,256) A stages hi (3 x 16) | [256,464) acc1 | [464,512) A stages lo
+// TMEM map (512 columns): [0,208) acc0 | [208,256) A stages hi (f16: 6 x 8 columns of packed pairs; tf32: 3 x 16)
+//                         | [256,464) acc1 | [464,512) A stages lo
 #pragma once
+#include <cuda_fp16.h>
+
 #include "tactor_tc.cuh"
 
 namespace tactor {
@@ -36,7 +39,9 @@ using fused::KH;
 constexpr int PTHREADS = 704;
 constexpr int NGENW = 16, NEPIW = 4, W_ISSUER = 20, W_PRODUCER = 21;
 constexpr int KPT = 4;                                      // k values per generator thread and chunk
-constexpr int PAST = 3;                                     // A-operand stages in tensor memory
+constexpr int PAST = F16 ? 6 : 3;                           // A-operand stages in tensor memory
+constexpr int ACOLS = F16 ? 8 : 16;                         // TMEM columns of one A stage (f16: two k per column)
+constexpr int MAXST = 6;                                    // barrier slots per ring
 constexpr int TM_ACC1 = 256, TM_AHI = 208, TM_ALO = 464;
 constexpr int LDH = 204;                                    // padded row length of the H tile (12 r mod 32 distinct for 8 rows)
 constexpr int LDX = 4;                                      // row length of the warp-private exchange tile
@@ -46,7 +51,7 @@ constexpr int DMAX = 8;                                     // neighbour slots o
 template <int NODES, int NCTA>
 __host__ __device__ constexpr int pipe_smem_bytes() {
   return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + NGENW * 32 * LDX * 4 + 14 * 208 * 4 +
-         (TCM / NODES) * 208 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + NGEMM * 208 * 4 + 256;
+         (TCM / NODES) * 208 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + NGEMM * 208 * 4 + 384;
 }
 
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
@@ -54,6 +59,10 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
                "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
                : "memory");
 }
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint32_t h2_bits(const __half2& h) { return *reinterpret_cast<const uint32_t*>(&h); }
 // tcgen05.ld of 8 accumulator columns without the wait (software pipelining in the epilogue)
 __device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -66,7 +75,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 
 template <int NODES, int NCTA>
 __global__ void __launch_bounds__(PTHREADS, 1)
-actor_pipe_kernel(const Params P) {
+actor_pipe_kernel(const __grid_constant__ Params P) {
   constexpr int ENVS = TCM / NODES;
   constexpr int WST = Cfg<NCTA>::WST, STAGE_BYTES = Cfg<NCTA>::STAGE_BYTES, B_LBO = Cfg<NCTA>::B_LBO;
   static_assert(pipe_smem_bytes<NODES, NCTA>() <= 232448, "shared memory budget");
@@ -80,10 +89,20 @@ actor_pipe_kernel(const Params P) {
   float* Us = Wh + 2 * 201 * 4;                                              // [128][4] head pre-activations
   float* Bs = Us + TCM * 4;                                                  // [7][208] biases of the hidden layers
   uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + NGEMM * 208);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * MAXST + 6);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * TCM;
+  // the shuffle tells the compiler that `warp` is warp-uniform: role branches become uniform branches and the
+  // constant-bank reads of the generators go through the uniform datapath
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  // CTAs below split_from own a full 128-row tile.  The tiles of the last, partial wave are cut into split_f pieces of
+  // 128 / split_f rows, one CTA each, so that the SMs a partial wave would leave idle share its work: a CTA with fewer
+  // live rows runs the same barrier protocol, but the warps of its dead 32-row groups skip their work.
+  int row0 = blockIdx.x * TCM, rows_here = TCM;
+  if ((int)blockIdx.x >= P.split_from) {
+    const int j = (int)blockIdx.x - P.split_from;
+    rows_here = TCM / P.split_f;
+    row0 = (P.split_from + j / P.split_f) * TCM + (j % P.split_f) * rows_here;
+  }
   const int env0 = row0 / NODES;
   const int M = P.M;
   // W ring (s < WST):  w_full  this CTA's W half landed (TMA tx)       w_peer  the peer's half landed (leader's copy)
@@ -92,9 +111,10 @@ actor_pipe_kernel(const Params P) {
   //                    a_empty stage consumed (commit)
   // acc_full[b] accumulator b complete (commit)   acc_empty[b] drained by the epilogue warps (leader's copy)
   // h_ready     the five-way sum H is complete (epilogue of GEMM 4 -> generators of GEMM 5)
-  const uint32_t w_full = smem_u32(&bars[0]), w_peer = smem_u32(&bars[5]), w_empty = smem_u32(&bars[10]);
-  const uint32_t a_full = smem_u32(&bars[15]), a_empty = smem_u32(&bars[18]);
-  const uint32_t acc_full = smem_u32(&bars[21]), acc_empty = smem_u32(&bars[23]), h_ready = smem_u32(&bars[25]);
+  static_assert(WST <= MAXST && PAST <= MAXST, "barrier slots");
+  const uint32_t w_full = smem_u32(&bars[0]), w_peer = smem_u32(&bars[MAXST]), w_empty = smem_u32(&bars[2 * MAXST]);
+  const uint32_t a_full = smem_u32(&bars[3 * MAXST]), a_empty = smem_u32(&bars[4 * MAXST]);
+  const uint32_t acc_full = smem_u32(&bars[5 * MAXST]), acc_empty = smem_u32(&bars[5 * MAXST + 2]), h_ready = smem_u32(&bars[5 * MAXST + 4]);
   const uint32_t cta_rank = (NCTA == 1) ? 0u : cluster_ctarank();
   const bool is_leader = (cta_rank == 0);
 
@@ -151,13 +171,16 @@ actor_pipe_kernel(const Params P) {
   const uint32_t tmem_base = *tmem_slot;
   bool ok = true;
 #ifdef DEBUG_TIMING
+#ifndef DEBUG_BLOCK
+#define DEBUG_BLOCK 200
+#endif
   // per role (generator warp 0, first epilogue warp, issuer) and GEMM: 8 cycle counters
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long Tstart = clock64();
 #define PDBG_T(x) const long long x = clock64()
 #define PDBG_ACC(i, v) dbg_acc[i] += (v)
 #define PDBG_FLUSH(role, g)                                                                         \
-  if (blockIdx.x == 200 && lane == 0) {                                                             \
+  if (blockIdx.x == DEBUG_BLOCK && lane == 0) {                                                           \
     long long* dbg = reinterpret_cast<long long*>(P.error_flag) + 16 + (role) * 64 + (g) * 8;      \
     for (int i = 0; i < 7; ++i) { dbg[i] = dbg_acc[i]; dbg_acc[i] = 0; }                             \
     dbg[7] = clock64() - Tstart;                                                                    \
@@ -168,9 +191,48 @@ actor_pipe_kernel(const Params P) {
 #define PDBG_FLUSH(role, g)
 #endif
 
-  if (warp < NGENW) {
-    // =================================================== generators ===========================================
+  // =================================================== generators ===========================================
+  auto generator_role = [&]() {
     const int q = warp & 3, kq = warp >> 2;
+    // gcn_l1_2 / gcn_l1_3 kernels replace gcn_l1_1's in shared memory before GEMM 1 / 3 (all 16 generator warps take part)
+    auto w1_src = [&](int l1, int idx) -> const float4* {
+      return (idx < 13 * 52) ? reinterpret_cast<const float4*>(P.w1[l1]) + idx
+                             : reinterpret_cast<const float4*>(P.b1[l1]) + (idx - 13 * 52);
+    };
+    auto reload_w1 = [&](int g) {
+      const int l1 = (g == 1) ? 1 : 2;
+      float4 wreg[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int idx = tid + t * NGENW * 32;
+        wreg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < 14 * 52) wreg[t] = __ldg(w1_src(l1, idx));
+      }
+      named_bar_sync(1, NGENW * 32);                         // all generators are done reading the old kernel
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int idx = tid + t * NGENW * 32;
+        if (idx < 14 * 52) reinterpret_cast<float4*>(W1s)[idx] = wreg[t];
+      }
+      named_bar_sync(1, NGENW * 32);
+    };
+    if (32 * q >= rows_here) {
+      // dead row group of a split tile: keep the barrier protocol going, produce nothing (the tensor core reads
+      // whatever these TMEM lanes hold; rows are independent and the epilogue never looks at them)
+      for (int g = 0; g < NGEMM; ++g) {
+        if (g == 1 || g == 3) reload_w1(g);
+        for (int c = 0; c < NCH; ++c) {
+          const uint32_t u = (uint32_t)(g * NCH + c), sa = u % PAST;
+          if (u >= PAST) ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok;
+          __syncwarp();
+          if (lane == 0) {
+            if (is_leader) mbar_arrive(a_full + 8 * sa);
+            else mbar_arrive_remote(a_full + 8 * sa, 0);
+          }
+        }
+      }
+      return;
+    }
     const int r = 32 * q + lane;                             // row of the tile
     const int e = r / NODES, n = r % NODES;
     const int lane_env0 = lane & ~(NODES - 1);               // first lane of this row's environment inside the warp
@@ -211,10 +273,17 @@ actor_pipe_kernel(const Params P) {
     }
     const bool dense = __any_sync(0xffffffffu, cnt > DMAX || (mask_o & ~mask_n) != 0u);
     const int dcnt = min(__reduce_max_sync(0xffffffffu, cnt), DMAX);       // neighbour slots in use (largest row of the warp)
+    // slot 0 is the row itself when every row of the warp has a self loop (A_n always has): its x is still in registers
+    const bool self_first = __all_sync(0xffffffffu, (mask_n >> n) & 1u);
+    {
+      const uint32_t rest = self_first ? (mask_n & ~(1u << n)) : mask_n;
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) {
-      const int j = (d < cnt) ? (int)__fns(mask_n, 0, d + 1) : n;
-      nidx_packed |= (uint64_t)(lane_env0 + j) << (8 * d);
+      for (int d = 0; d < DMAX; ++d) {
+        const int dd = self_first ? d - 1 : d;                // index into the remaining neighbours
+        int j = n;
+        if (!(self_first && d == 0) && d < cnt) j = (int)__fns(rest, 0, dd + 1);
+        nidx_packed |= (uint64_t)(lane_env0 + j) << (8 * d);
+      }
     }
     // adjacency row of this thread for GEMM g (element j at arow[j * astride]); rows past the batch read A_n
     auto row_of = [&](int g, const float*& rowp, int& stride) {
@@ -233,31 +302,33 @@ actor_pipe_kernel(const Params P) {
     };
     const float* arow = nullptr;
     int astride = 1;
-    // the next GEMM's small operands are pulled into L1 one GEMM ahead (no registers held across the chunk loop)
-    auto w1_src = [&](int l1, int idx) -> const float4* {
-      return (idx < 13 * 52) ? reinterpret_cast<const float4*>(P.w1[l1]) + idx
-                             : reinterpret_cast<const float4*>(P.b1[l1]) + (idx - 13 * 52);
+    float amax = 0.f;                                        // largest |A.X| this thread split (f16 range check)
+    // Hand-off of an A stage, decoupled from the chunk that filled it: the stage is acquired (a_empty) only right before
+    // its tcgen05.st, and published (wait::st, fence, arrive on a_full) in the middle of the NEXT chunk's arithmetic, so
+    // neither the barrier round trip nor the tensor-memory store latency sits on the warp's dependent chain.
+    int pending = -1;                                        // stage written but not yet published
+    auto hand_off = [&]() {
+      if (pending < 0) return;                               // warp-uniform
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (is_leader) mbar_arrive(a_full + 8 * pending);
+        else mbar_arrive_remote(a_full + 8 * pending, 0);
+      }
+      pending = -1;
+    };
+    auto acquire = [&](uint32_t u, uint32_t sa) {
+      PDBG_T(ta);
+      if (u >= PAST) ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok;        // chunk u-PAST consumed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      PDBG_T(tb);
+      PDBG_ACC(2, tb - ta);
     };
     for (int g = 0; g < NGEMM; ++g) {
       PDBG_T(tg0);
       // ---- per-GEMM setup ----
-      if (g == 1 || g == 3) {                                // g = 2 reuses gcn_l1_2's kernel
-        const int l1 = (g == 1) ? 1 : 2;
-        float4 wreg[2];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int idx = tid + t * NGENW * 32;
-          wreg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < 14 * 52) wreg[t] = __ldg(w1_src(l1, idx));
-        }
-        named_bar_sync(1, NGENW * 32);                       // all generators are done reading the old kernel
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int idx = tid + t * NGENW * 32;
-          if (idx < 14 * 52) reinterpret_cast<float4*>(W1s)[idx] = wreg[t];
-        }
-        named_bar_sync(1, NGENW * 32);
-      }
+      if (g == 1 || g == 3) reload_w1(g);                    // g = 2 reuses gcn_l1_2's kernel
       load_coefs(g, coef);
       row_of(g, arow, astride);
       if (g + 1 < NGEMM) {                                   // prefetch for the next GEMM
@@ -281,11 +352,7 @@ actor_pipe_kernel(const Params P) {
       // ---- 13 chunks: generate, mix with the adjacency, split, store to tensor memory ----
       for (int c = 0; c < NCH; ++c) {
         const uint32_t u = (uint32_t)(g * NCH + c), sa = u % PAST;
-        PDBG_T(t0);
-        if (u >= PAST) ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok;      // chunk u-PAST consumed
         PDBG_T(t1);
-        PDBG_ACC(2, t1 - t0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int k0 = c * KCH + KPT * kq;
         if (k0 < KH) {                                       // warp-uniform (tail chunk: k-quarters 0 and 1 only)
           float y[KPT] = {0.f, 0.f, 0.f, 0.f};
@@ -293,7 +360,7 @@ actor_pipe_kernel(const Params P) {
             float4 x;
             if (g <= 3) {
               x = *reinterpret_cast<const float4*>(W1s + 13 * 208 + k0);
-              float4 wa[7], wb[6];                           // two batches of loads in flight ahead of the FMAs
+              float4 wa[7], wb[6];                           // two batches of (broadcast) loads in flight ahead of the FMAs
 #pragma unroll
               for (int i = 0; i < 7; ++i) wa[i] = *reinterpret_cast<const float4*>(W1s + i * 208 + k0);
 #pragma unroll
@@ -315,13 +382,15 @@ actor_pipe_kernel(const Params P) {
             }
             PDBG_T(tx);
             PDBG_ACC(5, tx - t1);
+            hand_off();                                      // publish the previous chunk's stage
             *reinterpret_cast<float4*>(xt + lane * LDX) = x;
             __syncwarp();
             if (!dense) {
 #pragma unroll
               for (int d = 0; d < DMAX; ++d) {
                 if (d >= dcnt) break;                        // warp-uniform
-                const float4 t0 = *reinterpret_cast<const float4*>(xt + (int)((nidx_packed >> (8 * d)) & 0xff) * LDX);
+                float4 t0 = x;                               // slot 0 = this row itself when self_first (warp-uniform)
+                if (d > 0 || !self_first) t0 = *reinterpret_cast<const float4*>(xt + (int)((nidx_packed >> (8 * d)) & 0xff) * LDX);
                 y[0] = fmaf(coef[d], t0.x, y[0]); y[1] = fmaf(coef[d], t0.y, y[1]); y[2] = fmaf(coef[d], t0.z, y[2]); y[3] = fmaf(coef[d], t0.w, y[3]);
               }
             } else {
@@ -335,6 +404,7 @@ actor_pipe_kernel(const Params P) {
             __syncwarp();                                    // the tile is rewritten by the next chunk
           } else {
             // layer 3: the operand rows are rows of H (shared memory), no exchange tile needed
+            hand_off();                                      // publish the previous chunk's stage
             const float* hb = H + (32 * q) * LDH + k0;
             if (!dense) {
 #pragma unroll
@@ -354,38 +424,70 @@ actor_pipe_kernel(const Params P) {
           }
           PDBG_T(t2);
           PDBG_ACC(3, t2 - t1);
-          float hi[KPT], lo[KPT];
-#pragma unroll
-          for (int t = 0; t < KPT; ++t) {
-            hi[t] = __uint_as_float(__float_as_uint(y[t]) & 0xFFFFE000u);
-            lo[t] = y[t] - hi[t];
-          }
           const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
-          tmem_st4(tmem_base + lane_sel + (uint32_t)(TM_AHI + 16 * sa + KPT * kq), hi);
-          tmem_st4(tmem_base + lane_sel + (uint32_t)(TM_ALO + 16 * sa + KPT * kq), lo);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          acquire(u, sa);
+          if constexpr (F16) {
+            // y = hi + lo in fp16, two k per 32-bit column (even k in the low half)
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(y[0]), fabsf(y[1])), fmaxf(fabsf(y[2]), fabsf(y[3]))));
+            const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y), l23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
+            tmem_st2(tmem_base + lane_sel + (uint32_t)(TM_AHI + ACOLS * sa + 2 * kq), h2_bits(h01), h2_bits(h23));
+            tmem_st2(tmem_base + lane_sel + (uint32_t)(TM_ALO + ACOLS * sa + 2 * kq), h2_bits(l01), h2_bits(l23));
+          } else {
+            float hi[KPT], lo[KPT];
+#pragma unroll
+            for (int t = 0; t < KPT; ++t) {
+              hi[t] = __uint_as_float(__float_as_uint(y[t]) & 0xFFFFE000u);
+              lo[t] = y[t] - hi[t];
+            }
+            tmem_st4(tmem_base + lane_sel + (uint32_t)(TM_AHI + ACOLS * sa + KPT * kq), hi);
+            tmem_st4(tmem_base + lane_sel + (uint32_t)(TM_ALO + ACOLS * sa + KPT * kq), lo);
+          }
           PDBG_T(t4);
           PDBG_ACC(6, t4 - t2);
+        } else if constexpr (F16) {
+          // f16 k-steps are 16 wide: the tail chunk's k >= 200 columns of the A stage must hold zeros
+          const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
+          hand_off();
+          acquire(u, sa);
+          // ... except column k = 200, the constant 1 that multiplies the bias row of the W image
+          tmem_st2(tmem_base + lane_sel + (uint32_t)(TM_AHI + ACOLS * sa + 2 * kq), k0 == KH ? 0x00003C00u : 0u, 0u);
+          tmem_st2(tmem_base + lane_sel + (uint32_t)(TM_ALO + ACOLS * sa + 2 * kq), 0u, 0u);
+        } else {
+          hand_off();                                        // tf32 tail chunk: nothing to store for this k-quarter
+          acquire(u, sa);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (is_leader) mbar_arrive(a_full + 8 * sa);
-          else mbar_arrive_remote(a_full + 8 * sa, 0);
-        }
+        pending = (int)sa;
         PDBG_T(t3);
         PDBG_ACC(4, t3 - t1);
       }
+      hand_off();                                            // the accumulator of this GEMM must not wait for the next one
       if (warp == 0) { PDBG_FLUSH(0, g); }
     }
+    if (F16 && !(amax <= F16_MAX) && P.error_flag) atomicOr(P.error_flag, 2);   // |A.X| left the fp16 range (or NaN input)
+  };
+  if (warp < NGENW) {
+    generator_role();
   } else if (warp < NGENW + NEPIW) {
     // =================================================== epilogue =============================================
     const int q = warp & 3;
     const int r = 32 * q + lane;
     const int n = r % NODES;
     const int lane_env0 = lane & ~(NODES - 1);
+    const bool live = 32 * q < rows_here;                    // dead row group of a split tile: barriers only
     for (int g = 0; g < NGEMM; ++g) {
       const int b = g & 1;
+      if (!live) {
+        ok = mbar_wait(acc_full + 8 * b, (uint32_t)((g >> 1) & 1)) && ok;
+        __syncwarp();
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(acc_empty + 8 * b);
+          else mbar_arrive_remote(acc_empty + 8 * b, 0);
+          if (g == 4) mbar_arrive(h_ready);
+        }
+        continue;
+      }
       PDBG_T(t0);
       ok = mbar_wait(acc_full + 8 * b, (uint32_t)((g >> 1) & 1)) && ok;
       PDBG_T(t1);
@@ -393,6 +495,7 @@ actor_pipe_kernel(const Params P) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b ? TM_ACC1 : 0);
       const float* bias = Bs + g * 208;
+      const float wsi = P.wscale_inv[g];                     // undoes the power-of-two scale folded into W (exact)
       float* hrow = H + r * LDH;
       const float* wh = Wh + (g >= 5 ? g - 5 : 0) * 201 * 4; // only used for g >= 5
       float u0 = 0.f, u1 = 0.f, u2 = 0.f;
@@ -400,15 +503,23 @@ actor_pipe_kernel(const Params P) {
       tmem_ld8_async(tacc, vr[0]);
 #pragma unroll 2
       for (int cb = 0; cb < KH / 8; ++cb) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * cb);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * cb + 4);
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if constexpr (!F16) {
+          b0 = *reinterpret_cast<const float4*>(bias + 8 * cb);
+          b1 = *reinterpret_cast<const float4*>(bias + 8 * cb + 4);
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float v[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(vr[cb & 1][t]);
         if (cb + 1 < KH / 8) tmem_ld8_async(tacc + (uint32_t)(8 * (cb + 1)), vr[(cb + 1) & 1]);   // in flight while cb is processed
-        v[0] = fmaxf(v[0] + b0.x, 0.f); v[1] = fmaxf(v[1] + b0.y, 0.f); v[2] = fmaxf(v[2] + b0.z, 0.f); v[3] = fmaxf(v[3] + b0.w, 0.f);
-        v[4] = fmaxf(v[4] + b1.x, 0.f); v[5] = fmaxf(v[5] + b1.y, 0.f); v[6] = fmaxf(v[6] + b1.z, 0.f); v[7] = fmaxf(v[7] + b1.w, 0.f);
+        if constexpr (F16) {                                 // bias rode along as row 200 of the W image
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t] * wsi, 0.f);
+        } else {
+          v[0] = fmaxf(v[0] + b0.x, 0.f); v[1] = fmaxf(v[1] + b0.y, 0.f); v[2] = fmaxf(v[2] + b0.z, 0.f); v[3] = fmaxf(v[3] + b0.w, 0.f);
+          v[4] = fmaxf(v[4] + b1.x, 0.f); v[5] = fmaxf(v[5] + b1.y, 0.f); v[6] = fmaxf(v[6] + b1.z, 0.f); v[7] = fmaxf(v[7] + b1.w, 0.f);
+        }
         if (g <= 4) {
           float4* dst = reinterpret_cast<float4*>(hrow + 8 * cb);
           float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
@@ -459,11 +570,13 @@ actor_pipe_kernel(const Params P) {
     // =================================================== MMA issuer / W forwarder =============================
     if (lane == 0) {
       if (is_leader) {
-        uint64_t db[WST][2][2];                              // [stage][k-step][hi, lo] of a full chunk
+        // [stage][k-step][hi, lo] of a full chunk; a k-step spans two 16-byte core-matrix columns (f16: the whole chunk)
+        constexpr int KSTEPS = F16 ? 1 : 2;
+        uint64_t db[WST][KSTEPS][2];
 #pragma unroll
         for (int st = 0; st < WST; ++st)
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
+          for (int ks = 0; ks < KSTEPS; ++ks) {
             const uint32_t b_hi = smem_u32(smem + st * STAGE_BYTES) + 2 * ks * B_LBO;
             db[st][ks][0] = make_desc(b_hi, B_LBO);
             db[st][ks][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);
@@ -490,22 +603,27 @@ actor_pipe_kernel(const Params P) {
             PDBG_ACC(0, t1 - t0); PDBG_ACC(1, t2 - t1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int kw = chunk_kw(KH, c);
-            const uint32_t a_hi = tmem_base + (uint32_t)(TM_AHI + 16 * sa), a_lo = tmem_base + (uint32_t)(TM_ALO + 16 * sa);
+            const uint32_t a_hi = tmem_base + (uint32_t)(TM_AHI + ACOLS * sa), a_lo = tmem_base + (uint32_t)(TM_ALO + ACOLS * sa);
 #pragma unroll
             for (int st = 0; st < WST; ++st) {
               if (st != (int)sw) continue;                   // compile-time stage index keeps the descriptors in registers
-              if (kw == KCH) {
-                mma_tf32<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
-                mma_tf32<NCTA>(dacc, a_hi, db[st][0][1], 1);
-                mma_tf32<NCTA>(dacc, a_lo, db[st][0][0], 1);
-                mma_tf32<NCTA>(dacc, a_hi + 8, db[st][1][0], 1);
-                mma_tf32<NCTA>(dacc, a_hi + 8, db[st][1][1], 1);
-                mma_tf32<NCTA>(dacc, a_lo + 8, db[st][1][0], 1);
+              if constexpr (F16) {                           // one K = 16 step per chunk (tail chunk zero-padded)
+                (void)kw;
+                mma_split<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
+                mma_split<NCTA>(dacc, a_hi, db[st][0][1], 1);
+                mma_split<NCTA>(dacc, a_lo, db[st][0][0], 1);
+              } else if (kw == KCH) {
+                mma_split<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
+                mma_split<NCTA>(dacc, a_hi, db[st][0][1], 1);
+                mma_split<NCTA>(dacc, a_lo, db[st][0][0], 1);
+                mma_split<NCTA>(dacc, a_hi + 8, db[st][KSTEPS - 1][0], 1);
+                mma_split<NCTA>(dacc, a_hi + 8, db[st][KSTEPS - 1][1], 1);
+                mma_split<NCTA>(dacc, a_lo + 8, db[st][KSTEPS - 1][0], 1);
               } else {                                       // tail chunk: one k-step, lo half right after hi
                 const uint64_t dbl = make_desc(smem_u32(smem + st * STAGE_BYTES) + (kw / 4) * B_LBO, B_LBO);
-                mma_tf32<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
-                mma_tf32<NCTA>(dacc, a_hi, dbl, 1);
-                mma_tf32<NCTA>(dacc, a_lo, db[st][0][0], 1);
+                mma_split<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
+                mma_split<NCTA>(dacc, a_hi, dbl, 1);
+                mma_split<NCTA>(dacc, a_lo, db[st][0][0], 1);
               }
             }
             mma_commit<NCTA>(w_empty + 8 * sw);
@@ -532,7 +650,7 @@ actor_pipe_kernel(const Params P) {
         for (int c = 0; c < NCH; ++c) {
           const uint32_t u = (uint32_t)(g * NCH + c), s = u % WST;
           if (u >= WST) ok = mbar_wait(w_empty + 8 * s, ((u / WST) - 1) & 1) && ok;       // chunk u-WST consumed
-          const uint32_t bytes = 2u * (chunk_kw(KH, c) / 4) * B_LBO;                      // this CTA's half: hi then lo
+          const uint32_t bytes = F16 ? (uint32_t)STAGE_BYTES : 2u * (chunk_kw(KH, c) / 4) * B_LBO;   // this CTA's half: hi then lo
           const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg[g]) +
                                      (size_t)c * Cfg<NCTA>::CHUNK_IMG_BYTES + (size_t)cta_rank * bytes;
           mbar_expect_tx(w_full + 8 * s, bytes);
@@ -542,7 +660,7 @@ actor_pipe_kernel(const Params P) {
     __syncwarp();
   }
 
-  if (!ok && P.error_flag) atomicExch(P.error_flag, 1);
+  if (!ok && P.error_flag) atomicOr(P.error_flag, 1);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if constexpr (NCTA == 2) cluster_sync_all();               // neither CTA leaves while the pair's TMEM / barriers are in use

@@ -19,13 +19,23 @@
 namespace tactor {
 namespace tc {
 
+// Operand precision of the split product (both give float32-equivalent results):
+//   TACTOR_F16 = 1 (default)  x = hi + lo with hi = fp16(x), lo = fp16(x - hi): tcgen05.mma kind::f16, K = 16 per
+//                             instruction, half the operand bytes and twice the tensor rate of tf32.  fp16 and tf32
+//                             carry the same 11-bit significand; what fp16 lacks is range, so W is pre-scaled by a
+//                             power of two per layer (undone exactly in the epilogue) and |A.X| > 65504 is reported.
+//   TACTOR_F16 = 0            3xTF32: hi = x truncated to 10 mantissa bits, kind::tf32, K = 8 per instruction.
+#ifndef TACTOR_F16
+#define TACTOR_F16 1
+#endif
+constexpr bool F16 = TACTOR_F16 != 0;
 constexpr int TCM = 128;             // rows per CTA
 constexpr int TCN = 208;             // padded output columns (UMMA N, multiple of 16)
-constexpr int KCH = 16;              // K elements per chunk (2 MMA k-steps of 8)
-constexpr int NKB = KCH / 4;         // 16-byte core-matrix columns per chunk
-constexpr int A_LBO = TCM * 16;      // bytes between core matrices adjacent in K (A operand)
+constexpr int KCH = 16;              // K elements per chunk (f16: one MMA k-step of 16; tf32: two of 8)
+constexpr int KPC = F16 ? 8 : 4;     // K elements per 16-byte core-matrix row
+constexpr int NKB = KCH / KPC;       // 16-byte core-matrix columns per chunk
 constexpr int SBO = 128;             // bytes between 8-row groups
-constexpr int A_BYTES = NKB * A_LBO; // one of {hi, lo}
+constexpr float F16_MAX = 65504.f;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 // NCTA = 1: one CTA per 128-row tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on two
@@ -35,14 +45,16 @@ template <int NCTA> struct Cfg {
   static constexpr int BN = TCN / NCTA;                     // W columns held by one CTA
   static constexpr int B_LBO = BN * 16;                     // bytes between core matrices adjacent in K (B operand)
   static constexpr int B_BYTES = NKB * B_LBO;               // one of {hi, lo} of a full chunk
-  static constexpr int WST = NCTA == 1 ? 3 : 5;             // W stages in shared memory (K chunks in flight)
+  static constexpr int WST = NCTA == 1 ? (F16 ? 6 : 3) : 5; // W stages in shared memory (K chunks in flight)
   static constexpr int STAGE_BYTES = 2 * B_BYTES;           // Bhi, Blo of one K chunk
   static constexpr int CHUNK_IMG_BYTES = NCTA * 2 * B_BYTES;      // one full chunk of the W image (all CTAs)
-  // kind::tf32, fp32 accumulate, A and B K-major, M = 128 * NCTA, N = 208
+  // fp32 accumulate, A and B K-major, M = 128 * NCTA, N = 208; operand format 0 = f16, 2 = tf32
+  static constexpr uint32_t FMT = F16 ? 0u : 2u;
   static constexpr uint32_t IDESC =
-      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)((TCM * NCTA) >> 4) << 24);
+      (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)((TCM * NCTA) >> 4) << 24);
 };
-// W operand image in global memory: per chunk, per CTA of the pair, [hi: kb][n (BN)][4 floats] then [lo: ...]
+// W operand image in global memory: per chunk, per CTA of the pair, [hi: kb][n (BN)][16 bytes = KPC elements] then [lo: ...];
+// f16: every chunk is a full K = 16 step (rows k >= 200 are zero); tf32: the tail chunk holds 8 rows
 __host__ __device__ constexpr int chunk_kw(int K, int c) { return (K - c * KCH) < KCH ? (K - c * KCH) : KCH; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,19 +63,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((SBO >> 4) & 0x3FFFu) << 32) | (1ull << 46);        // version 1 (Blackwell), no swizzle
 }
-// D[tmem] (+)= A[tmem] . B[smem]: A is [128 lanes = rows][8 columns = k] of tensor memory (of each CTA of a pair)
+// D[tmem] (+)= A[tmem] . B[smem]: A is [128 lanes = rows][8 columns] of tensor memory (of each CTA of a pair): one k
+// per column for tf32 (K = 8), two packed fp16 per column, even k in the low half, for f16 (K = 16)
+#if TACTOR_F16
+#define TACTOR_MMA_KIND "kind::f16"
+#else
+#define TACTOR_MMA_KIND "kind::tf32"
+#endif
 template <int NCTA>
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_split(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
   if constexpr (NCTA == 1)
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "tcgen05.mma.cta_group::1." TACTOR_MMA_KIND " [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(Cfg<1>::IDESC), "r"(accumulate)
         : "memory");
   else
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "tcgen05.mma.cta_group::2." TACTOR_MMA_KIND " [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(Cfg<2>::IDESC), "r"(accumulate)
         : "memory");
 }
@@ -165,11 +183,14 @@ struct Params {
   const float* b1[3];     // [208]
   const float* wimg[NGEMM];
   const float* bias[NGEMM];
+  float wscale_inv[NGEMM]; // 1 / (power-of-two scale folded into wimg[g]); 1 for tf32
   const float* w_head[2]; // packed [208,208], first 2 / 3 columns used
   const float* b_head[2];
   float* geo;             // [B,N,2]
   float* topo;            // [B,N,3]
   int M;                  // B*N
+  int split_from;         // first CTA that owns a piece of a tile (tiles of the last partial wave), grid size if none
+  int split_f;            // pieces per split tile: 1, 2 or 4
   int* error_flag;
 };
 

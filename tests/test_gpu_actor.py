@@ -144,3 +144,26 @@ def test_set_weights_and_learner_round_trip():
     assert (g2 - gn2).abs().max() <= ATOL and (t2 - tn2).abs().max() <= ATOL
     assert not torch.equal(g2, g1)
     a.check()
+
+
+@pytest.mark.parametrize("nodes,B", [(16, 300), (16, 100), (32, 150)])
+def test_last_wave_split_is_bit_identical(nodes, B, monkeypatch):
+    """tiles of the last partial wave are cut into 2 or 4 row pieces (one CTA each); rows are independent, so the
+    outputs must equal those of the unsplit launch bit for bit"""
+    from mop_truss_marl_b200 import actor, tf_checkpoint
+    w = tf_checkpoint.random_actor_weights(seed=3)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    r = lambda *s: torch.rand(*s, device="cuda", generator=g)   # noqa: E731
+    sc = 1.0 / nodes                                             # keeps the activations O(1)
+    inp = (r(B, nodes, 13), r(nodes, nodes) * sc, r(B, nodes, nodes) * sc, r(B, nodes, nodes) * sc, r(B, nodes, nodes) * sc,
+           r(B, 3, 4), r(B, 3, 3) * 0.3)
+    outs = []
+    for no_split in ("0", "1"):
+        monkeypatch.setenv("TACTOR_NO_SPLIT", no_split)
+        pol = actor.BatchedActor(w, nodes, B)
+        geo, topo = pol.forward(*inp)
+        torch.cuda.synchronize()
+        pol.check()
+        outs.append((geo.clone(), topo.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert bool(torch.isfinite(outs[0][0]).all()) and 0.0 < float(outs[0][0].min()) and float(outs[0][0].max()) < 1.0
