@@ -38,25 +38,29 @@ using fused::KH;
 
 constexpr int PTHREADS = 704;
 constexpr int NGENW = 16, NEPIW = 4, W_ISSUER = 20, W_PRODUCER = 21;
-constexpr int KPT = 4;                                      // k values per generator thread and chunk
+constexpr int KPT = 8;                                      // k values per generator thread and chunk (a k-half)
 constexpr int PAST = F16 ? 6 : 3;                           // A-operand stages in tensor memory
 constexpr int ACOLS = F16 ? 8 : 16;                         // TMEM columns of one A stage (f16: two k per column)
 constexpr int MAXST = 6;                                    // barrier slots per ring
 constexpr int TM_ACC1 = 256, TM_AHI = 208, TM_ALO = 464;
 constexpr int LDH = 204;                                    // padded row length of the H tile (12 r mod 32 distinct for 8 rows)
-constexpr int LDX = 4;                                      // row length of the warp-private exchange tile
+constexpr int LDX = 4;                                      // row length of a warp-private exchange tile (two tiles per warp)
 constexpr int NCH = (KH + KCH - 1) / KCH;                   // 13 chunks per GEMM
 constexpr int DMAX = 8;                                     // neighbour slots of the compacted adjacency row
 
 template <int NODES, int NCTA>
 __host__ __device__ constexpr int pipe_smem_bytes() {
-  return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + NGENW * 32 * LDX * 4 + 14 * 208 * 4 +
+  return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + 2 * NGENW * 32 * LDX * 4 + 14 * 208 * 4 +
          (TCM / NODES) * 208 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + NGEMM * 208 * 4 + 384;
 }
 
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
                "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
                : "memory");
 }
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
@@ -79,10 +83,11 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   constexpr int ENVS = TCM / NODES;
   constexpr int WST = Cfg<NCTA>::WST, STAGE_BYTES = Cfg<NCTA>::STAGE_BYTES, B_LBO = Cfg<NCTA>::B_LBO;
   static_assert(pipe_smem_bytes<NODES, NCTA>() <= 232448, "shared memory budget");
+  static_assert(F16 && KH % KPT == 0 && KCH == 2 * KPT, "the generators are written for the fp16 split (16-wide k-steps, two k-halves)");
   extern __shared__ __align__(128) unsigned char smem[];
   float* H = reinterpret_cast<float*>(smem + WST * STAGE_BYTES);             // [128][LDH]
   float* Xt = H + TCM * LDH;                                                 // [8 warps][32][LDX] exchange tiles
-  float* W1s = Xt + NGENW * 32 * LDX;                                        // [14][208] layer-1 kernel + bias row
+  float* W1s = Xt + 2 * NGENW * 32 * LDX;                                        // [14][208] layer-1 kernel + bias row
   float* Pl = W1s + 14 * 208;                                                // [ENVS][208] pooled Pareto embedding
   float* AnT = Pl + ENVS * 208;                                              // [N(j)][N(n)] shared A_n, transposed
   float* Wh = AnT + NODES * NODES;                                           // [2][201][4] head kernels, row 200 = bias
@@ -134,7 +139,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       mbar_init(w_empty + 8 * s, 1);
     }
     for (int s = 0; s < PAST; ++s) {
-      mbar_init(a_full + 8 * s, NGENW * NCTA);
+      mbar_init(a_full + 8 * s, (NGENW / 2) * NCTA);       // the eight warps of the chunk's parity
       mbar_init(a_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -193,7 +198,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
 
   // =================================================== generators ===========================================
   auto generator_role = [&]() {
-    const int q = warp & 3, kq = warp >> 2;
+    // row group q, k-half kh of the chunk, chunk parity par: a warp works on every other chunk (8 k per thread), so
+    // two chunks are always in flight in different warps and the per-chunk sync overhead is paid per 8 k
+    const int q = warp & 3, kh = (warp >> 2) & 1, par = warp >> 3;
     // gcn_l1_2 / gcn_l1_3 kernels replace gcn_l1_1's in shared memory before GEMM 1 / 3 (all 16 generator warps take part)
     auto w1_src = [&](int l1, int idx) -> const float4* {
       return (idx < 13 * 52) ? reinterpret_cast<const float4*>(P.w1[l1]) + idx
@@ -223,6 +230,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         if (g == 1 || g == 3) reload_w1(g);
         for (int c = 0; c < NCH; ++c) {
           const uint32_t u = (uint32_t)(g * NCH + c), sa = u % PAST;
+          if ((int)(u & 1u) != par) continue;
           if (u >= PAST) ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok;
           __syncwarp();
           if (lane == 0) {
@@ -237,7 +245,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     const int e = r / NODES, n = r % NODES;
     const int lane_env0 = lane & ~(NODES - 1);               // first lane of this row's environment inside the warp
     const bool env_valid = (env0 + e) * NODES < M;
-    float* xt = Xt + warp * 32 * LDX;                        // warp-private exchange tile
+    float* xt = Xt + warp * 2 * 32 * LDX;                    // warp-private exchange tiles: k0..k0+3 | k0+4..k0+7
     // Z = A_n . x_n (gcn_l1_1..3 share input and adjacency: formed once, kept in registers)
     float z[13];
 #pragma unroll
@@ -349,59 +357,72 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       if (g == 5) { ok = mbar_wait(h_ready, 0) && ok; }      // H complete (epilogue of GEMM 4)
       PDBG_T(tg2);
       PDBG_ACC(0, tg1 - tg0); PDBG_ACC(1, tg2 - tg1);
-      // ---- 13 chunks: generate, mix with the adjacency, split, store to tensor memory ----
+      // ---- this warp's chunks of the GEMM: generate, mix with the adjacency, split, store to tensor memory ----
       for (int c = 0; c < NCH; ++c) {
         const uint32_t u = (uint32_t)(g * NCH + c), sa = u % PAST;
+        if ((int)(u & 1u) != par) continue;                  // the other parity's warps own this chunk
         PDBG_T(t1);
-        const int k0 = c * KCH + KPT * kq;
-        if (k0 < KH) {                                       // warp-uniform (tail chunk: k-quarters 0 and 1 only)
-          float y[KPT] = {0.f, 0.f, 0.f, 0.f};
+        const int k0 = c * KCH + KPT * kh;
+        const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
+        const uint32_t col = (uint32_t)(ACOLS * sa + (KPT / 2) * kh);      // packed column of k0 inside the A stage
+        if (k0 < KH) {                                       // warp-uniform; KH is a multiple of 8: all 8 k are real
+          float y[KPT];
+#pragma unroll
+          for (int t = 0; t < KPT; ++t) y[t] = 0.f;
           if (g <= 4) {
-            float4 x;
-            if (g <= 3) {
-              x = *reinterpret_cast<const float4*>(W1s + 13 * 208 + k0);
-              float4 wa[7], wb[6];                           // two batches of (broadcast) loads in flight ahead of the FMAs
 #pragma unroll
-              for (int i = 0; i < 7; ++i) wa[i] = *reinterpret_cast<const float4*>(W1s + i * 208 + k0);
+            for (int hf = 0; hf < 2; ++hf) {                 // the two float4 halves of the thread's 8 k, one after the other
+              const int kk = k0 + 4 * hf;
+              float4 x;
+              if (g <= 3) {
+                x = *reinterpret_cast<const float4*>(W1s + 13 * 208 + kk);
+                float4 wa[7], wb[6];                         // two batches of (broadcast) loads in flight ahead of the FMAs
 #pragma unroll
-              for (int i = 0; i < 6; ++i) wb[i] = *reinterpret_cast<const float4*>(W1s + (7 + i) * 208 + k0);
+                for (int i = 0; i < 7; ++i) wa[i] = *reinterpret_cast<const float4*>(W1s + i * 208 + kk);
 #pragma unroll
-              for (int i = 0; i < 7; ++i) {
-                x.x = fmaf(z[i], wa[i].x, x.x); x.y = fmaf(z[i], wa[i].y, x.y); x.z = fmaf(z[i], wa[i].z, x.z); x.w = fmaf(z[i], wa[i].w, x.w);
+                for (int i = 0; i < 6; ++i) wb[i] = *reinterpret_cast<const float4*>(W1s + (7 + i) * 208 + kk);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                  x.x = fmaf(z[i], wa[i].x, x.x); x.y = fmaf(z[i], wa[i].y, x.y); x.z = fmaf(z[i], wa[i].z, x.z); x.w = fmaf(z[i], wa[i].w, x.w);
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                  x.x = fmaf(z[7 + i], wb[i].x, x.x); x.y = fmaf(z[7 + i], wb[i].y, x.y); x.z = fmaf(z[7 + i], wb[i].z, x.z); x.w = fmaf(z[7 + i], wb[i].w, x.w);
+                }
+                x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
+              } else {
+                // the reference's stack-and-reshape scramble: x14b[b,n,h] = pooled[b,(n*200+h)/N] (truss2D_RL.py:89-95)
+                const float* pl = Pl + e * 208;
+                const int f = n * KH + kk;
+                x = make_float4(pl[f / NODES], pl[(f + 1) / NODES], pl[(f + 2) / NODES], pl[(f + 3) / NODES]);
               }
-#pragma unroll
-              for (int i = 0; i < 6; ++i) {
-                x.x = fmaf(z[7 + i], wb[i].x, x.x); x.y = fmaf(z[7 + i], wb[i].y, x.y); x.z = fmaf(z[7 + i], wb[i].z, x.z); x.w = fmaf(z[7 + i], wb[i].w, x.w);
-              }
-              x = make_float4(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f));
-            } else {
-              // the reference's stack-and-reshape scramble: x14b[b,n,h] = pooled[b,(n*200+h)/N] (truss2D_RL.py:89-95)
-              const float* pl = Pl + e * 208;
-              const int f = n * KH + k0;
-              x = make_float4(pl[f / NODES], pl[(f + 1) / NODES], pl[(f + 2) / NODES], pl[(f + 3) / NODES]);
+              *reinterpret_cast<float4*>(xt + (hf * 32 + lane) * LDX) = x;
             }
             PDBG_T(tx);
             PDBG_ACC(5, tx - t1);
             hand_off();                                      // publish the previous chunk's stage
-            *reinterpret_cast<float4*>(xt + lane * LDX) = x;
             __syncwarp();
             if (!dense) {
 #pragma unroll
               for (int d = 0; d < DMAX; ++d) {
                 if (d >= dcnt) break;                        // warp-uniform
-                float4 t0 = x;                               // slot 0 = this row itself when self_first (warp-uniform)
-                if (d > 0 || !self_first) t0 = *reinterpret_cast<const float4*>(xt + (int)((nidx_packed >> (8 * d)) & 0xff) * LDX);
+                const int j = (int)((nidx_packed >> (8 * d)) & 0xff);
+                const float4 t0 = *reinterpret_cast<const float4*>(xt + j * LDX);
+                const float4 t1v = *reinterpret_cast<const float4*>(xt + (32 + j) * LDX);
                 y[0] = fmaf(coef[d], t0.x, y[0]); y[1] = fmaf(coef[d], t0.y, y[1]); y[2] = fmaf(coef[d], t0.z, y[2]); y[3] = fmaf(coef[d], t0.w, y[3]);
+                y[4] = fmaf(coef[d], t1v.x, y[4]); y[5] = fmaf(coef[d], t1v.y, y[5]); y[6] = fmaf(coef[d], t1v.z, y[6]); y[7] = fmaf(coef[d], t1v.w, y[7]);
               }
             } else {
 #pragma unroll 1
               for (int j = 0; j < NODES; ++j) {
                 const float a = arow[j * astride];
                 const float4 t0 = *reinterpret_cast<const float4*>(xt + (lane_env0 + j) * LDX);
+                const float4 t1v = *reinterpret_cast<const float4*>(xt + (32 + lane_env0 + j) * LDX);
                 y[0] = fmaf(a, t0.x, y[0]); y[1] = fmaf(a, t0.y, y[1]); y[2] = fmaf(a, t0.z, y[2]); y[3] = fmaf(a, t0.w, y[3]);
+                y[4] = fmaf(a, t1v.x, y[4]); y[5] = fmaf(a, t1v.y, y[5]); y[6] = fmaf(a, t1v.z, y[6]); y[7] = fmaf(a, t1v.w, y[7]);
               }
             }
-            __syncwarp();                                    // the tile is rewritten by the next chunk
+            __syncwarp();                                    // the tiles are rewritten by this warp's next chunk
           } else {
             // layer 3: the operand rows are rows of H (shared memory), no exchange tile needed
             hand_off();                                      // publish the previous chunk's stage
@@ -410,53 +431,49 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
 #pragma unroll
               for (int d = 0; d < DMAX; ++d) {
                 if (d >= dcnt) break;                        // warp-uniform
-                const float4 t0 = *reinterpret_cast<const float4*>(hb + (int)((nidx_packed >> (8 * d)) & 0xff) * LDH);
+                const float* hr = hb + (int)((nidx_packed >> (8 * d)) & 0xff) * LDH;
+                const float4 t0 = *reinterpret_cast<const float4*>(hr);
+                const float4 t1v = *reinterpret_cast<const float4*>(hr + 4);
                 y[0] = fmaf(coef[d], t0.x, y[0]); y[1] = fmaf(coef[d], t0.y, y[1]); y[2] = fmaf(coef[d], t0.z, y[2]); y[3] = fmaf(coef[d], t0.w, y[3]);
+                y[4] = fmaf(coef[d], t1v.x, y[4]); y[5] = fmaf(coef[d], t1v.y, y[5]); y[6] = fmaf(coef[d], t1v.z, y[6]); y[7] = fmaf(coef[d], t1v.w, y[7]);
               }
             } else {
 #pragma unroll 1
               for (int j = 0; j < NODES; ++j) {
                 const float a = arow[j * astride];
-                const float4 t0 = *reinterpret_cast<const float4*>(hb + (lane_env0 + j) * LDH);
+                const float* hr = hb + (lane_env0 + j) * LDH;
+                const float4 t0 = *reinterpret_cast<const float4*>(hr);
+                const float4 t1v = *reinterpret_cast<const float4*>(hr + 4);
                 y[0] = fmaf(a, t0.x, y[0]); y[1] = fmaf(a, t0.y, y[1]); y[2] = fmaf(a, t0.z, y[2]); y[3] = fmaf(a, t0.w, y[3]);
+                y[4] = fmaf(a, t1v.x, y[4]); y[5] = fmaf(a, t1v.y, y[5]); y[6] = fmaf(a, t1v.z, y[6]); y[7] = fmaf(a, t1v.w, y[7]);
               }
             }
           }
           PDBG_T(t2);
           PDBG_ACC(3, t2 - t1);
-          const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
-          acquire(u, sa);
-          if constexpr (F16) {
-            // y = hi + lo in fp16, two k per 32-bit column (even k in the low half)
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(y[0]), fabsf(y[1])), fmaxf(fabsf(y[2]), fabsf(y[3]))));
-            const __half2 h01 = __floats2half2_rn(y[0], y[1]), h23 = __floats2half2_rn(y[2], y[3]);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const __half2 l01 = __floats2half2_rn(y[0] - f01.x, y[1] - f01.y), l23 = __floats2half2_rn(y[2] - f23.x, y[3] - f23.y);
-            tmem_st2(tmem_base + lane_sel + (uint32_t)(TM_AHI + ACOLS * sa + 2 * kq), h2_bits(h01), h2_bits(h23));
-            tmem_st2(tmem_base + lane_sel + (uint32_t)(TM_ALO + ACOLS * sa + 2 * kq), h2_bits(l01), h2_bits(l23));
-          } else {
-            float hi[KPT], lo[KPT];
+          // y = hi + lo in fp16, two k per 32-bit column (even k in the low half)
+          uint32_t hi[KPT / 2], lo[KPT / 2];
 #pragma unroll
-            for (int t = 0; t < KPT; ++t) {
-              hi[t] = __uint_as_float(__float_as_uint(y[t]) & 0xFFFFE000u);
-              lo[t] = y[t] - hi[t];
-            }
-            tmem_st4(tmem_base + lane_sel + (uint32_t)(TM_AHI + ACOLS * sa + KPT * kq), hi);
-            tmem_st4(tmem_base + lane_sel + (uint32_t)(TM_ALO + ACOLS * sa + KPT * kq), lo);
+          for (int t = 0; t < KPT / 2; ++t) {
+            amax = fmaxf(amax, fmaxf(fabsf(y[2 * t]), fabsf(y[2 * t + 1])));
+            const __half2 h = __floats2half2_rn(y[2 * t], y[2 * t + 1]);
+            const float2 f = __half22float2(h);
+            hi[t] = h2_bits(h);
+            lo[t] = h2_bits(__floats2half2_rn(y[2 * t] - f.x, y[2 * t + 1] - f.y));
           }
+          acquire(u, sa);
+          tmem_st4u(tmem_base + lane_sel + (uint32_t)TM_AHI + col, hi);
+          tmem_st4u(tmem_base + lane_sel + (uint32_t)TM_ALO + col, lo);
           PDBG_T(t4);
           PDBG_ACC(6, t4 - t2);
-        } else if constexpr (F16) {
-          // f16 k-steps are 16 wide: the tail chunk's k >= 200 columns of the A stage must hold zeros
-          const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
+        } else {
+          // k0 == 200 (tail chunk, upper k-half): column 200 of A is the constant 1 that multiplies the bias row of the
+          // W image, columns 201..207 are zero
+          const uint32_t one[4] = {0x00003C00u, 0u, 0u, 0u}, zero[4] = {0u, 0u, 0u, 0u};
           hand_off();
           acquire(u, sa);
-          // ... except column k = 200, the constant 1 that multiplies the bias row of the W image
-          tmem_st2(tmem_base + lane_sel + (uint32_t)(TM_AHI + ACOLS * sa + 2 * kq), k0 == KH ? 0x00003C00u : 0u, 0u);
-          tmem_st2(tmem_base + lane_sel + (uint32_t)(TM_ALO + ACOLS * sa + 2 * kq), 0u, 0u);
-        } else {
-          hand_off();                                        // tf32 tail chunk: nothing to store for this k-quarter
-          acquire(u, sa);
+          tmem_st4u(tmem_base + lane_sel + (uint32_t)TM_AHI + col, one);
+          tmem_st4u(tmem_base + lane_sel + (uint32_t)TM_ALO + col, zero);
         }
         pending = (int)sa;
         PDBG_T(t3);
