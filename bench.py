@@ -372,10 +372,10 @@ def main():
         stages = {"actor_ms": actor_ms, "fem_ms": fem_ms,
                   "fem_only_env_steps_per_s": B * world / (fem_ms * 1e-3)}
         if use_actor and actor_ms > fem_ms:
-            # dominant stage = actor_pipe_kernel (tcgen05 kind::tf32 with the 3xTF32 split = float32-equivalent
+            # dominant stage = actor_pipe_kernel (tcgen05 kind::f16 with the fp16 hi/lo split = float32-equivalent
             # accuracy, three MMAs per product).  achieved counts ALGORITHMIC flops (one multiply-add per
-            # product) against the measured bf16 cuBLAS roof; tf32 peak is half of bf16 and the split costs 3x,
-            # so 1/6 of that roof is the ceiling of this formulation.
+            # product) against the measured bf16 cuBLAS roof; fp16 runs at the bf16 rate and the split costs 3x,
+            # so 1/3 of that roof is the ceiling of this formulation.
             tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             aflops = actor_flops(N) * B
             ach = aflops / (actor_ms * 1e-3) / 1e12
@@ -386,8 +386,8 @@ def main():
                                   "OU-noise launches, about 3 % of it)",
                         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback",
                         "algorithmic_flops_per_env": actor_flops(N), "kernel_ms": actor_ms,
-                        "note": "tcgen05 kind::tf32, 3xTF32 split (float32-equivalent); algorithmic flops vs the bf16 "
-                                "tensor roof (formulation ceiling = roof/6)"}
+                        "note": "tcgen05 kind::f16, fp16 hi/lo split = 3 MMAs per product (float32-equivalent); algorithmic "
+                                "flops vs the bf16 tensor roof (formulation ceiling = roof/3)"}
         else:
             roofline = roof_fem
         n_cpu, t_cpu = oracle_steps_per_sec(args.family, args.cpu_seconds, with_actor=use_actor)

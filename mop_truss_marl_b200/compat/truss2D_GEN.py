@@ -169,10 +169,39 @@ class gen_model:
 
     # ---- structure text format (truss2D_GEN.py:193-211; parsed by render/truss2D_READ.py:136-172) --------
     def savetxt(self, name):
-        with open(name, "w+") as f:
+        """same lines as the reference; numbers are printed the way its pinned NumPy 1.23 prints them (float32 heights
+        as ``3.2``, never ``np.float32(3.2)``), see mop_truss_marl_b200/structure_text.py"""
+        from mop_truss_marl_b200.structure_text import _num
+        with open(name, "w+", newline="") as f:
             for ld in self.model.loads:
-                f.write(" {}\r\n".format(ld))
+                f.write(" {}, [{}, {}]\r\n".format(ld.name, _num(ld.size[0]), _num(ld.size[1])))
             for n in self.model.nodes:
-                f.write(" {}\r\n".format(n))
+                loads = "[" + ", ".join("[{}, [{}, {}]]".format(l[0].name, _num(l[0].size[0]), _num(l[0].size[1]))
+                                        for l in n.loads) + "]"
+                f.write(" {}, [{}, {}], [{}, {}], {}\r\n".format(n.name, _num(n.coord[0]), _num(n.coord[1]),
+                                                                 _num(n.res[0]), _num(n.res[1]), loads))
             for el in self.model.elements:
-                f.write(" {},{},{},{},{},{}\r\n".format(el.name, el.nodes[0].name, el.nodes[1].name, el.em, el.area, el.i))
+                f.write(" {},{},{},{},{},[[{}]]\r\n".format(el.name, el.nodes[0].name, el.nodes[1].name, _num(el.em),
+                                                            _num(el.area), _num(el.i[0][0])))
+
+    def read_src(self, src):
+        """``gen_model.read_src`` of the renderers (render/truss2D_READ.py:136-172): loads, node coordinates / supports
+        and element E / A / I / section number from a structure text file onto ``self.model``"""
+        from mop_truss_marl_b200.structure_text import parse_structure
+        with open(src, newline="") as f:
+            d = parse_structure(f.read())
+        for ld in self.model.loads:
+            if ld.name in d["loads"]:
+                ld.size[0], ld.size[1] = d["loads"][ld.name]
+        for n in self.model.nodes:
+            if n.name in d["nodes"]:
+                x, y, rx, ry = d["nodes"][n.name]
+                n.coord[0], n.coord[1], n.res[0], n.res[1] = x, y, rx, ry
+        for el in self.model.elements:
+            if el.name in d["elements"]:
+                _, _, em, area, inertia = d["elements"][el.name]
+                el.em, el.area = em, area
+                el.i[0][0] = inertia
+                for k in range(len(self.truss)):
+                    if el.area == self.truss[k][0] * 1e-4:
+                        el.section_no = k

@@ -164,59 +164,42 @@ cudaError_t upload_weights(tactor_handle_s* h, const tactor_weights* w) {
     if (e == cudaSuccess) e = cudaMemcpy(h->d_w[l], wp.data(), wp.size() * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_b[l], bp.data(), bp.size() * 4, cudaMemcpyHostToDevice);
   }
-  // tcgen05 operand images of the [200,200] layers: per 16-wide K chunk, per CTA of the pair (its half of the
-  // 208 columns), [hi|lo][kb][n][16 bytes].  tf32: 4 floats per 16 bytes, hi = 10-bit-mantissa truncation.  f16: 8 halfs
-  // per 16 bytes, W scaled by S = 2^s (largest s with max|W| S <= 2^14, so that hi and lo stay normal fp16 numbers),
-  // hi = fp16(W S), lo = fp16(W S - hi); the kernel's epilogue multiplies the accumulator by 1/S (exact).  Row k = 200
-  // of the image (inside the zero-padded tail chunk) holds the bias: the generators feed a constant 1 in column 200 of A.
+  // tcgen05 operand images of the [200,200] layers: per 16-wide K chunk, per CTA of the pair (its half of the 208
+  // columns), [hi|lo][kb][n][8 halfs].  W is scaled by S = 2^s (largest s with max(|W|, |b|) S < 2^14, so that hi and lo stay
+  // normal fp16 numbers), hi = fp16(W S), lo = fp16(W S - hi); the kernel's epilogue multiplies the accumulator by 1/S
+  // (exact).  Row k = 200 of the image (inside the zero-padded tail chunk) holds the bias: the generators feed a constant
+  // 1 in column 200 of A.
   const int bn = tactor::tc::TCN / h->ncta;
   for (int l = 0; l < TACTOR_NLAYERS; ++l) h->wscale_inv[l] = 1.f;
   for (int l = 4; l <= 10 && e == cudaSuccess; ++l) {
     const int K = kIn[l], kout = kOut[l];
-    std::vector<unsigned char> img;
-    auto push = [&](const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); img.insert(img.end(), b, b + n); };
-    float scale = 1.f;
-    if (tactor::tc::F16) {
-      float wmax = 0.f;
-      for (size_t i = 0; i < (size_t)K * kout; ++i) wmax = fmaxf(wmax, fabsf(w->kernel[l][i]));
-      for (int i = 0; i < kout; ++i) wmax = fmaxf(wmax, fabsf(w->bias[l][i]));      // row K of the image is the bias
-      if (!(wmax < INFINITY)) return cudaErrorInvalidValue;
-      int ex = 0;
-      if (wmax > 0.f) { frexpf(wmax, &ex); ex = 14 - ex; }         // wmax in [2^(e-1), 2^e): wmax * 2^(14-e) < 2^14
-      ex = ex > 24 ? 24 : (ex < -24 ? -24 : ex);
-      scale = ldexpf(1.f, ex);
-      h->wscale_inv[l] = ldexpf(1.f, -ex);
-    }
-    const int kpc = tactor::tc::KPC;
-    for (int c = 0; c * tactor::tc::KCH < K; ++c) {
-      const int kw = tactor::tc::F16 ? tactor::tc::KCH : tactor::tc::chunk_kw(K, c), nkb = kw / kpc;
+    float wmax = 0.f;
+    for (size_t i = 0; i < (size_t)K * kout; ++i) wmax = fmaxf(wmax, fabsf(w->kernel[l][i]));
+    for (int i = 0; i < kout; ++i) wmax = fmaxf(wmax, fabsf(w->bias[l][i]));
+    if (!(wmax < INFINITY)) return cudaErrorInvalidValue;
+    int ex = 0;
+    if (wmax > 0.f) { frexpf(wmax, &ex); ex = 14 - ex; }           // wmax in [2^(e-1), 2^e): wmax * 2^(14-e) < 2^14
+    ex = ex > 24 ? 24 : (ex < -24 ? -24 : ex);
+    const float scale = ldexpf(1.f, ex);
+    h->wscale_inv[l] = ldexpf(1.f, -ex);
+    std::vector<__half> img;
+    const int kpc = tactor::tc::KPC, nkb = tactor::tc::KCH / kpc;
+    for (int c = 0; c * tactor::tc::KCH < K + 1; ++c)
       for (int half = 0; half < h->ncta; ++half)
-      for (int part = 0; part < 2; ++part)
-        for (int kb = 0; kb < nkb; ++kb)
-          for (int nl = 0; nl < bn; ++nl)
-            for (int t = 0; t < kpc; ++t) {
-              const int n = half * bn + nl;
-              const int k = c * tactor::tc::KCH + kpc * kb + t;
-              float v = (n < kout && k < K) ? w->kernel[l][(size_t)k * kout + n] * scale : 0.f;
-              if (tactor::tc::F16 && n < kout && k == K) v = w->bias[l][n] * scale;   // A's column K is the constant 1
-              if (tactor::tc::F16) {
+        for (int part = 0; part < 2; ++part)
+          for (int kb = 0; kb < nkb; ++kb)
+            for (int nl = 0; nl < bn; ++nl)
+              for (int t = 0; t < kpc; ++t) {
+                const int n = half * bn + nl;
+                const int k = c * tactor::tc::KCH + kpc * kb + t;
+                float v = 0.f;
+                if (n < kout && k < K) v = w->kernel[l][(size_t)k * kout + n] * scale;
+                else if (n < kout && k == K) v = w->bias[l][n] * scale;       // A's column K is the constant 1
                 const __half hi = __float2half_rn(v);
-                const __half lo = __float2half_rn(v - __half2float(hi));
-                const __half pick = part == 0 ? hi : lo;
-                push(&pick, 2);
-              } else {
-                uint32_t bits;
-                memcpy(&bits, &v, 4);
-                bits &= 0xFFFFE000u;
-                float hi;
-                memcpy(&hi, &bits, 4);
-                const float pick = part == 0 ? hi : v - hi;
-                push(&pick, 4);
+                img.push_back(part == 0 ? hi : __float2half_rn(v - __half2float(hi)));
               }
-            }
-    }
-    if (!h->d_wimg[l]) e = cudaMalloc(&h->d_wimg[l], img.size());
-    if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size(), cudaMemcpyHostToDevice);
+    if (!h->d_wimg[l]) e = cudaMalloc(&h->d_wimg[l], img.size() * sizeof(__half));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice);
   }
   return e;
 }

@@ -1,28 +1,32 @@
 // Whole-network fused actor kernel, fully pipelined ("pipe") formulation.
 //
 // One CTA (or CTA pair, NCTA = 2) carries a 128-row tile (ENVS environments of NODES nodes) through all 13
-// GCNConv layers of multimodes_actor.call (train/code/truss2D_RL.py:75-127).  Compared with the first fused
-// kernel the adjacency product is moved IN FRONT of the dense contraction,
+// GCNConv layers of multimodes_actor.call (train/code/truss2D_RL.py:75-127).  The adjacency product is moved IN FRONT
+// of the dense contraction,
 //
-//      A_g . (X_g . W_g) + b_g   ==   (A_g . X_g) . W_g + b_g          (spektral GCNConv, associativity)
+//      A_g . (X_g . W_g) + b_g   ==   [A_g . X_g, 1] . [W_g ; b_g]        (spektral GCNConv, associativity)
 //
-// so that the tensor-core epilogue is row-local (bias, ReLU, accumulate) and three groups of warps can run
-// concurrently, coupled only by mbarriers:
+// so that the tensor-core epilogue is row-local (scale, ReLU, accumulate) and four groups of warps run concurrently,
+// coupled only by mbarriers:
 //
-//   generators  warps 0-15   row r = 32*(warp&3)+lane, k-quarter (warp>>2) of every 16-wide K chunk:
+//   generators  warps 0-15   row group q = warp & 3 (row r = 32 q + lane), k-half kh, chunk parity par: a warp owns
+//                            every other 16-wide K chunk and 8 k of it per thread:
 //                            x = layer-1 activations / Pareto embedding / H  ->  y = sum_j A_g[r,j] x[j]
-//                            (neighbour rows live in the same warp: exchange through a warp-private tile,
+//                            (neighbour rows live in the same warp: exchange through two warp-private tiles,
 //                            __syncwarp only; <= 8 neighbours per row go through a compacted list, denser rows
-//                            through the full row)  ->  3xTF32 split  ->  tcgen05.st into the A stage (TMEM)
+//                            through the full row)  ->  y = hi + lo in fp16  ->  tcgen05.st into the A stage (TMEM,
+//                            two k per column).  The stage is acquired right before the store and published in
+//                            the middle of the warp's next chunk (hand_off), off the dependent chain.
 //   producer    warp 21      streams the pre-split W chunks into shared memory (cp.async.bulk, mbarrier tx),
 //                            running ahead across GEMM boundaries
-//   issuer      warp 20      tcgen05.mma kind::tf32, A from tensor memory, B from shared memory, accumulator
-//                            g&1 of two (TMEM columns [0,208) and [256,464))
+//   issuer      warp 20      tcgen05.mma kind::f16 (Yhi.Whi + Yhi.Wlo + Ylo.Whi), A from tensor memory, B from
+//                            shared memory, accumulator g&1 of two (TMEM columns [0,208) and [256,464))
 //   epilogue    warps 16-19  tcgen05.ld the finished accumulator while the next GEMM is already running:
-//                            relu(D + b) -> H (+)= (g <= 4), or the sigmoid heads gcn_l4_1/2 (g = 5, 6)
+//                            relu(D / S) -> H (+)= (g <= 4), or the sigmoid heads gcn_l4_1/2 (g = 5, 6); the bias is
+//                            row 200 of the W image (A's column 200 is the constant 1)
 //
-// TMEM map (512 columns): [0,208) acc0 | [208,256) A stages hi (f16: 6 x 8 columns of packed pairs; tf32: 3 x 16)
-//                         | [256,464) acc1 | [464,512) A stages lo
+// TMEM map (512 columns): [0,208) acc0 | [208,256) A stages hi (6 x 8 columns of packed pairs) | [256,464) acc1
+//                         | [464,512) A stages lo
 #pragma once
 #include <cuda_fp16.h>
 
@@ -39,8 +43,8 @@ using fused::KH;
 constexpr int PTHREADS = 704;
 constexpr int NGENW = 16, NEPIW = 4, W_ISSUER = 20, W_PRODUCER = 21;
 constexpr int KPT = 8;                                      // k values per generator thread and chunk (a k-half)
-constexpr int PAST = F16 ? 6 : 3;                           // A-operand stages in tensor memory
-constexpr int ACOLS = F16 ? 8 : 16;                         // TMEM columns of one A stage (f16: two k per column)
+constexpr int PAST = 6;                                     // A-operand stages in tensor memory
+constexpr int ACOLS = 8;                                    // TMEM columns of one A stage (two fp16 k per 32-bit column)
 constexpr int MAXST = 6;                                    // barrier slots per ring
 constexpr int TM_ACC1 = 256, TM_AHI = 208, TM_ALO = 464;
 constexpr int LDH = 204;                                    // padded row length of the H tile (12 r mod 32 distinct for 8 rows)
@@ -51,20 +55,12 @@ constexpr int DMAX = 8;                                     // neighbour slots o
 template <int NODES, int NCTA>
 __host__ __device__ constexpr int pipe_smem_bytes() {
   return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + 2 * NGENW * 32 * LDX * 4 + 14 * 208 * 4 +
-         (TCM / NODES) * 208 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + NGEMM * 208 * 4 + 384;
+         (TCM / NODES) * 208 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + 384;
 }
 
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
-               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
-               : "memory");
-}
 __device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
                : "memory");
-}
-__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ uint32_t h2_bits(const __half2& h) { return *reinterpret_cast<const uint32_t*>(&h); }
 // tcgen05.ld of 8 accumulator columns without the wait (software pipelining in the epilogue)
@@ -83,7 +79,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   constexpr int ENVS = TCM / NODES;
   constexpr int WST = Cfg<NCTA>::WST, STAGE_BYTES = Cfg<NCTA>::STAGE_BYTES, B_LBO = Cfg<NCTA>::B_LBO;
   static_assert(pipe_smem_bytes<NODES, NCTA>() <= 232448, "shared memory budget");
-  static_assert(F16 && KH % KPT == 0 && KCH == 2 * KPT, "the generators are written for the fp16 split (16-wide k-steps, two k-halves)");
+  static_assert(KH % KPT == 0 && KCH == 2 * KPT, "16-wide k-steps, two k-halves per chunk");
   extern __shared__ __align__(128) unsigned char smem[];
   float* H = reinterpret_cast<float*>(smem + WST * STAGE_BYTES);             // [128][LDH]
   float* Xt = H + TCM * LDH;                                                 // [8 warps][32][LDX] exchange tiles
@@ -92,8 +88,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   float* AnT = Pl + ENVS * 208;                                              // [N(j)][N(n)] shared A_n, transposed
   float* Wh = AnT + NODES * NODES;                                           // [2][201][4] head kernels, row 200 = bias
   float* Us = Wh + 2 * 201 * 4;                                              // [128][4] head pre-activations
-  float* Bs = Us + TCM * 4;                                                  // [7][208] biases of the hidden layers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + NGEMM * 208);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Us + TCM * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * MAXST + 6);
 
   // the shuffle tells the compiler that `warp` is warp-uniform: role branches become uniform branches and the
@@ -164,8 +159,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   for (int idx = tid; idx < 14 * 52; idx += PTHREADS)
     reinterpret_cast<float4*>(W1s)[idx] = (idx < 13 * 52) ? __ldg(reinterpret_cast<const float4*>(P.w1[0]) + idx)
                                                           : __ldg(reinterpret_cast<const float4*>(P.b1[0]) + (idx - 13 * 52));
-  for (int idx = tid; idx < NGEMM * 52; idx += PTHREADS)
-    reinterpret_cast<float4*>(Bs)[idx] = __ldg(reinterpret_cast<const float4*>(P.bias[idx / 52]) + idx % 52);
   float* Xraw = H;                                                           // [128][13]
   for (int idx = tid; idx < TCM * 13; idx += PTHREADS)
     Xraw[idx] = (row0 + idx / 13 < M) ? P.x_n[(size_t)row0 * 13 + idx] : 0.f;
@@ -482,7 +475,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       hand_off();                                            // the accumulator of this GEMM must not wait for the next one
       if (warp == 0) { PDBG_FLUSH(0, g); }
     }
-    if (F16 && !(amax <= F16_MAX) && P.error_flag) atomicOr(P.error_flag, 2);   // |A.X| left the fp16 range (or NaN input)
+    if (!(amax <= F16_MAX) && P.error_flag) atomicOr(P.error_flag, 2);   // |A.X| left the fp16 range (or NaN input)
   };
   if (warp < NGENW) {
     generator_role();
@@ -511,7 +504,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       PDBG_ACC(0, t1 - t0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b ? TM_ACC1 : 0);
-      const float* bias = Bs + g * 208;
       const float wsi = P.wscale_inv[g];                     // undoes the power-of-two scale folded into W (exact)
       float* hrow = H + r * LDH;
       const float* wh = Wh + (g >= 5 ? g - 5 : 0) * 201 * 4; // only used for g >= 5
@@ -520,23 +512,13 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       tmem_ld8_async(tacc, vr[0]);
 #pragma unroll 2
       for (int cb = 0; cb < KH / 8; ++cb) {
-        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-        if constexpr (!F16) {
-          b0 = *reinterpret_cast<const float4*>(bias + 8 * cb);
-          b1 = *reinterpret_cast<const float4*>(bias + 8 * cb + 4);
-        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float v[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(vr[cb & 1][t]);
         if (cb + 1 < KH / 8) tmem_ld8_async(tacc + (uint32_t)(8 * (cb + 1)), vr[(cb + 1) & 1]);   // in flight while cb is processed
-        if constexpr (F16) {                                 // bias rode along as row 200 of the W image
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t] * wsi, 0.f);
-        } else {
-          v[0] = fmaxf(v[0] + b0.x, 0.f); v[1] = fmaxf(v[1] + b0.y, 0.f); v[2] = fmaxf(v[2] + b0.z, 0.f); v[3] = fmaxf(v[3] + b0.w, 0.f);
-          v[4] = fmaxf(v[4] + b1.x, 0.f); v[5] = fmaxf(v[5] + b1.y, 0.f); v[6] = fmaxf(v[6] + b1.z, 0.f); v[7] = fmaxf(v[7] + b1.w, 0.f);
-        }
+        for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t] * wsi, 0.f);   // the bias rode along as row 200 of the W image
         if (g <= 4) {
           float4* dst = reinterpret_cast<float4*>(hrow + 8 * cb);
           float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
@@ -587,17 +569,13 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     // =================================================== MMA issuer / W forwarder =============================
     if (lane == 0) {
       if (is_leader) {
-        // [stage][k-step][hi, lo] of a full chunk; a k-step spans two 16-byte core-matrix columns (f16: the whole chunk)
-        constexpr int KSTEPS = F16 ? 1 : 2;
-        uint64_t db[WST][KSTEPS][2];
+        uint64_t db[WST][2];                                 // [stage][hi, lo]: one K = 16 step spans the chunk's two core-matrix columns
 #pragma unroll
-        for (int st = 0; st < WST; ++st)
-#pragma unroll
-          for (int ks = 0; ks < KSTEPS; ++ks) {
-            const uint32_t b_hi = smem_u32(smem + st * STAGE_BYTES) + 2 * ks * B_LBO;
-            db[st][ks][0] = make_desc(b_hi, B_LBO);
-            db[st][ks][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);
-          }
+        for (int st = 0; st < WST; ++st) {
+          const uint32_t b_hi = smem_u32(smem + st * STAGE_BYTES);
+          db[st][0] = make_desc(b_hi, B_LBO);
+          db[st][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);
+        }
         for (int g = 0; g < NGEMM; ++g) {
           const int b = g & 1;
           const uint32_t dacc = tmem_base + (uint32_t)(b ? TM_ACC1 : 0);
@@ -619,29 +597,13 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
             PDBG_T(t2);
             PDBG_ACC(0, t1 - t0); PDBG_ACC(1, t2 - t1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int kw = chunk_kw(KH, c);
             const uint32_t a_hi = tmem_base + (uint32_t)(TM_AHI + ACOLS * sa), a_lo = tmem_base + (uint32_t)(TM_ALO + ACOLS * sa);
 #pragma unroll
             for (int st = 0; st < WST; ++st) {
               if (st != (int)sw) continue;                   // compile-time stage index keeps the descriptors in registers
-              if constexpr (F16) {                           // one K = 16 step per chunk (tail chunk zero-padded)
-                (void)kw;
-                mma_split<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
-                mma_split<NCTA>(dacc, a_hi, db[st][0][1], 1);
-                mma_split<NCTA>(dacc, a_lo, db[st][0][0], 1);
-              } else if (kw == KCH) {
-                mma_split<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
-                mma_split<NCTA>(dacc, a_hi, db[st][0][1], 1);
-                mma_split<NCTA>(dacc, a_lo, db[st][0][0], 1);
-                mma_split<NCTA>(dacc, a_hi + 8, db[st][KSTEPS - 1][0], 1);
-                mma_split<NCTA>(dacc, a_hi + 8, db[st][KSTEPS - 1][1], 1);
-                mma_split<NCTA>(dacc, a_lo + 8, db[st][KSTEPS - 1][0], 1);
-              } else {                                       // tail chunk: one k-step, lo half right after hi
-                const uint64_t dbl = make_desc(smem_u32(smem + st * STAGE_BYTES) + (kw / 4) * B_LBO, B_LBO);
-                mma_split<NCTA>(dacc, a_hi, db[st][0][0], c != 0);
-                mma_split<NCTA>(dacc, a_hi, dbl, 1);
-                mma_split<NCTA>(dacc, a_lo, db[st][0][0], 1);
-              }
+              mma_split<NCTA>(dacc, a_hi, db[st][0], c != 0);  // Yhi.Whi + Yhi.Wlo + Ylo.Whi (the tail chunk is zero-padded)
+              mma_split<NCTA>(dacc, a_hi, db[st][1], 1);
+              mma_split<NCTA>(dacc, a_lo, db[st][0], 1);
             }
             mma_commit<NCTA>(w_empty + 8 * sw);
             mma_commit<NCTA>(a_empty + 8 * sa);
@@ -667,7 +629,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         for (int c = 0; c < NCH; ++c) {
           const uint32_t u = (uint32_t)(g * NCH + c), s = u % WST;
           if (u >= WST) ok = mbar_wait(w_empty + 8 * s, ((u / WST) - 1) & 1) && ok;       // chunk u-WST consumed
-          const uint32_t bytes = F16 ? (uint32_t)STAGE_BYTES : 2u * (chunk_kw(KH, c) / 4) * B_LBO;   // this CTA's half: hi then lo
+          const uint32_t bytes = (uint32_t)STAGE_BYTES;                                    // this CTA's half: hi then lo
           const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg[g]) +
                                      (size_t)c * Cfg<NCTA>::CHUNK_IMG_BYTES + (size_t)cta_rank * bytes;
           mbar_expect_tx(w_full + 8 * s, bytes);

@@ -1,17 +1,14 @@
 // tcgen05 building blocks of the whole-network fused actor kernel (tactor_pipe.cuh).
 //
 //   * a CTA owns 128 rows (8 environments of 16 nodes / 4 of 32) and all 208 (padded) output columns
-//   * X.W on the 5th-gen tensor cores: tcgen05.mma kind::tf32, M=128 N=208 K=8 per instruction, fp32
-//     accumulators in TMEM
-//   * float32-equivalent accuracy by the 3xTF32 split: x = hi + lo with hi = x truncated to 10 mantissa bits,
-//     X.W ~= Xhi.Whi + Xhi.Wlo + Xlo.Whi (three MMAs per k-step into the same accumulator)
+//   * X.W on the 5th-gen tensor cores: tcgen05.mma kind::f16, M=128 N=208 K=16 per instruction, fp32 accumulators in TMEM
+//   * float32-equivalent accuracy by the fp16 hi/lo split (three MMAs per k-step into the same accumulator)
 //   * the B operand (W) sits in shared memory in the canonical no-swizzle K-major layout (8-row x 16-byte core
-//     matrices): W is pre-split and pre-laid-out on the host so a K-chunk is ONE cp.async.bulk (TMA 1-D bulk
-//     copy, completion on an mbarrier)
+//     matrices): W is pre-scaled, pre-split and pre-laid-out on the host so a K-chunk is ONE cp.async.bulk (TMA 1-D
+//     bulk copy, completion on an mbarrier)
 //   * the A operand is generated and split on the fly by the generator threads and written straight into
-//     TENSOR MEMORY (tcgen05.st, lane = row, column = k): it never touches shared memory, whose bandwidth the
-//     tensor core's B reads, the TMA writes and the epilogue already compete for
-//   * epilogue: tcgen05.ld 32x32b -> shared memory tile -> block-diagonal adjacency product, bias, ReLU
+//     TENSOR MEMORY (tcgen05.st, lane = row, two k per column): it never touches shared memory, whose bandwidth the
+//     exchange tiles, the tensor core's B reads, the TMA writes and the epilogue already compete for
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,16 +16,13 @@
 namespace tactor {
 namespace tc {
 
-// Operand precision of the split product (both give float32-equivalent results):
-//   TACTOR_F16 = 1 (default)  x = hi + lo with hi = fp16(x), lo = fp16(x - hi): tcgen05.mma kind::f16, K = 16 per
-//                             instruction, half the operand bytes and twice the tensor rate of tf32.  fp16 and tf32
-//                             carry the same 11-bit significand; what fp16 lacks is range, so W is pre-scaled by a
-//                             power of two per layer (undone exactly in the epilogue) and |A.X| > 65504 is reported.
-//   TACTOR_F16 = 0            3xTF32: hi = x truncated to 10 mantissa bits, kind::tf32, K = 8 per instruction.
-#ifndef TACTOR_F16
-#define TACTOR_F16 1
-#endif
-constexpr bool F16 = TACTOR_F16 != 0;
+// Operand precision of the split product: x = hi + lo with hi = fp16(x), lo = fp16(x - hi), X.W ~= Xhi.Whi + Xhi.Wlo +
+// Xlo.Whi on tcgen05.mma kind::f16 (K = 16 per instruction).  fp16 carries the same 11-bit significand as tf32, so the
+// result is float32-equivalent like 3xTF32 (measured <= 6e-6 on the sigmoid outputs against the float64 oracle) at half
+// the operand bytes and twice the tensor rate (3xTF32 on kind::tf32 was the first formulation of this kernel: 0.388 ms
+// against 0.382 ms per forward with everything else equal).  What fp16 lacks is range: W is pre-scaled by a power of
+// two per layer (undone exactly in the epilogue) and |A.X| > 65504 is reported through tactor_status.
+constexpr bool F16 = true;
 constexpr int TCM = 128;             // rows per CTA
 constexpr int TCN = 208;             // padded output columns (UMMA N, multiple of 16)
 constexpr int KCH = 16;              // K elements per chunk (f16: one MMA k-step of 16; tf32: two of 8)
@@ -65,11 +59,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // D[tmem] (+)= A[tmem] . B[smem]: A is [128 lanes = rows][8 columns] of tensor memory (of each CTA of a pair): one k
 // per column for tf32 (K = 8), two packed fp16 per column, even k in the low half, for f16 (K = 16)
-#if TACTOR_F16
 #define TACTOR_MMA_KIND "kind::f16"
-#else
-#define TACTOR_MMA_KIND "kind::tf32"
-#endif
 template <int NCTA>
 __device__ __forceinline__ void mma_split(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
   if constexpr (NCTA == 1)

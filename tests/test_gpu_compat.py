@@ -154,3 +154,30 @@ def test_dropin_read_genes_matches_golden(mods, name):
         assert nrm(np.array(m.d).ravel(), g[name + "_d"][t]) <= 1e-9
         assert nrm(np.array([e.prop_yeield for e in m.elements]), g[name + "_ratio"][t]) <= 1e-9
         assert m.elements[0].area == gm.truss[m.elements[0].section_no][0] * 1e-4
+
+
+def test_dropin_savetxt_read_src_round_trip(mods, tmp_path):
+    """savetxt writes the reference's bytes (tests/golden/structure_text.npz, reset state) and read_src brings a saved
+    structure back onto a fresh model, which then analyses to the same displacements"""
+    GEN = mods[0]
+    g = load_golden("structure_text")
+    gm = quiet(GEN.gen_model, *ARGS["small_roof"])
+    p0 = os.path.join(tmp_path, "reset.txt")
+    gm.savetxt(p0)
+    assert open(p0, newline="").read() == str(g["small_roof_text"][0])
+    p1 = os.path.join(tmp_path, "stepped.txt")
+    with open(p1, "w", newline="") as f:
+        f.write(str(g["small_roof_text"][2]))
+    gm.read_src(p1)
+    m = gm.model
+    assert np.array_equal(np.array([float(n.coord[1]) for n in m.nodes], dtype=np.float32),
+                          g["small_roof_y"][2].astype(np.float32))
+    assert [e.section_no for e in m.elements] == g["small_roof_section"][2].tolist()
+    m.restore(); m.gen_all()
+    d1 = np.array(m.d).ravel().copy()
+    p2 = os.path.join(tmp_path, "again.txt")
+    gm.savetxt(p2)
+    gm2 = quiet(GEN.gen_model, *ARGS["small_roof"])
+    gm2.read_src(p2)
+    gm2.model.restore(); gm2.model.gen_all()
+    assert np.array_equal(np.array(gm2.model.d).ravel(), d1)
