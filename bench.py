@@ -346,6 +346,43 @@ def main():
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    # ---- e2e, resident state: what a batched driver does when the state tuple lives with the environment object (as it
+    # does inside the reference's own Game / gen_model objects): per step the host sends the coins and the Pareto-front
+    # graph and receives point + status; only the states it wants to archive would be fetched (not timed here).  Reported
+    # next to `e2e`, never instead of it.
+    e2e_res = None
+    if use_actor:
+        point_h = torch.empty(B, 4).pin_memory()
+        status_h = torch.empty(B, dtype=torch.int32).pin_memory()
+        coin_d = torch.empty(B, dtype=torch.uint8, device=dev)
+        x_p_d, A_p_d = torch.empty_like(x_p), torch.empty_like(A_p)
+
+        def resident_step():
+            coin_d.copy_(coin_host, non_blocking=True)
+            x_p_d.copy_(x_p_host, non_blocking=True)
+            A_p_d.copy_(A_p_host, non_blocking=True)
+            a_geo, a_topo = pol.act(env.x_n, env.A_n, env.A_s, env.A_n_ts, env.A_n_cs, x_p_d, A_p_d)
+            env.step(a_geo, a_topo, coin_d)
+            point_h.copy_(env.point, non_blocking=True)
+            status_h.copy_(env.status, non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the driver reads point / status before the next step
+        for _ in range(3):
+            resident_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            resident_step()
+        res_ms = (time.perf_counter() - t0) * 1e3 / ke
+        if world > 1:
+            t = torch.tensor([res_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res_ms = float(t.item())
+        e2e_res = {"value": B * world / (res_ms * 1e-3), "unit": UNIT, "ms_per_step": res_ms,
+                   "h2d_bytes_per_step": int(B + x_p_host.numel() * 4 + A_p_host.numel() * 4),
+                   "d2h_bytes_per_step": int(B * 16 + B * 4),
+                   "path": "state tuple resident in HBM (BatchedTrussEnv); per step: pinned coins + Pareto graph -> device, "
+                           "BatchedActor.act + BatchedTrussEnv.step, point + status -> pinned host, stream sync"}
     clocks = sampler.result()
 
     if rank == 0:
@@ -409,6 +446,7 @@ def main():
                                  n_cpu, "numpy actor + env-step" if use_actor else "env-step", args.family, t_cpu)},
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "path": e2e_path},
+            "e2e_resident_state": e2e_res,
             "gpu_launches": launches,
             "clocks": clocks,
             "status_nonzero_envs": status_bad,
