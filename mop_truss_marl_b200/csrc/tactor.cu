@@ -4,7 +4,7 @@
 // Two launches per forward:
 //   pareto_kernel        Pareto-front branch (gcn_l1_4 + GlobalSumPool) -> pooled [B,208]
 //   actor_pipe_kernel    everything else, one CTA per 128 rows, tcgen05 tensor cores (tactor_pipe.cuh)
-// and two elementwise launches for the noise of tactor_act.
+// (the OU noise of tactor_act is applied by the actor kernel where it writes its outputs).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -62,28 +62,6 @@ pareto_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, cons
   // the reference's stack-and-reshape scramble (x14b[b,n,h] = pooled[b,(n*200+h)/N]) is applied by the fused
   // kernel's operand generator, so only the pooled embedding is materialised
   for (int i = tid; i < LD; i += blockDim.x) pooled_out[(size_t)b * LD + i] = (i < HID) ? pooled[i] : 0.f;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// OU noise of act() (truss2D_RL.py:41-48, 341-350): x += theta*(mu-x)*1e-4 + sigma*n, n ~ N(0,1)
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-// seed_call != nullptr (CUDA-graph replay, tactor_act_dev): seed = seed_call[0], call index = seed_call[1] + call
-__global__ void ou_noise_kernel(float* __restrict__ a, size_t n, float mu, float theta, float sigma,
-                                uint64_t seed, uint64_t call, uint64_t stream_id, const uint64_t* __restrict__ seed_call) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (seed_call) { seed = seed_call[0]; call += seed_call[1]; }
-  const uint64_t h = mix64(mix64(seed ^ (call * 0xD1342543DE82EF95ull)) + stream_id * 0x632BE59BD9B4E019ull + i);
-  const float u1 = ((uint32_t)(h >> 32) + 1.0f) * 2.3283064365386963e-10f;    // (0, 1]
-  const float u2 = (uint32_t)h * 2.3283064365386963e-10f;
-  const float nrm = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
-  const float x = a[i];
-  a[i] = x + (theta * (mu - x) * 0.0001f + sigma * nrm);
 }
 
 }  // namespace tactor
@@ -204,8 +182,16 @@ cudaError_t upload_weights(tactor_handle_s* h, const tactor_weights* w) {
   return e;
 }
 
+struct Noise {
+  int on = 0;
+  float mu = 0.f, theta = 0.f, sigma = 0.f;
+  uint64_t seed = 0, call = 0;
+  const uint64_t* seed_call = nullptr;
+};
+
 template <int NODES>
-cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, float* geo, float* topo, cudaStream_t st) {
+cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, float* geo, float* topo, const Noise& nz,
+                        cudaStream_t st) {
   using namespace tactor;
   const int M = B * NODES;
   float* pooled = h->pooled;
@@ -216,6 +202,7 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   for (int g = 0; g < tc::fused::NGEMM; ++g) { p.wimg[g] = h->d_wimg[4 + g]; p.bias[g] = h->d_b[4 + g]; p.wscale_inv[g] = h->wscale_inv[4 + g]; }
   p.w_head[0] = h->d_w[11]; p.w_head[1] = h->d_w[12]; p.b_head[0] = h->d_b[11]; p.b_head[1] = h->d_b[12];
   p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error;
+  p.noise = nz.on; p.mu = nz.mu; p.theta = nz.theta; p.sigma = nz.sigma; p.seed = nz.seed; p.call = nz.call; p.seed_call = nz.seed_call;
   cudaError_t e = (h->ncta == 2) ? launch_pipe<NODES, 2>(p, M, h->sms, st) : launch_pipe<NODES, 1>(p, M, h->sms, st);
   h->launches.fetch_add(2);
   return e != cudaSuccess ? e : cudaGetLastError();
@@ -290,41 +277,41 @@ static int check_inputs(tactor_handle_t h, int B, const tactor_inputs* in, float
   return TFEM_OK;
 }
 
-int tactor_forward(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, void* stream) {
+static int forward_impl(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, const Noise& nz,
+                        void* stream) {
   if (int rc = check_inputs(h, B, in, geo, topo)) return rc;
   if (B == 0) return TFEM_OK;
   Guard g(h->device);
-  cudaError_t e = (h->nodes == 16) ? run_forward<16>(h, B, in, geo, topo, (cudaStream_t)stream)
-                                   : run_forward<32>(h, B, in, geo, topo, (cudaStream_t)stream);
+  cudaError_t e = (h->nodes == 16) ? run_forward<16>(h, B, in, geo, topo, nz, (cudaStream_t)stream)
+                                   : run_forward<32>(h, B, in, geo, topo, nz, (cudaStream_t)stream);
   if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("actor forward: ") + cudaGetErrorString(e));
   return TFEM_OK;
 }
 
-static int ou_noise(tactor_handle_t h, int B, float* geo, float* topo, float mu, float theta, float sigma, uint64_t seed,
-                    uint64_t call, const uint64_t* seed_call_dev, void* stream) {
-  if (B == 0 || (sigma == 0.f && theta == 0.f)) return TFEM_OK;
-  Guard g(h->device);
-  const size_t ng = (size_t)B * h->nodes * 2, nt = (size_t)B * h->nodes * 3;
-  tactor::ou_noise_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, (cudaStream_t)stream>>>(geo, ng, mu, theta, sigma, seed, call, 1, seed_call_dev);
-  tactor::ou_noise_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(topo, nt, mu, theta, sigma, seed, call, 2, seed_call_dev);
-  h->launches.fetch_add(2);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("ou noise: ") + cudaGetErrorString(e));
-  return TFEM_OK;
+int tactor_forward(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, void* stream) {
+  return forward_impl(h, B, in, geo, topo, Noise{}, stream);
 }
 
+// the OU noise is applied by the actor kernel itself where it writes the sigmoid outputs (no extra launch)
 int tactor_act(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, float mu, float theta,
                float sigma, uint64_t seed, void* stream) {
-  if (int rc = tactor_forward(h, B, in, geo, topo, stream)) return rc;
-  if (B == 0 || (sigma == 0.f && theta == 0.f)) return TFEM_OK;
-  return ou_noise(h, B, geo, topo, mu, theta, sigma, seed, h->calls++, nullptr, stream);
+  Noise nz;
+  if (h && B > 0 && !(sigma == 0.f && theta == 0.f)) {
+    nz.on = 1; nz.mu = mu; nz.theta = theta; nz.sigma = sigma; nz.seed = seed; nz.call = h->calls;
+  }
+  const int rc = forward_impl(h, B, in, geo, topo, nz, stream);
+  if (rc == TFEM_OK && nz.on) h->calls++;
+  return rc;
 }
 
 int tactor_act_dev(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, float mu, float theta,
                    float sigma, const uint64_t* seed_call_dev, uint32_t call_offset, void* stream) {
   if (!seed_call_dev) return afail(TFEM_ERR_ARG, "null argument");
-  if (int rc = tactor_forward(h, B, in, geo, topo, stream)) return rc;
-  return ou_noise(h, B, geo, topo, mu, theta, sigma, 0, call_offset, seed_call_dev, stream);
+  Noise nz;
+  if (B > 0 && !(sigma == 0.f && theta == 0.f)) {
+    nz.on = 1; nz.mu = mu; nz.theta = theta; nz.sigma = sigma; nz.call = call_offset; nz.seed_call = seed_call_dev;
+  }
+  return forward_impl(h, B, in, geo, topo, nz, stream);
 }
 
 uint64_t tactor_reserve_calls(tactor_handle_t h, uint32_t n, int64_t replayed_launches) {

@@ -558,7 +558,13 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         const int row = row0 + r;
         if (row < M) {
           float* dst = (hd == 0 ? P.geo : P.topo) + (size_t)row * nout;
-          for (int t = 0; t < nout; ++t) dst[t] = 1.f / (1.f + expf(-o[t]));
+          uint64_t seed = P.seed, call = P.call;
+          if (P.noise && P.seed_call) { seed = P.seed_call[0]; call += P.seed_call[1]; }
+          for (int t = 0; t < nout; ++t) {
+            float v = 1.f / (1.f + expf(-o[t]));
+            if (P.noise) v = ou_step(v, P.mu, P.theta, P.sigma, seed, call, (uint64_t)(hd + 1), (uint64_t)row * nout + t);
+            dst[t] = v;
+          }
         }
       }
       PDBG_T(t3);

@@ -155,6 +155,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// counter-based standard normal for the OU noise: element i of tensor `stream_id` (1 = geo, 2 = topo) of call `call`
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float ou_step(float x, float mu, float theta, float sigma, uint64_t seed, uint64_t call,
+                                         uint64_t stream_id, uint64_t i) {
+  const uint64_t h = mix64(mix64(seed ^ (call * 0xD1342543DE82EF95ull)) + stream_id * 0x632BE59BD9B4E019ull + i);
+  const float u1 = ((uint32_t)(h >> 32) + 1.0f) * 2.3283064365386963e-10f;    // (0, 1]
+  const float u2 = (uint32_t)h * 2.3283064365386963e-10f;
+  const float nrm = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+  return x + (theta * (mu - x) * 0.0001f + sigma * nrm);
+}
+
 // =========================================================================================================
 // Kernel parameters of the whole-network fused actor kernel (tactor_pipe.cuh).
 namespace fused {
@@ -179,6 +195,12 @@ struct Params {
   float* geo;             // [B,N,2]
   float* topo;            // [B,N,3]
   int M;                  // B*N
+  // OU noise of act() (truss2D_RL.py:41-48, 341-350), applied where the sigmoid outputs are written: noise != 0 adds
+  // theta*(mu-x)*1e-4 + sigma*n(seed, call, tensor, element); seed_call != nullptr: seed = seed_call[0], call += seed_call[1]
+  int noise;
+  float mu, theta, sigma;
+  uint64_t seed, call;
+  const uint64_t* seed_call;
   int split_from;         // first CTA that owns a piece of a tile (tiles of the last partial wave), grid size if none
   int split_f;            // pieces per split tile: 1, 2 or 4
   int* error_flag;

@@ -80,9 +80,9 @@ def test_graph_replay_equals_direct_enqueue(family, B, pieces, monkeypatch):
         for k in STATE_OUT + ("a_geo", "a_topo"):
             assert torch.equal(bufs[0][1 - (it & 1)][k], bufs[1][1 - (it & 1)][k]), (it, k)
         counts.append((envs[0].launch_count(), pols[0].launch_count(), envs[1].launch_count(), pols[1].launch_count()))
-    # both arms launched the same number of kernels every step (1 env-step + 4 actor kernels per piece)
+    # both arms launched the same number of kernels every step (1 env-step + 2 actor kernels per piece: the OU noise is applied inside the actor kernel)
     assert counts[-1][0] == counts[-1][2] and counts[-1][1] == counts[-1][3]
     per_step = [(b[0] - a[0], b[1] - a[1]) for a, b in zip(counts, counts[1:])]
-    assert all(p == (pieces, 4 * pieces) for p in per_step), per_step
+    assert all(p == (pieces, 2 * pieces) for p in per_step), per_step
     assert int(bufs[0][0]["status"].abs().max()) == 0
     pols[0].check()
