@@ -75,7 +75,9 @@ uint64_t tactor_reserve_calls(tactor_handle_t h, uint32_t n, int64_t replayed_la
 int64_t tactor_launch_count(tactor_handle_t h);
 
 /* Synchronises the device and returns 0, or TFEM_ERR_CUDA if a kernel of this handle reported a
- * timed-out mbarrier wait (the waits are bounded so that a programming error cannot hang the GPU). */
+ * timed-out mbarrier wait (the waits are bounded so that a programming error cannot hang the GPU), or
+ * TFEM_ERR_UNSUPPORTED if an activation left the fp16 range of the split tensor-core product (|A.X| > 65504 or a NaN
+ * input; the outputs of that forward are not valid).  A reported condition is cleared. */
 int tactor_status(tactor_handle_t h);
 
 #ifdef __cplusplus

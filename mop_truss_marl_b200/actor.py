@@ -130,5 +130,6 @@ class BatchedActor:
         return int(_lib.tactor_launch_count(self._h))
 
     def check(self) -> None:
-        """synchronise and raise if a kernel reported a timed-out barrier wait"""
+        """synchronise and raise if a kernel reported a timed-out barrier wait or an activation outside the fp16 range
+        of the split tensor-core product"""
         _check(_lib.tactor_status(self._h))

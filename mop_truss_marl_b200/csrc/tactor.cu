@@ -30,39 +30,73 @@ constexpr int KC = 16;               // layer-1 / head kernels are stored with K
 // ---------------------------------------------------------------------------------------------------------
 // Pareto branch (truss2D_RL.py:86-88): x14 = relu(A_p (x_p W14) + b14), summed over the valid Pareto rows
 // (GlobalSumPool).  One CTA per environment.
+// One CTA per environment: T = x_p W14 [P,200] once, then U = A_p T as a register-tiled product -- thread (p-slice of 13
+// rows, 4 feature columns) keeps 13 x 4 accumulators, reads one float4 of T and 13 broadcast entries of A_p per q -- and
+// pooled[h] = sum over the valid rows of relu(U[p][h] + b[h]).
+constexpr int PSL = 13;                   // Pareto rows per thread slice (4 slices cover P <= 52)
 template <int NODES>
 __global__ void __launch_bounds__(256)
 pareto_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
               int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out,
               int B) {
-  __shared__ float xs[50 * 4];
-  __shared__ float as[50 * 50];
-  __shared__ float pooled[HID];
+  extern __shared__ __align__(16) float psm[];
+  float* ts = psm;                        // [P][LD]   x_p W14
+  float* red = ts + 50 * LD;              // [4][LD]   per-slice partial sums
+  float* as = red + 4 * LD;               // [P][P]
+  float* xs = as + 50 * 50;               // [P][4]
   const int b = blockIdx.x, tid = threadIdx.x;
   if (b >= B) return;
   for (int i = tid; i < P * 4; i += blockDim.x) xs[i] = x_p[(size_t)b * P * 4 + i];
   for (int i = tid; i < P * P; i += blockDim.x) as[i] = A_p[(size_t)b * P * P + i];
   __syncthreads();
+  for (int idx = tid; idx < P * (LD / 4); idx += blockDim.x) {
+    const int q = idx / (LD / 4), h4 = idx % (LD / 4);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W14 + 0 * LD) + h4), w1 = __ldg(reinterpret_cast<const float4*>(W14 + 1 * LD) + h4);
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(W14 + 2 * LD) + h4), w3 = __ldg(reinterpret_cast<const float4*>(W14 + 3 * LD) + h4);
+    const float x0 = xs[q * 4], x1 = xs[q * 4 + 1], x2 = xs[q * 4 + 2], x3 = xs[q * 4 + 3];
+    float4 t;                             // same operation order as the scalar form: fma(x3,w3, fma(x2,w2, fma(x1,w1, x0*w0)))
+    t.x = fmaf(x3, w3.x, fmaf(x2, w2.x, fmaf(x1, w1.x, x0 * w0.x)));
+    t.y = fmaf(x3, w3.y, fmaf(x2, w2.y, fmaf(x1, w1.y, x0 * w0.y)));
+    t.z = fmaf(x3, w3.z, fmaf(x2, w2.z, fmaf(x1, w1.z, x0 * w0.z)));
+    t.w = fmaf(x3, w3.w, fmaf(x2, w2.w, fmaf(x1, w1.w, x0 * w0.w)));
+    reinterpret_cast<float4*>(ts + q * LD)[h4] = t;
+  }
+  __syncthreads();
   const int valid = n_pf ? min(max(n_pf[b], 0), P) : P;
-  if (tid < HID) {
-    const float w0 = W14[0 * LD + tid], w1 = W14[1 * LD + tid], w2 = W14[2 * LD + tid], w3 = W14[3 * LD + tid];
-    const float bias = b14[tid];
-    float sum = 0.f;
-    for (int p = 0; p < valid; ++p) {
-      float u = 0.f;
-      for (int q = 0; q < P; ++q) {
-        const float t = fmaf(xs[q * 4 + 3], w3, fmaf(xs[q * 4 + 2], w2, fmaf(xs[q * 4 + 1], w1, xs[q * 4] * w0)));
-        u = fmaf(as[p * P + q], t, u);
+  const int ps = tid >> 6, h4 = tid & 63;                    // slice = two warps; lanes 52..63 of a slice idle
+  if (h4 < LD / 4) {
+    float4 acc[PSL];
+#pragma unroll
+    for (int i = 0; i < PSL; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int p0 = ps * PSL;
+    for (int q = 0; q < P; ++q) {
+      const float4 t = reinterpret_cast<const float4*>(ts + q * LD)[h4];
+#pragma unroll
+      for (int i = 0; i < PSL; ++i) {
+        if (p0 + i < valid) {                                // warp-uniform
+          const float a = as[(p0 + i) * P + q];
+          acc[i].x = fmaf(a, t.x, acc[i].x); acc[i].y = fmaf(a, t.y, acc[i].y);
+          acc[i].z = fmaf(a, t.z, acc[i].z); acc[i].w = fmaf(a, t.w, acc[i].w);
+        }
       }
-      sum += fmaxf(u + bias, 0.f);
     }
-    pooled[tid] = sum;
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(b14) + h4);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < PSL; ++i) {
+      if (p0 + i < valid) {
+        sum.x += fmaxf(acc[i].x + bias.x, 0.f); sum.y += fmaxf(acc[i].y + bias.y, 0.f);
+        sum.z += fmaxf(acc[i].z + bias.z, 0.f); sum.w += fmaxf(acc[i].w + bias.w, 0.f);
+      }
+    }
+    reinterpret_cast<float4*>(red + ps * LD)[h4] = sum;
   }
   __syncthreads();
   // the reference's stack-and-reshape scramble (x14b[b,n,h] = pooled[b,(n*200+h)/N]) is applied by the fused
   // kernel's operand generator, so only the pooled embedding is materialised
-  for (int i = tid; i < LD; i += blockDim.x) pooled_out[(size_t)b * LD + i] = (i < HID) ? pooled[i] : 0.f;
+  if (tid < LD) pooled_out[(size_t)b * LD + tid] = (tid < HID) ? ((red[tid] + red[LD + tid]) + (red[2 * LD + tid] + red[3 * LD + tid])) : 0.f;
 }
+constexpr int PARETO_SMEM = (50 * LD + 4 * LD + 50 * 50 + 50 * 4) * 4;
 
 }  // namespace tactor
 
@@ -195,7 +229,7 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   using namespace tactor;
   const int M = B * NODES;
   float* pooled = h->pooled;
-  pareto_kernel<NODES><<<B, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
+  pareto_kernel<NODES><<<B, 256, PARETO_SMEM, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
   tc::fused::Params p{};
   p.x_n = in->x_n; p.A_n = in->A_n; p.A_s = in->A_s; p.A_ts = in->A_n_ts; p.A_cs = in->A_n_cs; p.pooled = pooled;
   for (int k = 0; k < 3; ++k) { p.w1[k] = h->d_w[k]; p.b1[k] = h->d_b[k]; }
@@ -237,6 +271,9 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
     if (nodes == 16) e = (h->ncta == 2) ? set_pipe_smem<16, 2>() : set_pipe_smem<16, 1>();
     else e = (h->ncta == 2) ? set_pipe_smem<32, 2>() : set_pipe_smem<32, 1>();
   }
+  if (e == cudaSuccess)
+    e = (nodes == 16) ? cudaFuncSetAttribute(tactor::pareto_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM)
+                      : cudaFuncSetAttribute(tactor::pareto_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM);
   if (e == cudaSuccess) e = cudaMalloc(&h->pooled, (size_t)max_batch * tactor::LD * 4);
   if (e != cudaSuccess) { tactor_destroy(h); return afail(TFEM_ERR_CUDA, std::string("actor setup: ") + cudaGetErrorString(e)); }
   *out = h;
@@ -332,6 +369,7 @@ int tactor_status(tactor_handle_t h) {
   int flag = 0;
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(&flag, h->d_error, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && flag) e = cudaMemset(h->d_error, 0, 4);          // reported once: later forwards are judged on their own
   if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("actor status: ") + cudaGetErrorString(e));
   if (flag & 1) return afail(TFEM_ERR_CUDA, "an mbarrier wait timed out inside actor_pipe_kernel");
   if (flag & 2) return afail(TFEM_ERR_UNSUPPORTED, "an activation left the fp16 range of the split tensor-core product (|A.X| > 65504 or NaN input)");

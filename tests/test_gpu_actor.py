@@ -189,3 +189,24 @@ def test_cta_pair_build_matches_single_cta(nodes, B, monkeypatch):
         pol.check()
         outs.append((geo.clone(), topo.clone()))
     assert float((outs[0][0] - outs[1][0]).abs().max()) <= 1e-6 and float((outs[0][1] - outs[1][1]).abs().max()) <= 1e-6
+
+
+def test_fp16_range_overflow_is_reported():
+    """the split tensor-core product carries activations as fp16 hi + lo: an activation beyond 65504 cannot be
+    represented and must be reported (tactor_status -> TfemError), never silently returned"""
+    from mop_truss_marl_b200 import actor, capi, tf_checkpoint
+    nodes, B = 16, 16
+    w = tf_checkpoint.random_actor_weights(seed=4)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    r = lambda *s: torch.rand(*s, device="cuda", generator=g)   # noqa: E731
+    sc = 1.0 / nodes
+    adj = (r(nodes, nodes) * sc, r(B, nodes, nodes) * sc, r(B, nodes, nodes) * sc, r(B, nodes, nodes) * sc)
+    pol = actor.BatchedActor(w, nodes, B)
+    pol.forward(r(B, nodes, 13), *adj, r(B, 1, 4), r(B, 1, 1))
+    torch.cuda.synchronize()
+    pol.check()                                                  # ordinary inputs: fine
+    pol2 = actor.BatchedActor(w, nodes, B)
+    pol2.forward(r(B, nodes, 13) * 3e6, *adj, r(B, 1, 4), r(B, 1, 1))
+    torch.cuda.synchronize()
+    with pytest.raises(capi.TfemError, match="fp16 range"):
+        pol2.check()
