@@ -123,6 +123,19 @@ __device__ __forceinline__ float norm_f32(float v, float mn, float mx) {
   return __fdiv_rn(__fsub_rn(v, mn), __fadd_rn(__fsub_rn(mx, mn), 1e-6f));
 }
 
+// 1/a for the 4*NX sequential pivots of the factorisation: MUFU.RCP64H seed (relative error ~2^-20) and two Newton steps
+// (-> 2^-80, i.e. full double precision, at worst 1 ulp from the correctly rounded quotient).  The compiler's own IEEE
+// division is a 20-instruction sequence with a dependent chain twice as long and a slow-path call; pivots here are normal
+// positive numbers, and a zero / negative / non-finite pivot still yields a value the SPD check flags.
+__device__ __forceinline__ double pivot_rcp(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  return fma(x, e, x);
+}
+
 template <int NX>
 struct Dims {
   static constexpr int N = 2 * NX;
@@ -423,7 +436,7 @@ tfem_step_kernel(const StepArgs args) {
       double* col = Kb;
 #pragma unroll 4
       for (int j = 0; j < NI; ++j, col += BAND) {
-        const double inv = 1.0 / col[0];
+        const double inv = pivot_rcp(col[0]);
         const double la = col[ta] * inv;                      // L[j+a][j]
         const double upd = fma(-la, col[tb], col[tgt_off]);
         double zl = 0.0;
