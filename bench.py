@@ -137,6 +137,8 @@ def run_reference_arm(args, rank, world):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     per_step_seconds = max(0.25, min(10.0, 120.0 / max(1, args.steps + args.warmup)))   # whole run ~2 minutes
+    if args.ref_step_seconds:
+        per_step_seconds = float(args.ref_step_seconds)
     with_actor = not args.no_actor
     ctx = mp.get_context("fork")
     rates = []
@@ -189,6 +191,7 @@ def main():
     ap.add_argument("--family", default="small_bridge")
     ap.add_argument("--batch", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-step-seconds", type=float, default=0.0, help="--impl reference: CPU seconds per bench step (default: sized for a ~2 minute run)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--e2e-pieces", type=int, default=2, help="pieces the batch is cut into on the end-to-end path")
     ap.add_argument("--no-actor", action="store_true", help="drive the env with resident uniform actions instead of the actor")

@@ -40,10 +40,10 @@ pareto_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, cons
               int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out,
               int B) {
   extern __shared__ __align__(16) float psm[];
-  float* ts = psm;                        // [P][LD]   x_p W14
-  float* red = ts + 50 * LD;              // [4][LD]   per-slice partial sums
+  float* ts = psm;                        // [P][LD]   x_p W14          (the launch sizes the buffer for this P: a
+  float* red = ts + P * LD;               // [4][LD]   per-slice sums     small front keeps many CTAs per SM)
   float* as = red + 4 * LD;               // [P][P]
-  float* xs = as + 50 * 50;               // [P][4]
+  float* xs = as + P * P;                 // [P][4]
   const int b = blockIdx.x, tid = threadIdx.x;
   if (b >= B) return;
   for (int i = tid; i < P * 4; i += blockDim.x) xs[i] = x_p[(size_t)b * P * 4 + i];
@@ -96,7 +96,44 @@ pareto_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, cons
   // kernel's operand generator, so only the pooled embedding is materialised
   if (tid < LD) pooled_out[(size_t)b * LD + tid] = (tid < HID) ? ((red[tid] + red[LD + tid]) + (red[2 * LD + tid] + red[3 * LD + tid])) : 0.f;
 }
-constexpr int PARETO_SMEM = (50 * LD + 4 * LD + 50 * 50 + 50 * 4) * 4;
+// Small fronts (P <= PSMALL; the reset-time graph has P = 1): one thread per feature column, everything recomputed in
+// registers -- no barrier-separated stages, a few registers, many CTAs per SM (the tiled kernel above needs 3 barriers and
+// ~80 registers, which costs more than it saves until the P^2 product dominates).
+constexpr int PSMALL = 16;
+template <int NODES>
+__global__ void __launch_bounds__(256)
+pareto_small_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
+                    int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out,
+                    int B) {
+  __shared__ float xs[PSMALL * 4];
+  __shared__ float as[PSMALL * PSMALL];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (b >= B) return;
+  if (tid < P * 4) xs[tid] = x_p[(size_t)b * P * 4 + tid];
+  if (tid < P * P) as[tid] = A_p[(size_t)b * P * P + tid];
+  __syncthreads();
+  const int valid = n_pf ? min(max(n_pf[b], 0), P) : P;
+  float sum = 0.f;
+  if (tid < HID) {
+    const float w0 = W14[0 * LD + tid], w1 = W14[1 * LD + tid], w2 = W14[2 * LD + tid], w3 = W14[3 * LD + tid];
+    const float bias = b14[tid];
+    float t[PSMALL];
+#pragma unroll
+    for (int q = 0; q < PSMALL; ++q)
+      t[q] = (q < P) ? fmaf(xs[q * 4 + 3], w3, fmaf(xs[q * 4 + 2], w2, fmaf(xs[q * 4 + 1], w1, xs[q * 4] * w0))) : 0.f;
+    for (int p = 0; p < valid; ++p) {
+      float u = 0.f;
+#pragma unroll
+      for (int q = 0; q < PSMALL; ++q)
+        if (q < P) u = fmaf(as[p * P + q], t[q], u);
+      sum += fmaxf(u + bias, 0.f);
+    }
+  }
+  if (tid < LD) pooled_out[(size_t)b * LD + tid] = (tid < HID) ? sum : 0.f;
+}
+
+constexpr int pareto_smem(int P) { return (P * LD + 4 * LD + P * P + P * 4) * 4; }
+constexpr int PARETO_SMEM = pareto_smem(50);
 
 }  // namespace tactor
 
@@ -229,7 +266,10 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   using namespace tactor;
   const int M = B * NODES;
   float* pooled = h->pooled;
-  pareto_kernel<NODES><<<B, 256, PARETO_SMEM, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
+  if (in->P <= PSMALL)
+    pareto_small_kernel<NODES><<<B, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
+  else
+    pareto_kernel<NODES><<<B, 256, pareto_smem(in->P), st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
   tc::fused::Params p{};
   p.x_n = in->x_n; p.A_n = in->A_n; p.A_s = in->A_s; p.A_ts = in->A_n_ts; p.A_cs = in->A_n_cs; p.pooled = pooled;
   for (int k = 0; k < 3; ++k) { p.w1[k] = h->d_w[k]; p.b1[k] = h->d_b[k]; }

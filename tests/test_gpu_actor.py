@@ -25,7 +25,7 @@ def random_inputs(rng, B, N, P):
     return x_n, A_n, A_s, A_ts, A_cs, x_p, A_p
 
 
-@pytest.mark.parametrize("N,B,P", [(16, 37, 1), (16, 64, 7), (32, 9, 50), (32, 32, 3)])
+@pytest.mark.parametrize("N,B,P", [(16, 37, 1), (16, 64, 7), (32, 9, 50), (32, 32, 3), (16, 21, 8), (16, 21, 9), (16, 12, 27), (32, 10, 16), (16, 10, 17)])
 def test_forward_matches_float64_oracle(N, B, P):
     from mop_truss_marl_b200 import actor, tf_checkpoint
     from oracle.actor_oracle import actor_forward
