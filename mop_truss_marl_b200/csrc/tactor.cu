@@ -117,16 +117,21 @@ pareto_small_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p
   if (tid < HID) {
     const float w0 = W14[0 * LD + tid], w1 = W14[1 * LD + tid], w2 = W14[2 * LD + tid], w3 = W14[3 * LD + tid];
     const float bias = b14[tid];
-    float t[PSMALL];
-#pragma unroll
-    for (int q = 0; q < PSMALL; ++q)
-      t[q] = (q < P) ? fmaf(xs[q * 4 + 3], w3, fmaf(xs[q * 4 + 2], w2, fmaf(xs[q * 4 + 1], w1, xs[q * 4] * w0))) : 0.f;
-    for (int p = 0; p < valid; ++p) {
-      float u = 0.f;
+    if (P == 1) {                         // the reset-time graph (truss2D_ENV.py:348-351): one row, one entry
+      const float t0 = fmaf(xs[3], w3, fmaf(xs[2], w2, fmaf(xs[1], w1, xs[0] * w0)));
+      if (valid > 0) sum = fmaxf(fmaf(as[0], t0, 0.f) + bias, 0.f);
+    } else {
+      float t[PSMALL];
 #pragma unroll
       for (int q = 0; q < PSMALL; ++q)
-        if (q < P) u = fmaf(as[p * P + q], t[q], u);
-      sum += fmaxf(u + bias, 0.f);
+        t[q] = (q < P) ? fmaf(xs[q * 4 + 3], w3, fmaf(xs[q * 4 + 2], w2, fmaf(xs[q * 4 + 1], w1, xs[q * 4] * w0))) : 0.f;
+      for (int p = 0; p < valid; ++p) {
+        float u = 0.f;
+#pragma unroll
+        for (int q = 0; q < PSMALL; ++q)
+          if (q < P) u = fmaf(as[p * P + q], t[q], u);
+        sum += fmaxf(u + bias, 0.f);
+      }
     }
   }
   if (tid < LD) pooled_out[(size_t)b * LD + tid] = (tid < HID) ? sum : 0.f;

@@ -330,3 +330,52 @@ def test_empty_batch_and_bad_args(envmod):
     sin, sout = capi.StepIn(), capi.StepOut()
     assert capi.lib.tfem_step(env.handle.ptr, 0, C.byref(sin), C.byref(sout), None) == 0   # B = 0 is a no-op
     assert capi.lib.tfem_step(env.handle.ptr, 4, C.byref(sin), C.byref(sout), None) == -1  # missing inputs
+
+
+@pytest.mark.parametrize("name,B", [("small_bridge", 4096), ("small_roof", 16384), ("large_bridge", 8192), ("large_roof", 4096)])
+def test_full_batch_against_c_oracle(envmod, name, B):
+    """EVERY environment of a BASELINE.json-sized batch against the C restatement of the oracle (oracle/truss_oracle.c,
+    pinned by tests/test_c_oracle.py): three env steps from reset, each step's inputs taken from the GPU state"""
+    from oracle.c_oracle import COracle
+    from util import ulp_diff
+    co = COracle(name)
+    env = make_env(envmod, name, B)
+    env.reset()
+    N, E, nx = env.N, env.E, env.N // 2
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for s in range(3):
+        scale = (1.3, 0.6, 0.25)[s]                                   # out-of-range, ordinary and small actions
+        a_geo = (torch.rand(B, N, 2, device="cuda", generator=g) * scale - 0.05).contiguous()
+        a_topo = (torch.rand(B, N, 3, device="cuda", generator=g) * 1.2 - 0.1).contiguous()
+        coin = (torch.rand(B, device="cuda", generator=g) >= 0.5).to(torch.uint8)
+        set_node, set_elem, stale = cpu(env.nN_x_n).copy(), cpu(env.nN_x_e).copy(), cpu(env.move_range).copy()
+        ag, at = cpu(a_geo).copy(), cpu(a_topo).copy()
+        want = co.step(set_node, set_elem, ag, at, cpu(coin), stale)
+        env.step(a_geo, a_topo, coin)
+        torch.cuda.synchronize()
+        tag = "%s step %d" % (name, s)
+        assert int(env.status.abs().max()) == 0 and int(want["status"].max()) == 0, tag
+        # bit-exact: clipped actions, heights (float64 bit patterns), weak flags, sections, move range
+        assert np.array_equal(cpu(a_geo), ag) and np.array_equal(cpu(a_topo), at), tag + " clip"
+        assert np.array_equal(cpu(env.y), want["y"]), tag + " y"
+        assert np.array_equal(cpu(env.y_weak), want["weak"]), tag + " weak"
+        assert np.array_equal(cpu(env.nN_x_e)[:, :, 0].astype(np.int32), want["section"]), tag + " section"
+        assert np.array_equal(cpu(env.move_range), want["move_range"]), tag + " move range"
+        # FP64: 1e-9 normwise per environment where the truss is at least 1 m deep everywhere (cond(K) < 1e6); the
+        # d_min-deep ones (cond up to ~1e8) get eps * cond
+        depth = (want["y"][:, nx:] - want["y"][:, :nx]).min(axis=1)
+        deep = depth >= 1.0
+        assert deep.sum() > B // 50, tag
+        for k in ("d", "axial", "ratio"):
+            got = cpu(getattr(env, k))
+            err = np.abs(got - want[k]).max(axis=1) / np.abs(want[k]).max(axis=1)
+            assert err[deep].max() <= FP64_TOL, "%s %s %.3e" % (tag, k, err[deep].max())
+            assert err.max() <= 1e-6, "%s %s %.3e" % (tag, k, err.max())
+        errU = np.abs(cpu(env.U) - want["U"]) / np.abs(want["U"])
+        assert errU[deep].max() <= FP64_TOL and errU.max() <= 1e-6, tag + " U"
+        # flags: compression flag wherever the member force is not a rounding-level zero
+        ax = want["axial"]
+        clear = np.abs(ax) > 1e-7 * np.abs(ax).max(axis=1, keepdims=True)
+        assert np.array_equal(cpu(env.nN_x_e)[:, :, 4].astype(np.int32)[clear], want["iscompress"][clear]), tag + " iscompress"
+        # objective point: <= 2 ulp(float32)
+        assert ulp_diff(cpu(env.point), want["point"]).max() <= 2, tag + " point"
