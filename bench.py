@@ -122,6 +122,33 @@ def oracle_steps_per_sec(family, seconds, seed=0, with_actor=False):
     return n, time.perf_counter() - t0
 
 
+def c_oracle_env_steps_per_sec(family, seconds=2.0, B=2048, seed=0):
+    """the compiled CPU port (oracle/truss_oracle.c, OpenMP on every host core) stepping B environments in a closed
+    loop with i.i.d. uniform actions: transition + FEM + objectives (it does not build the observation tensors, so it
+    does LESS work per env-step than the GPU path or the reference).  Returns (env_steps, elapsed, cores)."""
+    from oracle.c_oracle import COracle
+    co = COracle(family)
+    N, E = co.N, co.E
+    rng = np.random.RandomState(seed)
+    st = co.py.reset()
+    set_node = np.repeat(st["nN_x_n"][None], B, axis=0).astype(np.float32)
+    set_elem = np.repeat(st["nN_x_e"][None], B, axis=0).astype(np.float32)
+    stale = np.repeat(np.stack([st["max_up"], st["max_down"]], axis=-1)[None], B, axis=0).astype(np.float32)
+    acts = [(rng.rand(B, N, 2).astype(np.float32), rng.rand(B, N, 3).astype(np.float32),
+             (rng.rand(B) >= 0.5).astype(np.uint8)) for _ in range(4)]
+    n, t0 = 0, time.perf_counter()
+    while True:
+        a_geo, a_topo, coin = acts[n % 4]
+        out = co.step(set_node, set_elem, a_geo.copy(), a_topo.copy(), coin, stale)
+        set_node[:, :, 1] = out["y"].astype(np.float32)
+        set_elem[:, :, 0] = out["section"]
+        stale = out["move_range"]
+        n += 1
+        if n >= 2 and time.perf_counter() - t0 >= seconds:
+            break
+    return n * B, time.perf_counter() - t0, co.threads
+
+
 def _oracle_worker(args):
     family, seconds, seed, with_actor = args
     import warnings
@@ -431,6 +458,13 @@ def main():
         else:
             roofline = roof_fem
         n_cpu, t_cpu = oracle_steps_per_sec(args.family, args.cpu_seconds, with_actor=use_actor)
+        try:
+            nc, tc, cores_c = c_oracle_env_steps_per_sec(args.family, seconds=min(3.0, max(0.3, args.cpu_seconds / 4)))
+            c_line = {"value": nc / tc, "unit": UNIT, "cores": cores_c, "kind": "port",
+                      "sample": "%d env-steps of %s in %.2f s: oracle/truss_oracle.c (C, OpenMP), FEM env-step only "
+                                "(transition + solve + objectives, no observation tensors, no actor)" % (nc, args.family, tc)}
+        except Exception as exc:                          # no gcc on the box: the Python port above is the baseline
+            c_line = {"unavailable": str(exc)[:200]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -447,6 +481,7 @@ def main():
             "cpu_baseline": {"value": n_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "%d oracle steps (%s) of %s in %.1f s, one process" % (
                                  n_cpu, "numpy actor + env-step" if use_actor else "env-step", args.family, t_cpu)},
+            "cpu_baseline_c_env_step": c_line,
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "path": e2e_path},
             "e2e_resident_state": e2e_res,
