@@ -154,7 +154,8 @@ struct tactor_handle_s {
   float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
   int* d_error = nullptr;              // set by a kernel whose mbarrier wait timed out
   int ncta = 1;                        // CTAs per tcgen05 group (2 = CTA pair, cta_group::2)
-  int sms = 0;                         // SM count of the device (tile splitting of the last wave); TACTOR_NO_SPLIT=1 disables
+  int sms = 0;                         // SM count of the device (persistent grid, tile splitting of the last wave); TACTOR_NO_SPLIT=1:
+                                       // one CTA per unsplit tile
   float wscale_inv[TACTOR_NLAYERS] = {};  // 1 / power-of-two scale folded into d_wimg[l] (f16 split), 1 otherwise
   std::atomic<int64_t> launches{0};
   uint64_t calls = 0;
@@ -184,6 +185,8 @@ cudaError_t launch_pipe(tactor::tc::fused::Params& p, int M, int sms, cudaStream
     const int f = (rem > 0 && 4 * rem <= sms) ? 4 : (rem > 0 && 2 * rem <= sms) ? 2 : 1;
     if (f > 1) { p.split_from = full; p.split_f = f; grid = full + f * rem; }
   }
+  p.n_items = grid;
+  if (NCTA == 1 && sms > 0 && grid > sms) grid = sms;      // persistent: one CTA per SM walks the items
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(tc::pipe::PTHREADS);

@@ -97,13 +97,19 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   // CTAs below split_from own a full 128-row tile.  The tiles of the last, partial wave are cut into split_f pieces of
   // 128 / split_f rows, one CTA each, so that the SMs a partial wave would leave idle share its work: a CTA with fewer
   // live rows runs the same barrier protocol, but the warps of its dead 32-row groups skip their work.
-  int row0 = blockIdx.x * TCM, rows_here = TCM;
-  if ((int)blockIdx.x >= P.split_from) {
-    const int j = (int)blockIdx.x - P.split_from;
-    rows_here = TCM / P.split_f;
-    row0 = (P.split_from + j / P.split_f) * TCM + (j % P.split_f) * rows_here;
-  }
-  const int env0 = row0 / NODES;
+  //
+  // PERSISTENT: the grid is one CTA per SM and a CTA walks the work items blockIdx.x, blockIdx.x + gridDim.x, ...; TMEM,
+  // barriers and the tile-independent constants are set up once, every barrier parity is derived from chunk / GEMM
+  // counters that keep running across items, and the generators start on the next item while the issuer and the
+  // epilogue still finish the current one.
+  auto item_rows = [&](int item, int& row0, int& rows_here) {
+    row0 = item * TCM; rows_here = TCM;
+    if (item >= P.split_from) {
+      const int j = item - P.split_from;
+      rows_here = TCM / P.split_f;
+      row0 = (P.split_from + j / P.split_f) * TCM + (j % P.split_f) * rows_here;
+    }
+  };
   const int M = P.M;
   // W ring (s < WST):  w_full  this CTA's W half landed (TMA tx)       w_peer  the peer's half landed (leader's copy)
   //                    w_empty stage consumed (tcgen05.commit, multicast to the pair)
@@ -144,24 +150,14 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     mbar_init(h_ready, NEPIW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // tile constants: A_n (transposed), pooled rows, head kernels, first layer-1 kernel, raw x_n rows (staged in H,
-  // which is not written before the first epilogue)
+  // item-independent constants: A_n (transposed) and the head kernels; the generators stage the per-item data
   for (int idx = tid; idx < NODES * NODES; idx += PTHREADS) AnT[(idx % NODES) * NODES + idx / NODES] = P.A_n[idx];
-  for (int idx = tid; idx < ENVS * 208; idx += PTHREADS) {
-    const int env = env0 + idx / 208;
-    Pl[idx] = (env * NODES < M) ? P.pooled[(size_t)env * 208 + idx % 208] : 0.f;
-  }
   for (int idx = tid; idx < 2 * 201; idx += PTHREADS) {
     const int hd = idx / 201, k = idx % 201;
     reinterpret_cast<float4*>(Wh)[idx] = (k < KH) ? __ldg(reinterpret_cast<const float4*>(P.w_head[hd] + (size_t)k * 208))
                                                   : __ldg(reinterpret_cast<const float4*>(P.b_head[hd]));
   }
-  for (int idx = tid; idx < 14 * 52; idx += PTHREADS)
-    reinterpret_cast<float4*>(W1s)[idx] = (idx < 13 * 52) ? __ldg(reinterpret_cast<const float4*>(P.w1[0]) + idx)
-                                                          : __ldg(reinterpret_cast<const float4*>(P.b1[0]) + (idx - 13 * 52));
-  float* Xraw = H;                                                           // [128][13]
-  for (int idx = tid; idx < TCM * 13; idx += PTHREADS)
-    Xraw[idx] = (row0 + idx / 13 < M) ? P.x_n[(size_t)row0 * 13 + idx] : 0.f;
+  float* Xraw = H;                                                           // [128][13] raw x_n rows of the item
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if constexpr (NCTA == 2) cluster_sync_all();
@@ -170,7 +166,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   bool ok = true;
 #ifdef DEBUG_TIMING
 #ifndef DEBUG_BLOCK
-#define DEBUG_BLOCK 200
+#define DEBUG_BLOCK 100
 #endif
   // per role (generator warp 0, first epilogue warp, issuer) and GEMM: 8 cycle counters
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -216,13 +212,30 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       }
       named_bar_sync(1, NGENW * 32);
     };
+    float amax = 0.f;                                        // largest |A.X| this thread split (f16 range check)
+    for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
+    int row0, rows_here;
+    item_rows(item, row0, rows_here);
+    const int env0 = row0 / NODES;
+    const uint32_t ubase = (uint32_t)it * (uint32_t)(NGEMM * NCH);
+    // per-item data, staged by the 16 generator warps once every one of them is done with the previous item (its
+    // layer-3 GEMMs read H, where the raw x_n rows go; the epilogue does not touch H after GEMM 4)
+    named_bar_sync(1, NGENW * 32);
+    for (int idx = tid; idx < ENVS * 208; idx += NGENW * 32) {
+      const int env = env0 + idx / 208;
+      Pl[idx] = (env * NODES < M) ? P.pooled[(size_t)env * 208 + idx % 208] : 0.f;
+    }
+    for (int idx = tid; idx < 14 * 52; idx += NGENW * 32) reinterpret_cast<float4*>(W1s)[idx] = __ldg(w1_src(0, idx));
+    for (int idx = tid; idx < TCM * 13; idx += NGENW * 32)
+      Xraw[idx] = (row0 + idx / 13 < M) ? P.x_n[(size_t)row0 * 13 + idx] : 0.f;
+    named_bar_sync(1, NGENW * 32);
     if (32 * q >= rows_here) {
       // dead row group of a split tile: keep the barrier protocol going, produce nothing (the tensor core reads
       // whatever these TMEM lanes hold; rows are independent and the epilogue never looks at them)
       for (int g = 0; g < NGEMM; ++g) {
         if (g == 1 || g == 3) reload_w1(g);
         for (int c = 0; c < NCH; ++c) {
-          const uint32_t u = (uint32_t)(g * NCH + c), sa = u % PAST;
+          const uint32_t u = ubase + (uint32_t)(g * NCH + c), sa = u % PAST;
           if ((int)(u & 1u) != par) continue;
           if (u >= PAST) ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok;
           __syncwarp();
@@ -232,7 +245,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           }
         }
       }
-      return;
+      continue;
     }
     const int r = 32 * q + lane;                             // row of the tile
     const int e = r / NODES, n = r % NODES;
@@ -303,7 +316,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     };
     const float* arow = nullptr;
     int astride = 1;
-    float amax = 0.f;                                        // largest |A.X| this thread split (f16 range check)
     // Hand-off of an A stage, decoupled from the chunk that filled it: the stage is acquired (a_empty) only right before
     // its tcgen05.st, and published (wait::st, fence, arrive on a_full) in the middle of the NEXT chunk's arithmetic, so
     // neither the barrier round trip nor the tensor-memory store latency sits on the warp's dependent chain.
@@ -347,12 +359,12 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         }
       }
       PDBG_T(tg1);
-      if (g == 5) { ok = mbar_wait(h_ready, 0) && ok; }      // H complete (epilogue of GEMM 4)
+      if (g == 5) { ok = mbar_wait(h_ready, (uint32_t)(it & 1)) && ok; }      // H complete (epilogue of GEMM 4)
       PDBG_T(tg2);
       PDBG_ACC(0, tg1 - tg0); PDBG_ACC(1, tg2 - tg1);
       // ---- this warp's chunks of the GEMM: generate, mix with the adjacency, split, store to tensor memory ----
       for (int c = 0; c < NCH; ++c) {
-        const uint32_t u = (uint32_t)(g * NCH + c), sa = u % PAST;
+        const uint32_t u = ubase + (uint32_t)(g * NCH + c), sa = u % PAST;
         if ((int)(u & 1u) != par) continue;                  // the other parity's warps own this chunk
         PDBG_T(t1);
         const int k0 = c * KCH + KPT * kh;
@@ -473,8 +485,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         PDBG_ACC(4, t3 - t1);
       }
       hand_off();                                            // the accumulator of this GEMM must not wait for the next one
-      if (warp == 0) { PDBG_FLUSH(0, g); }
+      if (warp == 0 && it == 0) { PDBG_FLUSH(0, g); }
     }
+    }  // items
     if (!(amax <= F16_MAX) && P.error_flag) atomicOr(P.error_flag, 2);   // |A.X| left the fp16 range (or NaN input)
   };
   if (warp < NGENW) {
@@ -485,11 +498,14 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     const int r = 32 * q + lane;
     const int n = r % NODES;
     const int lane_env0 = lane & ~(NODES - 1);
+    for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
+    int row0, rows_here;
+    item_rows(item, row0, rows_here);
     const bool live = 32 * q < rows_here;                    // dead row group of a split tile: barriers only
     for (int g = 0; g < NGEMM; ++g) {
-      const int b = g & 1;
+      const int G = it * NGEMM + g, b = G & 1;               // GEMM counter across items: accumulator and parity
       if (!live) {
-        ok = mbar_wait(acc_full + 8 * b, (uint32_t)((g >> 1) & 1)) && ok;
+        ok = mbar_wait(acc_full + 8 * b, (uint32_t)((G >> 1) & 1)) && ok;
         __syncwarp();
         if (lane == 0) {
           if (is_leader) mbar_arrive(acc_empty + 8 * b);
@@ -499,7 +515,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         continue;
       }
       PDBG_T(t0);
-      ok = mbar_wait(acc_full + 8 * b, (uint32_t)((g >> 1) & 1)) && ok;
+      ok = mbar_wait(acc_full + 8 * b, (uint32_t)((G >> 1) & 1)) && ok;
       PDBG_T(t1);
       PDBG_ACC(0, t1 - t0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -569,8 +585,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       }
       PDBG_T(t3);
       PDBG_ACC(2, t3 - t2);
-      if (warp == NGENW) { PDBG_FLUSH(1, g); }
+      if (warp == NGENW && it == 0) { PDBG_FLUSH(1, g); }
     }
+    }  // items
   } else if (warp == W_ISSUER) {
     // =================================================== MMA issuer / W forwarder =============================
     if (lane == 0) {
@@ -582,18 +599,20 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           db[st][0] = make_desc(b_hi, B_LBO);
           db[st][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);
         }
+        for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
+        const uint32_t ubase = (uint32_t)it * (uint32_t)(NGEMM * NCH);
         for (int g = 0; g < NGEMM; ++g) {
-          const int b = g & 1;
+          const int G = it * NGEMM + g, b = G & 1;
           const uint32_t dacc = tmem_base + (uint32_t)(b ? TM_ACC1 : 0);
           PDBG_T(ta0);
-          if (g >= 2) {                                      // the epilogue of GEMM g-2 has drained this accumulator
-            ok = mbar_wait_cluster(acc_empty + 8 * b, (uint32_t)(((g >> 1) - 1) & 1)) && ok;
+          if (G >= 2) {                                      // the epilogue of GEMM G-2 has drained this accumulator
+            ok = mbar_wait_cluster(acc_empty + 8 * b, (uint32_t)(((G >> 1) - 1) & 1)) && ok;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
           PDBG_T(ta1);
           PDBG_ACC(3, ta1 - ta0);
           for (int c = 0; c < NCH; ++c) {
-            const uint32_t u = (uint32_t)(g * NCH + c), sw = u % WST, sa = u % PAST;
+            const uint32_t u = ubase + (uint32_t)(g * NCH + c), sw = u % WST, sa = u % PAST;
             PDBG_T(t0);
             if constexpr (NCTA == 2) ok = mbar_wait_cluster(a_full + 8 * sa, (u / PAST) & 1) && ok;
             else ok = mbar_wait(a_full + 8 * sa, (u / PAST) & 1) && ok;
@@ -617,12 +636,14 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
             PDBG_T(t3);
             PDBG_ACC(2, t3 - t2);
           }
-          PDBG_FLUSH(2, g);
+          if (it == 0) { PDBG_FLUSH(2, g); }
         }
+        }  // items
       } else {
-        for (int u = 0; u < NGEMM * NCH; ++u) {              // peer CTA: tell the leader that W chunk u has landed here
-          const uint32_t sw = (uint32_t)u % WST;
-          ok = mbar_wait(w_full + 8 * sw, ((uint32_t)u / WST) & 1) && ok;
+        for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it)
+        for (int uu = 0; uu < NGEMM * NCH; ++uu) {           // peer CTA: tell the leader that W chunk u has landed here
+          const uint32_t u = (uint32_t)it * (uint32_t)(NGEMM * NCH) + (uint32_t)uu, sw = u % WST;
+          ok = mbar_wait(w_full + 8 * sw, (u / WST) & 1) && ok;
           mbar_arrive_remote(w_peer + 8 * sw, 0);
         }
       }
@@ -631,9 +652,10 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   } else {
     // =================================================== W producer ===========================================
     if (lane == 0) {
+      for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it)
       for (int g = 0; g < NGEMM; ++g)
         for (int c = 0; c < NCH; ++c) {
-          const uint32_t u = (uint32_t)(g * NCH + c), s = u % WST;
+          const uint32_t u = (uint32_t)it * (uint32_t)(NGEMM * NCH) + (uint32_t)(g * NCH + c), s = u % WST;
           if (u >= WST) ok = mbar_wait(w_empty + 8 * s, ((u / WST) - 1) & 1) && ok;       // chunk u-WST consumed
           const uint32_t bytes = (uint32_t)STAGE_BYTES;                                    // this CTA's half: hi then lo
           const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg[g]) +

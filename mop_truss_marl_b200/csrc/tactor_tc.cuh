@@ -201,7 +201,8 @@ struct Params {
   float mu, theta, sigma;
   uint64_t seed, call;
   const uint64_t* seed_call;
-  int split_from;         // first CTA that owns a piece of a tile (tiles of the last partial wave), grid size if none
+  int n_items;            // work items (full tiles + pieces of split tiles); a persistent CTA walks item, item + grid, ...
+  int split_from;         // first work item that is a piece of a tile (tiles of the last partial wave), n_items if none
   int split_f;            // pieces per split tile: 1, 2 or 4
   int* error_flag;
 };
