@@ -8,6 +8,11 @@
  * The environments are independent, so the batch is cut into `pieces` pieces that run through three CUDA streams
  * (upload / act + step / download): piece i+1 uploads while piece i computes and piece i-1 downloads.  Host buffers
  * should be pinned (cudaHostAlloc / torch pin_memory); pageable buffers work but do not overlap.
+ *
+ * With pinned buffers the whole step (every copy and kernel of every piece) is captured into a CUDA graph the second
+ * time a set of buffer addresses is seen and replayed afterwards (four graphs are kept: a driver that ping-pongs two
+ * state tuples alternates between two of them); replayed steps give the bits of directly enqueued ones, OU noise
+ * included.  TROLLOUT_NO_GRAPH=1 disables the graphs, TROLLOUT_TIMELINE=1 prints a per-piece event timeline to stderr.
  */
 #ifndef TROLLOUT_H_
 #define TROLLOUT_H_
