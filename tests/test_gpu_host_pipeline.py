@@ -86,3 +86,35 @@ def test_graph_replay_equals_direct_enqueue(family, B, pieces, monkeypatch):
     assert all(p == (pieces, 2 * pieces) for p in per_step), per_step
     assert int(bufs[0][0]["status"].abs().max()) == 0
     pols[0].check()
+
+
+@pytest.mark.parametrize("family,B", [("small_bridge", 1024), ("large_roof", 256)])
+def test_closed_loop_episode_stays_healthy(family, B):
+    """BASELINE.json configs[0] runs one episode of 500 game steps: the resident actor -> env loop for a whole episode must
+    keep every environment solvable (status 0), every tensor finite, the actor inside the fp16 range of its split product
+    (tactor_status), and the geometry inside the reference's own bounds"""
+    from mop_truss_marl_b200 import actor, batched_env, tf_checkpoint
+    env = batched_env.BatchedTrussEnv(family, B)
+    env.reset()
+    pol = actor.BatchedActor(tf_checkpoint.random_actor_weights(seed=20), env.N, B, seed=20)
+    dev = env.device
+    x_p = torch.tensor([1.0, 1.0, 1.0, 1.0 / 50], device=dev).repeat(B, 1, 1).contiguous()
+    A_p = torch.ones(B, 1, 1, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    bad = torch.zeros((), dtype=torch.int32, device=dev)
+    for t in range(500):
+        a_geo, a_topo = pol.act(env.x_n, env.A_n, env.A_s, env.A_n_ts, env.A_n_cs, x_p, A_p)
+        coin = (torch.rand(B, device=dev, generator=g) >= 0.5).to(torch.uint8)
+        env.step(a_geo, a_topo, coin)
+        bad |= env.status.abs().max()
+    torch.cuda.synchronize()
+    pol.check()
+    assert int(bad) == 0
+    for k in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "point", "move_range"):
+        assert bool(torch.isfinite(getattr(env, k)).all()), k
+    y = env.nN_x_n[:, :, 1]
+    scal = env.handle.table("scalars")                       # y_max, y_min, d_min, ...
+    assert float(y.min()) >= float(scal[1]) and float(y.max()) <= float(scal[0]) + 1e-6
+    nx = env.N // 2
+    assert float((y[:, nx:] - y[:, :nx]).min()) >= float(scal[2]) - 1e-6      # at least d_min deep everywhere
+    assert env.game_step == 501                                # the reference counts from 1 (truss2D_ENV.py:242)
