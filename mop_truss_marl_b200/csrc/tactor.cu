@@ -137,6 +137,30 @@ pareto_small_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p
   if (tid < LD) pooled_out[(size_t)b * LD + tid] = (tid < HID) ? sum : 0.f;
 }
 
+// P == 1 (the reset-time graph, truss2D_ENV.py:348-351): pooled[h] = relu(A_p x_p W14[:,h] + b[h]) is five FMAs per
+// (environment, column); eight environments per CTA keep the launch from being all CTA-scheduling overhead
+constexpr int P1_ENVS = 8;
+__global__ void __launch_bounds__(256)
+pareto_p1_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
+                 const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out, int B) {
+  const int tid = threadIdx.x;
+  if (tid >= LD) return;
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, bias = 0.f;
+  if (tid < HID) { w0 = W14[0 * LD + tid]; w1 = W14[1 * LD + tid]; w2 = W14[2 * LD + tid]; w3 = W14[3 * LD + tid]; bias = b14[tid]; }
+#pragma unroll
+  for (int i = 0; i < P1_ENVS; ++i) {
+    const int b = blockIdx.x * P1_ENVS + i;
+    if (b >= B) break;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(x_p) + b);
+    const float a = __ldg(A_p + b);
+    const int valid = n_pf ? min(max(n_pf[b], 0), 1) : 1;
+    const float t0 = fmaf(x.w, w3, fmaf(x.z, w2, fmaf(x.y, w1, x.x * w0)));   // same operation order as the general kernels
+    float sum = 0.f;
+    if (valid > 0) sum = fmaxf(fmaf(a, t0, 0.f) + bias, 0.f);
+    pooled_out[(size_t)b * LD + tid] = (tid < HID) ? sum : 0.f;
+  }
+}
+
 constexpr int pareto_smem(int P) { return (P * LD + 4 * LD + P * P + P * 4) * 4; }
 constexpr int PARETO_SMEM = pareto_smem(50);
 
@@ -274,7 +298,9 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   using namespace tactor;
   const int M = B * NODES;
   float* pooled = h->pooled;
-  if (in->P <= PSMALL)
+  if (in->P == 1 && (reinterpret_cast<uintptr_t>(in->x_p) & 15u) == 0)
+    pareto_p1_kernel<<<(B + P1_ENVS - 1) / P1_ENVS, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, h->d_w[3], h->d_b[3], pooled, B);
+  else if (in->P <= PSMALL)
     pareto_small_kernel<NODES><<<B, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
   else
     pareto_kernel<NODES><<<B, 256, pareto_smem(in->P), st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
