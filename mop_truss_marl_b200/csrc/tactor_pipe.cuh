@@ -164,6 +164,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   bool ok = true;
+  // programmatic dependent launch: the env-step kernel that follows in the stream may be scheduled as soon as SMs free up
+  // (it waits in griddepcontrol.wait for this grid to finish before it reads the actions)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef DEBUG_TIMING
 #ifndef DEBUG_BLOCK
 #define DEBUG_BLOCK 100

@@ -188,7 +188,6 @@ tfem_step_kernel(const StepArgs args) {
     }
     in_coin = args.in.coin ? (int)args.in.coin[b] : 0;
   };
-  fetch_inputs(blockIdx.x * WARPS_PER_CTA + warp);
   {  // stage the family tables and output maps once per CTA (L2-resident, 8..15 KB)
     const uint4* src = reinterpret_cast<const uint4*>(args.fam);
     uint4* dst = reinterpret_cast<uint4*>(fam);
@@ -197,6 +196,10 @@ tfem_step_kernel(const StepArgs args) {
     uint4* mdst = reinterpret_cast<uint4*>(maps);
     for (int i = tid; i < args.map_entries / 8; i += blockDim.x) mdst[i] = msrc[i];
   }
+  // programmatic dependent launch: the kernel may have been started while its predecessor in the stream (the actor, whose
+  // actions it reads) is still running; everything above only touches the handle's constant tables
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  fetch_inputs(blockIdx.x * WARPS_PER_CTA + warp);
   __syncthreads();
   unsigned char* wbase = smem_raw + align16((int)sizeof(FamilyTables)) + align16(args.map_entries * 2) + warp * D::WARP_BYTES;
   double* Kb = reinterpret_cast<double*>(wbase);            // [NI][BAND]: Kb[j*8+k] = K[j+k][j]
@@ -695,12 +698,20 @@ int step_kernel_launch(int nx, const StepArgs& args, const LaunchInfo& info, cud
   const int needed = (args.B + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   const int full = gm ? info.grid_genes : info.grid;
   const int grid = needed < full ? needed : full;
-  if (nx == 8 && !gm) tfem_step_kernel<8, false><<<grid, info.block, info.smem_bytes, stream>>>(args);
-  else if (nx == 8) tfem_step_kernel<8, true><<<grid, info.block, info.smem_bytes, stream>>>(args);
-  else if (nx == 16 && !gm) tfem_step_kernel<16, false><<<grid, info.block, info.smem_bytes, stream>>>(args);
-  else if (nx == 16) tfem_step_kernel<16, true><<<grid, info.block, info.smem_bytes, stream>>>(args);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)info.block);
+  cfg.dynamicSmemBytes = (size_t)info.smem_bytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e;
+  if (nx == 8 && !gm) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<8, false>, args);
+  else if (nx == 8) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<8, true>, args);
+  else if (nx == 16 && !gm) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<16, false>, args);
+  else if (nx == 16) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<16, true>, args);
   else return (int)cudaErrorInvalidValue;
-  return (int)cudaGetLastError();
+  return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 }  // namespace tfem
