@@ -46,6 +46,9 @@ class GeneEvaluator:
                   "U": ((B,), torch.float64), "reactions": ((B, self.handle.dims.nres), torch.float64), "status": ((B,), torch.int32)}
         o = capi.GenesOut()
         self.out = {}
+        if B == 0:                                           # empty population: nothing to launch
+            self.out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=self.device) for k in fields}
+            return self.out.get("point")
         for k in fields:
             shape, dt = shapes[k]
             self.out[k] = torch.empty(shape, dtype=dt, device=self.device)

@@ -81,6 +81,13 @@ def test_read_genes_custom_normalisers_and_errors(genesmod):
     assert np.array_equal(p0[:, 2:], p1[:, 2:])
     with pytest.raises(ValueError):
         ev.read_genes(np.zeros((2, 5)))
+    launches = ev.handle.launch_count()
+    empty = ev.read_genes(np.zeros((0, ev.N + ev.E)))                  # empty population
+    assert tuple(empty.shape) == (0, 4) and ev.handle.launch_count() == launches
+    one = ev.read_genes(g[3])                                          # a single individual, 1-D
+    assert np.array_equal(one.cpu().numpy()[0], p0[3])
+    odd = ev.read_genes(g[:7]).cpu().numpy()                           # ragged against the 8 warps of a CTA
+    assert np.array_equal(odd, p0[:7])
 
 
 @pytest.mark.parametrize("name,B", [("small_bridge", 18000), ("large_bridge", 12000)])
