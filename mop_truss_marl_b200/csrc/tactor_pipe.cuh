@@ -54,7 +54,7 @@ constexpr int DMAX = 8;                                     // neighbour slots o
 
 template <int NODES, int NCTA>
 __host__ __device__ constexpr int pipe_smem_bytes() {
-  return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + 2 * NGENW * 32 * LDX * 4 + 14 * 208 * 4 +
+  return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + 2 * NGENW * 32 * LDX * 4 + 3 * 14 * 208 * 4 +
          (TCM / NODES) * 208 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + 384;
 }
 
@@ -83,8 +83,8 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* H = reinterpret_cast<float*>(smem + WST * STAGE_BYTES);             // [128][LDH]
   float* Xt = H + TCM * LDH;                                                 // [8 warps][32][LDX] exchange tiles
-  float* W1s = Xt + 2 * NGENW * 32 * LDX;                                        // [14][208] layer-1 kernel + bias row
-  float* Pl = W1s + 14 * 208;                                                // [ENVS][208] pooled Pareto embedding
+  float* W1all = Xt + 2 * NGENW * 32 * LDX;                                  // [3][14][208] the three layer-1 kernels + bias rows, resident
+  float* Pl = W1all + 3 * 14 * 208;                                                // [ENVS][208] pooled Pareto embedding
   float* AnT = Pl + ENVS * 208;                                              // [N(j)][N(n)] shared A_n, transposed
   float* Wh = AnT + NODES * NODES;                                           // [2][201][4] head kernels, row 200 = bias
   float* Us = Wh + 2 * 201 * 4;                                              // [128][4] head pre-activations
@@ -157,6 +157,11 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     reinterpret_cast<float4*>(Wh)[idx] = (k < KH) ? __ldg(reinterpret_cast<const float4*>(P.w_head[hd] + (size_t)k * 208))
                                                   : __ldg(reinterpret_cast<const float4*>(P.b_head[hd]));
   }
+  for (int idx = tid; idx < 3 * 14 * 52; idx += PTHREADS) {
+    const int l1 = idx / (14 * 52), i = idx % (14 * 52);
+    reinterpret_cast<float4*>(W1all)[idx] = (i < 13 * 52) ? __ldg(reinterpret_cast<const float4*>(P.w1[l1]) + i)
+                                                          : __ldg(reinterpret_cast<const float4*>(P.b1[l1]) + (i - 13 * 52));
+  }
   float* Xraw = H;                                                           // [128][13] raw x_n rows of the item
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -193,28 +198,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     // row group q, k-half kh of the chunk, chunk parity par: a warp works on every other chunk (8 k per thread), so
     // two chunks are always in flight in different warps and the per-chunk sync overhead is paid per 8 k
     const int q = warp & 3, kh = (warp >> 2) & 1, par = warp >> 3;
-    // gcn_l1_2 / gcn_l1_3 kernels replace gcn_l1_1's in shared memory before GEMM 1 / 3 (all 16 generator warps take part)
-    auto w1_src = [&](int l1, int idx) -> const float4* {
-      return (idx < 13 * 52) ? reinterpret_cast<const float4*>(P.w1[l1]) + idx
-                             : reinterpret_cast<const float4*>(P.b1[l1]) + (idx - 13 * 52);
-    };
-    auto reload_w1 = [&](int g) {
-      const int l1 = (g == 1) ? 1 : 2;
-      float4 wreg[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int idx = tid + t * NGENW * 32;
-        wreg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < 14 * 52) wreg[t] = __ldg(w1_src(l1, idx));
-      }
-      named_bar_sync(1, NGENW * 32);                         // all generators are done reading the old kernel
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int idx = tid + t * NGENW * 32;
-        if (idx < 14 * 52) reinterpret_cast<float4*>(W1s)[idx] = wreg[t];
-      }
-      named_bar_sync(1, NGENW * 32);
-    };
     float amax = 0.f;                                        // largest |A.X| this thread split (f16 range check)
     for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
     int row0, rows_here;
@@ -228,7 +211,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       const int env = env0 + idx / 208;
       Pl[idx] = (env * NODES < M) ? P.pooled[(size_t)env * 208 + idx % 208] : 0.f;
     }
-    for (int idx = tid; idx < 14 * 52; idx += NGENW * 32) reinterpret_cast<float4*>(W1s)[idx] = __ldg(w1_src(0, idx));
     for (int idx = tid; idx < TCM * 13; idx += NGENW * 32)
       Xraw[idx] = (row0 + idx / 13 < M) ? P.x_n[(size_t)row0 * 13 + idx] : 0.f;
     named_bar_sync(1, NGENW * 32);
@@ -236,7 +218,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       // dead row group of a split tile: keep the barrier protocol going, produce nothing (the tensor core reads
       // whatever these TMEM lanes hold; rows are independent and the epilogue never looks at them)
       for (int g = 0; g < NGEMM; ++g) {
-        if (g == 1 || g == 3) reload_w1(g);
         for (int c = 0; c < NCH; ++c) {
           const uint32_t u = ubase + (uint32_t)(g * NCH + c), sa = u % PAST;
           if ((int)(u & 1u) != par) continue;
@@ -344,7 +325,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     for (int g = 0; g < NGEMM; ++g) {
       PDBG_T(tg0);
       // ---- per-GEMM setup ----
-      if (g == 1 || g == 3) reload_w1(g);                    // g = 2 reuses gcn_l1_2's kernel
       load_coefs(g, coef);
       row_of(g, arow, astride);
       if (g + 1 < NGEMM) {                                   // prefetch for the next GEMM
@@ -352,14 +332,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         row_of(g + 1, rowp, stride);
         if (stride == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp));
         if (NODES == 32 && stride == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp + 16));
-        if (g == 0 || g == 2) {
-          const int l1 = (g == 0) ? 1 : 2;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int idx = tid + t * NGENW * 32;
-            if (idx < 14 * 52) asm volatile("prefetch.global.L1 [%0];" ::"l"(w1_src(l1, idx)));
-          }
-        }
       }
       PDBG_T(tg1);
       if (g == 5) { ok = mbar_wait(h_ready, (uint32_t)(it & 1)) && ok; }      // H complete (epilogue of GEMM 4)
@@ -383,6 +355,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
               const int kk = k0 + 4 * hf;
               float4 x;
               if (g <= 3) {
+                const float* W1s = W1all + ((g == 0) ? 0 : (g <= 2 ? 1 : 2)) * 14 * 208;   // gcn_l1_1 | gcn_l1_2 (g = 1, 2) | gcn_l1_3
                 x = *reinterpret_cast<const float4*>(W1s + 13 * 208 + kk);
                 float4 wa[7], wb[6];                         // two batches of (broadcast) loads in flight ahead of the FMAs
 #pragma unroll

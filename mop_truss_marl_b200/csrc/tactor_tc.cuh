@@ -39,7 +39,7 @@ template <int NCTA> struct Cfg {
   static constexpr int BN = TCN / NCTA;                     // W columns held by one CTA
   static constexpr int B_LBO = BN * 16;                     // bytes between core matrices adjacent in K (B operand)
   static constexpr int B_BYTES = NKB * B_LBO;               // one of {hi, lo} of a full chunk
-  static constexpr int WST = NCTA == 1 ? (F16 ? 5 : 3) : 5; // W stages in shared memory (K chunks in flight)
+  static constexpr int WST = 3;                             // W stages in shared memory (K chunks in flight)
   static constexpr int STAGE_BYTES = 2 * B_BYTES;           // Bhi, Blo of one K chunk
   static constexpr int CHUNK_IMG_BYTES = NCTA * 2 * B_BYTES;      // one full chunk of the W image (all CTAs)
   // fp32 accumulate, A and B K-major, M = 128 * NCTA, N = 208; operand format 0 = f16, 2 = tf32
