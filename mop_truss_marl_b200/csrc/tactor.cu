@@ -382,9 +382,9 @@ static int check_inputs(tactor_handle_t h, int B, const tactor_inputs* in, float
   if (!in->x_n || !in->A_n || !in->A_s || !in->A_n_ts || !in->A_n_cs || !in->x_p || !in->A_p)
     return afail(TFEM_ERR_ARG, "x_n, A_n, A_s, A_n_ts, A_n_cs, x_p and A_p are required");
   if (in->P < 1 || in->P > 50) return afail(TFEM_ERR_ARG, "P must be in 1..50 (MAX_FRONT)");
-  const void* vec[] = {in->A_n, in->A_s, in->A_n_ts, in->A_n_cs};     // read with 128-bit loads
+  const void* vec[] = {in->A_n, in->A_s, in->A_n_ts, in->A_n_cs, in->x_n};     // read with 128-bit loads / 16-byte async copies
   for (const void* p : vec)
-    if (reinterpret_cast<uintptr_t>(p) & 15u) return afail(TFEM_ERR_ALIGN, "adjacency tensors must be 16-byte aligned");
+    if (reinterpret_cast<uintptr_t>(p) & 15u) return afail(TFEM_ERR_ALIGN, "x_n and the adjacency tensors must be 16-byte aligned");
   return TFEM_OK;
 }
 

@@ -55,7 +55,7 @@ constexpr int DMAX = 8;                                     // neighbour slots o
 template <int NODES, int NCTA>
 __host__ __device__ constexpr int pipe_smem_bytes() {
   return Cfg<NCTA>::WST * Cfg<NCTA>::STAGE_BYTES + TCM * LDH * 4 + 2 * NGENW * 32 * LDX * 4 + 3 * 14 * 208 * 4 +
-         (TCM / NODES) * 208 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + 384;
+         2 * (TCM / NODES) * 208 * 4 + 2 * TCM * 13 * 4 + NODES * NODES * 4 + 2 * 201 * 4 * 4 + TCM * 4 * 4 + 384;
 }
 
 __device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t* v) {
@@ -84,8 +84,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   float* H = reinterpret_cast<float*>(smem + WST * STAGE_BYTES);             // [128][LDH]
   float* Xt = H + TCM * LDH;                                                 // [8 warps][32][LDX] exchange tiles
   float* W1all = Xt + 2 * NGENW * 32 * LDX;                                  // [3][14][208] the three layer-1 kernels + bias rows, resident
-  float* Pl = W1all + 3 * 14 * 208;                                                // [ENVS][208] pooled Pareto embedding
-  float* AnT = Pl + ENVS * 208;                                              // [N(j)][N(n)] shared A_n, transposed
+  float* Pl2 = W1all + 3 * 14 * 208;                                         // [2][ENVS][208] pooled Pareto embedding of the item / the next item
+  float* Xr2 = Pl2 + 2 * ENVS * 208;                                         // [2][128][13] raw x_n rows of the item / the next item
+  float* AnT = Xr2 + 2 * TCM * 13;                                              // [N(j)][N(n)] shared A_n, transposed
   float* Wh = AnT + NODES * NODES;                                           // [2][201][4] head kernels, row 200 = bias
   float* Us = Wh + 2 * 201 * 4;                                              // [128][4] head pre-activations
   uint64_t* bars = reinterpret_cast<uint64_t*>(Us + TCM * 4);
@@ -162,7 +163,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     reinterpret_cast<float4*>(W1all)[idx] = (i < 13 * 52) ? __ldg(reinterpret_cast<const float4*>(P.w1[l1]) + i)
                                                           : __ldg(reinterpret_cast<const float4*>(P.b1[l1]) + (i - 13 * 52));
   }
-  float* Xraw = H;                                                           // [128][13] raw x_n rows of the item
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if constexpr (NCTA == 2) cluster_sync_all();
@@ -199,21 +199,41 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     // two chunks are always in flight in different warps and the per-chunk sync overhead is paid per 8 k
     const int q = warp & 3, kh = (warp >> 2) & 1, par = warp >> 3;
     float amax = 0.f;                                        // largest |A.X| this thread split (f16 range check)
+    // asynchronous copy of one item's x_n rows and pooled rows into buffer `buf` (all 512 generator threads take part)
+    auto stage_item = [&](int item_s, int buf) {
+      int row0s, rows_s;
+      item_rows(item_s, row0s, rows_s);
+      const long long xbytes = (long long)M * 13 * 4;        // bytes of x_n that exist
+      for (int idx = tid; idx < TCM * 13 / 4; idx += NGENW * 32) {
+        const long long off = (long long)row0s * 13 * 4 + (long long)idx * 16;
+        const long long left = xbytes - off;
+        const int nbytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+        const uint32_t dst = smem_u32(Xr2 + buf * TCM * 13 + idx * 4);
+        const char* src = reinterpret_cast<const char*>(P.x_n) + (nbytes > 0 ? off : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+      }
+      const int env0s = row0s / NODES;
+      for (int idx = tid; idx < ENVS * 52; idx += NGENW * 32) {
+        const int env = env0s + idx / 52;
+        const int nbytes = (env * NODES < M) ? 16 : 0;
+        const uint32_t dst = smem_u32(Pl2 + buf * ENVS * 208 + idx * 4);
+        const char* src = reinterpret_cast<const char*>(P.pooled) + (nbytes ? ((size_t)env * 208 * 4 + (size_t)(idx % 52) * 16) : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+      }
+    };
     for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
     int row0, rows_here;
     item_rows(item, row0, rows_here);
     const int env0 = row0 / NODES;
     const uint32_t ubase = (uint32_t)it * (uint32_t)(NGEMM * NCH);
-    // per-item data, staged by the 16 generator warps once every one of them is done with the previous item (its
-    // layer-3 GEMMs read H, where the raw x_n rows go; the epilogue does not touch H after GEMM 4)
-    named_bar_sync(1, NGENW * 32);
-    for (int idx = tid; idx < ENVS * 208; idx += NGENW * 32) {
-      const int env = env0 + idx / 208;
-      Pl[idx] = (env * NODES < M) ? P.pooled[(size_t)env * 208 + idx % 208] : 0.f;
-    }
-    for (int idx = tid; idx < TCM * 13; idx += NGENW * 32)
-      Xraw[idx] = (row0 + idx / 13 < M) ? P.x_n[(size_t)row0 * 13 + idx] : 0.f;
-    named_bar_sync(1, NGENW * 32);
+    // per-item data (x_n rows, pooled rows): double-buffered; the copies of THIS item were issued one item ago
+    // (cp.async, 16 bytes each, zero-filled past the batch), so the item starts with one barrier and no global latency
+    if (it == 0) stage_item(item, 0);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    named_bar_sync(1, NGENW * 32);                           // everyone's copies have landed, everyone is done with item it-1
+    if (item + (int)gridDim.x < P.n_items) stage_item(item + (int)gridDim.x, (it + 1) & 1);
+    const float* Xraw = Xr2 + (it & 1) * TCM * 13;
+    const float* Pl = Pl2 + (it & 1) * ENVS * 208;
     if (32 * q >= rows_here) {
       // dead row group of a split tile: keep the barrier protocol going, produce nothing (the tensor core reads
       // whatever these TMEM lanes hold; rows are independent and the epilogue never looks at them)
