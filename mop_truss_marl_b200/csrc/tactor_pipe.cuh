@@ -220,6 +220,16 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         const char* src = reinterpret_cast<const char*>(P.pooled) + (nbytes ? ((size_t)env * 208 * 4 + (size_t)(idx % 52) * 16) : 0);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
       }
+      // the three per-environment adjacency tensors of that item are read straight from global memory (pattern masks,
+      // coefficients): pull their lines into L2 now
+      if (row0s + TCM <= M) {
+        constexpr int LINES = ENVS * NODES * NODES * 4 / 128;
+        for (int idx = tid; idx < 3 * LINES; idx += NGENW * 32) {
+          const int arr = idx / LINES, line = idx % LINES;
+          const float* base = (arr == 0 ? P.A_s : arr == 1 ? P.A_ts : P.A_cs) + (size_t)env0s * NODES * NODES;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + 128 * line));
+        }
+      }
     };
     for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
     int row0, rows_here;
