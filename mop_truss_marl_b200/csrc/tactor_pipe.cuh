@@ -270,7 +270,11 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     float z[13];
 #pragma unroll
     for (int i = 0; i < 13; ++i) z[i] = 0.f;
-    for (int j = 0; j < NODES; ++j) {
+    uint32_t mask_n = 0;                                     // pattern of this row of A_n
+#pragma unroll 8
+    for (int j = 0; j < NODES; ++j) mask_n |= (AnT[j * NODES + n] != 0.f) ? (1u << j) : 0u;
+    for (uint32_t m = mask_n; m; m &= m - 1) {               // only the row's neighbours: a zero entry adds exactly nothing
+      const int j = __ffs(m) - 1;
       const float a = AnT[j * NODES + n];
       const float* xr = Xraw + (e * NODES + j) * 13;
 #pragma unroll
@@ -281,9 +285,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     // per-environment matrix has an entry outside A_n's pattern, the warp uses the full row instead ("dense").
     float coef[DMAX];
     uint64_t nidx_packed = 0;                                // 8 neighbour lane ids, one byte each
-    uint32_t mask_n = 0;
-#pragma unroll 8
-    for (int j = 0; j < NODES; ++j) mask_n |= (AnT[j * NODES + n] != 0.f) ? (1u << j) : 0u;
     const int cnt = __popc(mask_n);
     uint32_t mask_o = 0;
     if (env_valid) {
