@@ -90,7 +90,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   float* Wh = AnT + NODES * NODES;                                           // [2][201][4] head kernels, row 200 = bias
   float* Us = Wh + 2 * 201 * 4;                                              // [128][4] head pre-activations
   uint64_t* bars = reinterpret_cast<uint64_t*>(Us + TCM * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * MAXST + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * MAXST + 8);
 
   // the shuffle tells the compiler that `warp` is warp-uniform: role branches become uniform branches and the
   // constant-bank reads of the generators go through the uniform datapath
@@ -122,6 +122,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   const uint32_t w_full = smem_u32(&bars[0]), w_peer = smem_u32(&bars[MAXST]), w_empty = smem_u32(&bars[2 * MAXST]);
   const uint32_t a_full = smem_u32(&bars[3 * MAXST]), a_empty = smem_u32(&bars[4 * MAXST]);
   const uint32_t acc_full = smem_u32(&bars[5 * MAXST]), acc_empty = smem_u32(&bars[5 * MAXST + 2]), h_ready = smem_u32(&bars[5 * MAXST + 4]);
+  const uint32_t x_full = smem_u32(&bars[5 * MAXST + 6]);      // [2] the item's x_n / pooled rows have landed (cp.async arrivals of all generator threads)
   const uint32_t cta_rank = (NCTA == 1) ? 0u : cluster_ctarank();
   const bool is_leader = (cta_rank == 0);
 
@@ -149,6 +150,8 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       mbar_init(acc_empty + 8 * b, NEPIW * NCTA);
     }
     mbar_init(h_ready, NEPIW);
+    mbar_init(x_full, NGENW * 32);
+    mbar_init(x_full + 8, NGENW * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // item-independent constants: A_n (transposed) and the head kernels; the generators stage the per-item data
@@ -222,6 +225,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       }
       // the three per-environment adjacency tensors of that item are read straight from global memory (pattern masks,
       // coefficients): pull their lines into L2 now
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(x_full + 8 * buf) : "memory");
       if (row0s + TCM <= M) {
         constexpr int LINES = ENVS * NODES * NODES * 4 / 128;
         for (int idx = tid; idx < 3 * LINES; idx += NGENW * 32) {
@@ -237,11 +241,12 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     const int env0 = row0 / NODES;
     const uint32_t ubase = (uint32_t)it * (uint32_t)(NGEMM * NCH);
     // per-item data (x_n rows, pooled rows): double-buffered; the copies of THIS item were issued one item ago
-    // (cp.async, 16 bytes each, zero-filled past the batch), so the item starts with one barrier and no global latency
+    // (cp.async, 16 bytes each, zero-filled past the batch), so the item starts without global latency.
+    // No rendezvous of the generator warps: the buffer's mbarrier completes when the copies of all 512 threads have
+    // landed, and the buffer being refilled (item it-1's) is free because no warp can be more than PAST chunks behind.
     if (it == 0) stage_item(item, 0);
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    named_bar_sync(1, NGENW * 32);                           // everyone's copies have landed, everyone is done with item it-1
     if (item + (int)gridDim.x < P.n_items) stage_item(item + (int)gridDim.x, (it + 1) & 1);
+    ok = mbar_wait(x_full + 8 * (it & 1), (uint32_t)((it >> 1) & 1)) && ok;
     const float* Xraw = Xr2 + (it & 1) * TCM * 13;
     const float* Pl = Pl2 + (it & 1) * ENVS * 208;
     if (32 * q >= rows_here) {
