@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256)
 pareto_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
               int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out,
               int B) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) float psm[];
   float* ts = psm;                        // [P][LD]   x_p W14          (the launch sizes the buffer for this P: a
   float* red = ts + P * LD;               // [4][LD]   per-slice sums     small front keeps many CTAs per SM)
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(256)
 pareto_small_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
                     int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out,
                     int B) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ float xs[PSMALL * 4];
   __shared__ float as[PSMALL * PSMALL];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -143,6 +145,7 @@ constexpr int P1_ENVS = 8;
 __global__ void __launch_bounds__(256)
 pareto_p1_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
                  const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out, int B) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the actor kernel may set itself up beside this one
   const int tid = threadIdx.x;
   if (tid >= LD) return;
   float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, bias = 0.f;
@@ -216,10 +219,14 @@ cudaError_t launch_pipe(tactor::tc::fused::Params& p, int M, int sms, cudaStream
   cfg.blockDim = dim3(tc::pipe::PTHREADS);
   cfg.dynamicSmemBytes = tc::pipe::pipe_smem_bytes<NODES, NCTA>();
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  // programmatic dependent launch: the kernel's set-up (TMEM, barriers, weights) runs beside the Pareto-branch kernel that
+  // precedes it; the generators wait (griddepcontrol.wait) before they touch its output or the state tensors
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (NCTA == 1) ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, tc::pipe::actor_pipe_kernel<NODES, NCTA>, p);
 }
 

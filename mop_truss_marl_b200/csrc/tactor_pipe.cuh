@@ -244,7 +244,10 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     // (cp.async, 16 bytes each, zero-filled past the batch), so the item starts without global latency.
     // No rendezvous of the generator warps: the buffer's mbarrier completes when the copies of all 512 threads have
     // landed, and the buffer being refilled (item it-1's) is free because no warp can be more than PAST chunks behind.
-    if (it == 0) stage_item(item, 0);
+    if (it == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");      // the Pareto-branch kernel (pooled) and everything before it are done
+      stage_item(item, 0);
+    }
     if (item + (int)gridDim.x < P.n_items) stage_item(item + (int)gridDim.x, (it + 1) & 1);
     ok = mbar_wait(x_full + 8 * (it & 1), (uint32_t)((it >> 1) & 1)) && ok;
     const float* Xraw = Xr2 + (it & 1) * TCM * 13;
