@@ -80,6 +80,11 @@ int64_t tactor_launch_count(tactor_handle_t h);
  * input; the outputs of that forward are not valid).  A reported condition is cleared. */
 int tactor_status(tactor_handle_t h);
 
+/* Hardware self-test of the one layout fact the generators of actor_pipe_kernel rely on beyond the PTX fragment tables:
+ * tcgen05.st.16x128b.x2 issued at lane offsets 0 and 16 of a warp's 32-lane TMEM window writes the mma accumulator
+ * fragment (lane / 4, lane % 4) to (TMEM lane, column) as documented in csrc/tactor_tc.cuh.  0 = holds on this device. */
+int tactor_selftest_tmem_layout(int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,8 @@ class _Inputs(C.Structure):
 
 
 ACTOR_EXPORTS = ("tactor_last_error", "tactor_create", "tactor_destroy", "tactor_set_weights", "tactor_forward", "tactor_act",
-                 "tactor_act_dev", "tactor_reserve_calls", "tactor_launch_count", "tactor_status")
+                 "tactor_act_dev", "tactor_reserve_calls", "tactor_launch_count", "tactor_status",
+                 "tactor_selftest_tmem_layout")
 
 _lib = capi.lib
 _lib.tactor_last_error.restype = C.c_char_p
@@ -36,6 +37,7 @@ _lib.tactor_act.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.c_void_p,
 _lib.tactor_launch_count.argtypes = [C.c_void_p]
 _lib.tactor_launch_count.restype = C.c_int64
 _lib.tactor_status.argtypes = [C.c_void_p]
+_lib.tactor_selftest_tmem_layout.argtypes = [C.c_int]
 
 
 def _check(rc):
@@ -45,6 +47,12 @@ def _check(rc):
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def selftest_tmem_layout(device: int = 0) -> None:
+    """raises unless ``tcgen05.st.16x128b`` places the mma accumulator fragment in tensor memory the way the actor kernel's
+    operand generators assume (hardware check, one tiny launch)"""
+    _check(_lib.tactor_selftest_tmem_layout(int(device)))
 
 
 class BatchedActor:

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
@@ -164,6 +165,37 @@ pareto_p1_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, c
   }
 }
 
+// tactor_selftest_tmem_layout: every warp stores a tagged accumulator-layout fragment with tcgen05.st.16x128b.x2 at lane
+// offsets 0 and 16 and reads its 32 lanes back with the row-per-thread shape (tcgen05.ld.32x32b.x8)
+__global__ void __launch_bounds__(128) tmem_layout_selftest_kernel(uint32_t* out) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&slot)), "n"(32) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t base = slot;
+  for (int mt = 0; mt < 2; ++mt) {
+    uint32_t v[4];
+    for (int i = 0; i < 4; ++i) v[i] = 0x1000000u | ((uint32_t)warp << 16) | ((uint32_t)mt << 12) | ((uint32_t)lane << 4) | (uint32_t)i;
+    tc::tmem_st_16x128b_x2(base + ((uint32_t)(32 * warp + 16 * mt) << 16), v);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  __syncwarp();
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(base + ((uint32_t)(32 * warp) << 16)));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  for (int i = 0; i < 8; ++i) out[(32 * warp + lane) * 8 + i] = r[i];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(32) : "memory");
+}
+
 constexpr int pareto_smem(int P) { return (P * LD + 4 * LD + P * P + P * 4) * 4; }
 constexpr int PARETO_SMEM = pareto_smem(50);
 
@@ -179,11 +211,13 @@ struct tactor_handle_s {
   float* d_b[TACTOR_NLAYERS] = {};     // [208]
   float* pooled = nullptr;             // [max_batch, 208] Pareto embedding
   float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
+  uint32_t* d_w1frag = nullptr;        // mma.sync A-fragment image of the three layer-1 kernels (tactor_pipe.cuh)
+  float* d_wscale_inv = nullptr;       // [NGEMM + 3] 1 / power-of-two scale of d_wimg[4 + g] and of the three layer-1 images
+  int variant = 0;                     // generator phases / epilogue warps of actor_pipe_kernel (TACTOR_VARIANT, A/B timing)
   int* d_error = nullptr;              // set by a kernel whose mbarrier wait timed out
   int ncta = 1;                        // CTAs per tcgen05 group (2 = CTA pair, cta_group::2)
   int sms = 0;                         // SM count of the device (persistent grid, tile splitting of the last wave); TACTOR_NO_SPLIT=1:
                                        // one CTA per unsplit tile
-  float wscale_inv[TACTOR_NLAYERS] = {};  // 1 / power-of-two scale folded into d_wimg[l] (f16 split), 1 otherwise
   std::atomic<int64_t> launches{0};
   uint64_t calls = 0;
 };
@@ -199,7 +233,7 @@ struct Guard {
   ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-template <int NODES, int NCTA>
+template <int NODES, int NCTA, int NPH, int NEPIW>
 cudaError_t launch_pipe(tactor::tc::fused::Params& p, int M, int sms, cudaStream_t st) {
   using namespace tactor;
   const int tiles = (M + tc::TCM - 1) / tc::TCM;
@@ -216,7 +250,7 @@ cudaError_t launch_pipe(tactor::tc::fused::Params& p, int M, int sms, cudaStream
   if (NCTA == 1 && sms > 0 && grid > sms) grid = sms;      // persistent: one CTA per SM walks the items
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(tc::pipe::PTHREADS);
+  cfg.blockDim = dim3((unsigned)tc::pipe::pipe_threads<NPH, NEPIW>());
   cfg.dynamicSmemBytes = tc::pipe::pipe_smem_bytes<NODES, NCTA>();
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -227,13 +261,34 @@ cudaError_t launch_pipe(tactor::tc::fused::Params& p, int M, int sms, cudaStream
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = (NCTA == 1) ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, tc::pipe::actor_pipe_kernel<NODES, NCTA>, p);
+  return cudaLaunchKernelEx(&cfg, tc::pipe::actor_pipe_kernel<NODES, NCTA, NPH, NEPIW>, p);
 }
 
-template <int NODES, int NCTA>
+template <int NODES, int NCTA, int NPH, int NEPIW>
 cudaError_t set_pipe_smem() {
-  return cudaFuncSetAttribute(tactor::tc::pipe::actor_pipe_kernel<NODES, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(tactor::tc::pipe::actor_pipe_kernel<NODES, NCTA, NPH, NEPIW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               tactor::tc::pipe::pipe_smem_bytes<NODES, NCTA>());
+}
+
+// Build variants of actor_pipe_kernel: (generator phases, epilogue warps).  0 is the production choice; the others are
+// kept for A/B timing (TACTOR_VARIANT).  The CTA-pair build exists for variant 0 only.
+template <int NODES>
+cudaError_t set_pipe_smem_variant(int ncta, int variant) {
+  if (ncta == 2) return set_pipe_smem<NODES, 2, 2, 8>();
+  switch (variant) {
+    case 1: return set_pipe_smem<NODES, 1, 3, 4>();
+    case 2: return set_pipe_smem<NODES, 1, 2, 4>();
+    default: return set_pipe_smem<NODES, 1, 2, 8>();
+  }
+}
+template <int NODES>
+cudaError_t launch_pipe_variant(int ncta, int variant, tactor::tc::fused::Params& p, int M, int sms, cudaStream_t st) {
+  if (ncta == 2) return launch_pipe<NODES, 2, 2, 8>(p, M, sms, st);
+  switch (variant) {
+    case 1: return launch_pipe<NODES, 1, 3, 4>(p, M, sms, st);
+    case 2: return launch_pipe<NODES, 1, 2, 4>(p, M, sms, st);
+    default: return launch_pipe<NODES, 1, 2, 8>(p, M, sms, st);
+  }
 }
 
 // (re)builds the device copies of the weights: packed [Kpad,208] kernels / [208] biases and the tcgen05 operand
@@ -258,18 +313,22 @@ cudaError_t upload_weights(tactor_handle_s* h, const tactor_weights* w) {
   // (exact).  Row k = 200 of the image (inside the zero-padded tail chunk) holds the bias: the generators feed a constant
   // 1 in column 200 of A.
   const int bn = tactor::tc::TCN / h->ncta;
-  for (int l = 0; l < TACTOR_NLAYERS; ++l) h->wscale_inv[l] = 1.f;
+  float wscale_inv[tactor::tc::fused::NGEMM + 3];
+  auto pow2_scale = [](float wmax, float& scale, float& inv) {     // largest 2^s with wmax 2^s < 2^14
+    int ex = 0;
+    if (wmax > 0.f) { frexpf(wmax, &ex); ex = 14 - ex; }            // wmax in [2^(e-1), 2^e): wmax * 2^(14-e) < 2^14
+    ex = ex > 24 ? 24 : (ex < -24 ? -24 : ex);
+    scale = ldexpf(1.f, ex);
+    inv = ldexpf(1.f, -ex);
+  };
   for (int l = 4; l <= 10 && e == cudaSuccess; ++l) {
     const int K = kIn[l], kout = kOut[l];
     float wmax = 0.f;
     for (size_t i = 0; i < (size_t)K * kout; ++i) wmax = fmaxf(wmax, fabsf(w->kernel[l][i]));
     for (int i = 0; i < kout; ++i) wmax = fmaxf(wmax, fabsf(w->bias[l][i]));
     if (!(wmax < INFINITY)) return cudaErrorInvalidValue;
-    int ex = 0;
-    if (wmax > 0.f) { frexpf(wmax, &ex); ex = 14 - ex; }           // wmax in [2^(e-1), 2^e): wmax * 2^(14-e) < 2^14
-    ex = ex > 24 ? 24 : (ex < -24 ? -24 : ex);
-    const float scale = ldexpf(1.f, ex);
-    h->wscale_inv[l] = ldexpf(1.f, -ex);
+    float scale;
+    pow2_scale(wmax, scale, wscale_inv[l - 4]);
     std::vector<__half> img;
     const int kpc = tactor::tc::KPC, nkb = tactor::tc::KCH / kpc;
     for (int c = 0; c * tactor::tc::KCH < K + 1; ++c)
@@ -289,6 +348,48 @@ cudaError_t upload_weights(tactor_handle_s* h, const tactor_weights* w) {
     if (!h->d_wimg[l]) e = cudaMalloc(&h->d_wimg[l], img.size() * sizeof(__half));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_wimg[l], img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice);
   }
+  // mma.sync A fragments of [W1k ; b1k]^T (the generators' layer-1 product X^T = relu([W1k ; b1k]^T . [Z, 1]^T)): per
+  // layer-1 kernel, per 16-feature chunk, [hi | lo][lane][a0..a3]; lane (g = lane / 4, t = lane % 4) holds
+  // a0 (feature g, c 2t..2t+1)  a1 (feature g+8, same c)  a2 (feature g, c 2t+8..)  a3 (feature g+8, c 2t+8..), c = 13 is
+  // the bias.  Scaled by a power of two like the hidden layers (the generator multiplies by 1/S, exact).
+  std::vector<uint32_t> frag((size_t)tactor::tc::pipe::W1F_WORDS, 0u);
+  for (int l = 0; l < 3 && e == cudaSuccess; ++l) {
+    const int kout = kOut[l];
+    float wmax = 0.f;
+    for (size_t i = 0; i < (size_t)13 * kout; ++i) wmax = fmaxf(wmax, fabsf(w->kernel[l][i]));
+    for (int i = 0; i < kout; ++i) wmax = fmaxf(wmax, fabsf(w->bias[l][i]));
+    if (!(wmax < INFINITY)) return cudaErrorInvalidValue;
+    float scale;
+    pow2_scale(wmax, scale, wscale_inv[tactor::tc::fused::NGEMM + l]);
+    auto we = [&](int c, int f) -> float {
+      if (f >= kout || c > 13) return 0.f;
+      return (c < 13 ? w->kernel[l][(size_t)c * kout + f] : w->bias[l][f]) * scale;
+    };
+    auto pack = [](float x0, float x1, uint32_t& hi, uint32_t& lo) {
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+      uint16_t b[4];
+      memcpy(&b[0], &h0, 2); memcpy(&b[1], &h1, 2); memcpy(&b[2], &l0, 2); memcpy(&b[3], &l1, 2);
+      hi = (uint32_t)b[0] | ((uint32_t)b[1] << 16);
+      lo = (uint32_t)b[2] | ((uint32_t)b[3] << 16);
+    };
+    for (int c = 0; c < tactor::tc::pipe::NCH; ++c)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane / 4, t = lane % 4, f0 = c * tactor::tc::KCH + g;
+        uint32_t* hi = &frag[(((size_t)l * tactor::tc::pipe::NCH + c) * 2 + 0) * 128 + (size_t)lane * 4];
+        uint32_t* lo = &frag[(((size_t)l * tactor::tc::pipe::NCH + c) * 2 + 1) * 128 + (size_t)lane * 4];
+        pack(we(2 * t, f0), we(2 * t + 1, f0), hi[0], lo[0]);
+        pack(we(2 * t, f0 + 8), we(2 * t + 1, f0 + 8), hi[1], lo[1]);
+        pack(we(2 * t + 8, f0), we(2 * t + 9, f0), hi[2], lo[2]);
+        pack(we(2 * t + 8, f0 + 8), we(2 * t + 9, f0 + 8), hi[3], lo[3]);
+      }
+  }
+  if (e == cudaSuccess && !h->d_w1frag) e = cudaMalloc(&h->d_w1frag, frag.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_w1frag, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice);
+  // the scales live in device memory: a CUDA graph that captured a forward of this handle (trollout_step_host) reads the
+  // values that belong to the weight images it replays with
+  if (e == cudaSuccess && !h->d_wscale_inv) e = cudaMalloc(&h->d_wscale_inv, sizeof(wscale_inv));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_wscale_inv, wscale_inv, sizeof(wscale_inv), cudaMemcpyHostToDevice);
   return e;
 }
 
@@ -314,11 +415,12 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   tc::fused::Params p{};
   p.x_n = in->x_n; p.A_n = in->A_n; p.A_s = in->A_s; p.A_ts = in->A_n_ts; p.A_cs = in->A_n_cs; p.pooled = pooled;
   for (int k = 0; k < 3; ++k) { p.w1[k] = h->d_w[k]; p.b1[k] = h->d_b[k]; }
-  for (int g = 0; g < tc::fused::NGEMM; ++g) { p.wimg[g] = h->d_wimg[4 + g]; p.bias[g] = h->d_b[4 + g]; p.wscale_inv[g] = h->wscale_inv[4 + g]; }
+  for (int g = 0; g < tc::fused::NGEMM; ++g) { p.wimg[g] = h->d_wimg[4 + g]; p.bias[g] = h->d_b[4 + g]; }
+  p.wscale_inv = h->d_wscale_inv; p.w1frag = h->d_w1frag;
   p.w_head[0] = h->d_w[11]; p.w_head[1] = h->d_w[12]; p.b_head[0] = h->d_b[11]; p.b_head[1] = h->d_b[12];
   p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error;
   p.noise = nz.on; p.mu = nz.mu; p.theta = nz.theta; p.sigma = nz.sigma; p.seed = nz.seed; p.call = nz.call; p.seed_call = nz.seed_call;
-  cudaError_t e = (h->ncta == 2) ? launch_pipe<NODES, 2>(p, M, h->sms, st) : launch_pipe<NODES, 1>(p, M, h->sms, st);
+  cudaError_t e = launch_pipe_variant<NODES>(h->ncta, h->variant, p, M, h->sms, st);
   h->launches.fetch_add(2);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -339,7 +441,8 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   tactor_handle_s* h = new (std::nothrow) tactor_handle_s();
   if (!h) return afail(TFEM_ERR_ARG, "out of host memory");
   h->device = device; h->nodes = nodes; h->max_batch = max_batch;
-  if (const char* v = getenv("TACTOR_NCTA")) h->ncta = (atoi(v) == 2) ? 2 : 1;     // development switch (A/B timing)
+  if (const char* v = getenv("TACTOR_NCTA")) h->ncta = (atoi(v) == 2) ? 2 : 1;     // development switches (A/B timing)
+  if (const char* v = getenv("TACTOR_VARIANT")) h->variant = atoi(v);
   Guard g(device);
   for (int l = 0; l < TACTOR_NLAYERS; ++l)
     if (!w->kernel[l] || !w->bias[l]) { tactor_destroy(h); return afail(TFEM_ERR_ARG, "missing layer weights"); }
@@ -348,10 +451,7 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   if (const char* v = getenv("TACTOR_NO_SPLIT")) { if (v[0] == '1') h->sms = 0; }
   if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4096);
   if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4096);
-  if (e == cudaSuccess) {
-    if (nodes == 16) e = (h->ncta == 2) ? set_pipe_smem<16, 2>() : set_pipe_smem<16, 1>();
-    else e = (h->ncta == 2) ? set_pipe_smem<32, 2>() : set_pipe_smem<32, 1>();
-  }
+  if (e == cudaSuccess) e = (nodes == 16) ? set_pipe_smem_variant<16>(h->ncta, h->variant) : set_pipe_smem_variant<32>(h->ncta, h->variant);
   if (e == cudaSuccess)
     e = (nodes == 16) ? cudaFuncSetAttribute(tactor::pareto_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM)
                       : cudaFuncSetAttribute(tactor::pareto_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM);
@@ -379,6 +479,8 @@ int tactor_destroy(tactor_handle_t h) {
   if (h->pooled) cudaFree(h->pooled);
   for (int l = 0; l < TACTOR_NLAYERS; ++l) if (h->d_wimg[l]) cudaFree(h->d_wimg[l]);
   if (h->d_error) cudaFree(h->d_error);
+  if (h->d_w1frag) cudaFree(h->d_w1frag);
+  if (h->d_wscale_inv) cudaFree(h->d_wscale_inv);
   delete h;
   return TFEM_OK;
 }
@@ -442,7 +544,35 @@ uint64_t tactor_reserve_calls(tactor_handle_t h, uint32_t n, int64_t replayed_la
 
 int64_t tactor_launch_count(tactor_handle_t h) { return h ? h->launches.load() : 0; }
 
-extern "C" int tactor_debug_dump(tactor_handle_t h, void* dst) { return (int)cudaMemcpy(dst, h->d_error, 4096, cudaMemcpyDeviceToHost); }
+int tactor_selftest_tmem_layout(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return afail(TFEM_ERR_CUDA, "no such CUDA device");
+  Guard g(device);
+  uint32_t* d = nullptr;
+  std::vector<uint32_t> hbuf(128 * 8, 0u);
+  cudaError_t e = cudaMalloc(&d, hbuf.size() * 4);
+  if (e == cudaSuccess) e = cudaMemset(d, 0, hbuf.size() * 4);
+  if (e == cudaSuccess) { tactor::tmem_layout_selftest_kernel<<<1, 128>>>(d); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(hbuf.data(), d, hbuf.size() * 4, cudaMemcpyDeviceToHost);
+  if (d) cudaFree(d);
+  if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("tmem self-test: ") + cudaGetErrorString(e));
+  // register i of lane (g = lane / 4, t = lane % 4) of block mt -> TMEM lane 16 mt + g + 8 (i & 1), column t + 4 (i >> 1)
+  for (int warp = 0; warp < 4; ++warp)
+    for (int mt = 0; mt < 2; ++mt)
+      for (int lane = 0; lane < 32; ++lane)
+        for (int i = 0; i < 4; ++i) {
+          const int row = 32 * warp + 16 * mt + lane / 4 + 8 * (i & 1), col = lane % 4 + 4 * (i >> 1);
+          const uint32_t want = 0x1000000u | ((uint32_t)warp << 16) | ((uint32_t)mt << 12) | ((uint32_t)lane << 4) | (uint32_t)i;
+          if (hbuf[row * 8 + col] != want) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "tcgen05.st.16x128b.x2 layout differs: warp %d block %d lane %d reg %d expected at (%d,%d), found 0x%x there",
+                     warp, mt, lane, i, row, col, hbuf[row * 8 + col]);
+            return afail(TFEM_ERR_UNSUPPORTED, msg);
+          }
+        }
+  return TFEM_OK;
+}
 
 int tactor_status(tactor_handle_t h) {
   if (!h) return afail(TFEM_ERR_ARG, "null argument");

@@ -155,6 +155,29 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- warp-level tensor-core pieces of the operand generators (tactor_pipe.cuh) -------------------------------
+// D (+)= A.B, m16n8k16, fp16 operands, fp32 accumulators (SASS HMMA.16816.F32).  Fragment ownership (g = lane / 4, t = lane % 4):
+//   A [16 x 16] row-major: a0 (row g, k 2t..2t+1)  a1 (row g+8, same k)  a2 (row g, k 2t+8..)  a3 (row g+8, k 2t+8..)
+//   B [16 x 8]  col-major: b0 (k 2t..2t+1, col g)  b1 (k 2t+8.., col g)
+//   C [16 x 8]           : c0 c1 (row g, cols 2t, 2t+1)  c2 c3 (row g+8, same cols)
+__device__ __forceinline__ void hmma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// three-term split product: c += (ahi + alo).(bhi + blo) without the lo.lo term
+__device__ __forceinline__ void hmma_split(float* c, const uint32_t* ahi, const uint32_t* alo, const uint32_t* bhi, const uint32_t* blo) {
+  hmma16816(c, ahi, bhi[0], bhi[1]);
+  hmma16816(c, ahi, blo[0], blo[1]);
+  hmma16816(c, alo, bhi[0], bhi[1]);
+}
+// 16 lanes x 8 columns of tensor memory from the mma accumulator layout: r0 (lane g, column t), r1 (lane g+8, column t),
+// r2 (lane g, column 4+t), r3 (lane g+8, column 4+t); the lane field of taddr is the first of the 16 lanes
+__device__ __forceinline__ void tmem_st_16x128b_x2(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+
 // counter-based standard normal for the OU noise: element i of tensor `stream_id` (1 = geo, 2 = topo) of call `call`
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -189,7 +212,11 @@ struct Params {
   const float* b1[3];     // [208]
   const float* wimg[NGEMM];
   const float* bias[NGEMM];
-  float wscale_inv[NGEMM]; // 1 / (power-of-two scale folded into wimg[g]); 1 for tf32
+  // 1 / (power-of-two scale folded into the fp16 operand images), in DEVICE memory so that a CUDA graph that captured
+  // this launch sees the values of the weights it replays with: [0, NGEMM) the seven hidden layers, [NGEMM, NGEMM + 3) the
+  // three layer-1 kernels (written by upload_weights next to the images themselves)
+  const float* wscale_inv;
+  const uint32_t* w1frag;  // [3][13 chunks][32 lanes][8]: mma.sync A fragments (hi a0..a3, lo a0..a3) of [W1k ; b1k]^T, pre-scaled
   const float* w_head[2]; // packed [208,208], first 2 / 3 columns used
   const float* b_head[2];
   float* geo;             // [B,N,2]

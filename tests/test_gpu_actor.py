@@ -211,3 +211,33 @@ def test_fp16_range_overflow_is_reported():
     torch.cuda.synchronize()
     with pytest.raises(capi.TfemError, match="fp16 range"):
         pol2.check()
+
+
+def test_tmem_store_layout_selftest():
+    """the generators write the mma accumulator fragment straight into tensor memory (tcgen05.st.16x128b.x2 at lane offsets
+    0 and 16): the layout the kernel assumes is checked on the device itself"""
+    from mop_truss_marl_b200 import actor
+    actor.selftest_tmem_layout(0)
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_generator_variants_match_production(variant, monkeypatch):
+    """TACTOR_VARIANT selects other (generator phases, epilogue warps) builds of the fused kernel, kept for A/B timing;
+    every row's arithmetic is the same in all of them, so the outputs must be bit-identical"""
+    from mop_truss_marl_b200 import actor, tf_checkpoint
+    w = tf_checkpoint.random_actor_weights(seed=11)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    r = lambda *s: torch.rand(*s, device="cuda", generator=g)   # noqa: E731
+    for nodes, B in ((16, 333), (32, 77)):
+        sc = 1.0 / nodes
+        inp = (r(B, nodes, 13), r(nodes, nodes) * sc, r(B, nodes, nodes) * sc, r(B, nodes, nodes) * sc, r(B, nodes, nodes) * sc,
+               r(B, 2, 4), r(B, 2, 2) * 0.3)
+        outs = []
+        for v in ("0", variant):
+            monkeypatch.setenv("TACTOR_VARIANT", v)
+            pol = actor.BatchedActor(w, nodes, B)
+            geo, topo = pol.forward(*inp)
+            torch.cuda.synchronize()
+            pol.check()
+            outs.append((geo.clone(), topo.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
