@@ -331,6 +331,8 @@ def main():
         bufs = [roll.alloc_host(), roll.alloc_host()]
         for k in STATE_IN:
             bufs[0][k].copy_(getattr(env, k))
+        torch.cuda.synchronize()
+        HostRollout.fill_compact(bufs[0])                   # the two live table columns travel as compact arrays
         x_p_host, A_p_host = x_p.cpu().pin_memory(), A_p.cpu().pin_memory()
         torch.cuda.synchronize()
         flip = [0]

@@ -101,6 +101,11 @@ typedef struct tfem_step_in {
   float* move_range;          /* [B,N,2]   in : max_up/max_down left on the model by the previous
                                            call (the reference's hidden state, :405,:410);
                                            out: the range set_moveRange() leaves behind (:557) */
+  /* The two table columns _set_model actually reads (:365, :369), as compact arrays.  When non-NULL they are read
+   * INSTEAD of set_node / set_element (which may then be NULL): a caller that keeps the state on the host uploads
+   * 4 (N + E) bytes per environment instead of the 4 (12 N + 21 E) of the full tables (trollout_step_host). */
+  const float* set_node_y;          /* [B,N]  = set_node[:, :, 1] */
+  const float* set_element_section; /* [B,E]  = set_element[:, :, 0] */
 } tfem_step_in;
 
 /* Everything _game_modify returns (point, St_S) plus the FP64 fields of the solved model.
@@ -124,6 +129,8 @@ typedef struct tfem_step_out {
   double* y;         /* [B,N]     node.coord[1] after the transition, as float(...) of what the reference holds */
   uint8_t* y_weak;   /* [B,N]     1 where the reference holds a python int/float (assigned by a constraint
                                   pass or a support), 0 where it holds an np.float32 */
+  float* node_y;          /* [B,N]  = nN_x_n[:, :, 1] of the child state (the next call's set_node_y) */
+  float* element_section; /* [B,E]  = nN_x_e[:, :, 0] of the child state (the next call's set_element_section) */
 } tfem_step_out;
 
 const char* tfem_version(void);

@@ -38,6 +38,12 @@ typedef struct trollout_state {
   float* nN_x_n;     /* [B,N,12] */
   float* nN_x_e;     /* [B,E,21] */
   float* move_range; /* [B,N,2]  the model's max_up/max_down left by the previous call (tfem_step_in.move_range) */
+  /* optional compact copies of the two table columns _set_model reads (truss2D_ENV.py:365, :369): node_y =
+   * nN_x_n[:, :, 1], element_section = nN_x_e[:, :, 0].  `out`: written when non-NULL.  `in`: when BOTH are non-NULL
+   * they are uploaded instead of the two full tables (4 (N + E) instead of 4 (12 N + 21 E) bytes per environment), and
+   * nN_x_n / nN_x_e of `in` are not read and may be NULL; otherwise the full tables go up as before. */
+  float* node_y;          /* [B,N] */
+  float* element_section; /* [B,E] */
 } trollout_state;
 
 typedef struct trollout_io {
@@ -64,8 +70,14 @@ int trollout_destroy(trollout_handle_t h);
 int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float mu, float theta, float sigma,
                        uint64_t seed);
 
-/* bytes moved per environment and step: host->device, device->host (for P Pareto rows) */
-int trollout_bytes_per_env(trollout_handle_t h, int P, size_t* h2d, size_t* d2h);
+/* bytes moved per environment and step: host->device, device->host (for P Pareto rows); compact_columns != 0: the
+ * parent tables travel as node_y / element_section and the child state carries them too */
+int trollout_bytes_per_env(trollout_handle_t h, int P, int compact_columns, size_t* h2d, size_t* d2h);
+
+/* Drops the CUDA graphs cached for the host buffers seen so far.  A cached graph replays copies against the raw host
+ * addresses it was captured with: call this before freeing (or un-pinning) buffers that were passed to
+ * trollout_step_host, or keep them alive and pinned for the lifetime of the handle. */
+int trollout_forget_buffers(trollout_handle_t h);
 
 #ifdef __cplusplus
 }

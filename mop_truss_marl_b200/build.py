@@ -39,5 +39,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+PEAKS_SRC = os.path.join(os.path.dirname(HERE), "scripts", "peaks.cu")
+PEAKS_BIN = os.path.join(LIB_DIR, "tfem_peaks")
+
+
+def build_peaks(force: bool = False) -> str:
+    """the pipe-peak microbenchmarks (FP64 FMA, DMMA, warp-level HMMA): a stand-alone binary run on the GPU box"""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    if force or _stale(PEAKS_BIN, [PEAKS_SRC]):
+        nvcc = os.environ.get("NVCC", "nvcc")
+        subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-o", PEAKS_BIN, PEAKS_SRC], check=True)
+    return PEAKS_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_peaks(force="--force" in sys.argv))

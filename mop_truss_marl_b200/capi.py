@@ -36,13 +36,14 @@ class Dims(C.Structure):
 
 class StepIn(C.Structure):
     _fields_ = [("set_node", C.c_void_p), ("set_element", C.c_void_p), ("a_geo", C.c_void_p),
-                ("a_topo", C.c_void_p), ("coin", C.c_void_p), ("move_range", C.c_void_p)]
+                ("a_topo", C.c_void_p), ("coin", C.c_void_p), ("move_range", C.c_void_p),
+                ("set_node_y", C.c_void_p), ("set_element_section", C.c_void_p)]
 
 
 class StepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "point", "point64", "d", "axial", "ratio", "U",
-        "reactions", "status", "y", "y_weak")]
+        "reactions", "status", "y", "y_weak", "node_y", "element_section")]
 
 
 # table ids (enum in tfem.h) -> (dtype, shape builder)

@@ -195,6 +195,8 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     const int q = warp & 3, ph = warp >> 2;
     const int g8 = lane >> 2, t4 = lane & 3;                 // mma fragment coordinates
     float amax = 0.f;                                        // largest |X|, |A.X| this thread split (f16 range check)
+    bool bad = false;                                        // an input / adjacency entry / Z outside the fp16 range, or NaN (the ReLU
+                                                             // behind Z would hide it from amax)
     // asynchronous copy of one item's x_n rows and pooled rows into buffer `buf` (all generator threads take part)
     auto stage_item = [&](int item_s, int buf) {
       int row0s, rows_s;
@@ -277,6 +279,10 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           v0 = __ldg(reinterpret_cast<const float2*>(p0)); v1 = __ldg(reinterpret_cast<const float2*>(p0 + 8 * NODES));
           v2 = __ldg(reinterpret_cast<const float2*>(p0 + 8)); v3 = __ldg(reinterpret_cast<const float2*>(p0 + 8 * NODES + 8));
         }
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v1.x), fabsf(v1.y))),
+                              fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v3.x), fabsf(v3.y))));
+        bad = bad || !(m <= F16_MAX) || (v0.x != v0.x) || (v0.y != v0.y) || (v1.x != v1.x) || (v1.y != v1.y) || (v2.x != v2.x) ||
+              (v2.y != v2.y) || (v3.x != v3.x) || (v3.y != v3.y);
         split2(v0.x, v0.y, hi[0], lo[0]); split2(v1.x, v1.y, hi[1], lo[1]);
         split2(v2.x, v2.y, hi[2], lo[2]); split2(v3.x, v3.y, hi[3], lo[3]);
       };
@@ -304,12 +310,17 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
             const int c = 8 * nt + g8;
             float x00 = 0.f, x01 = 0.f, x10 = 0.f, x11 = 0.f;
             if (c < 13) { x00 = xr[c]; x01 = xr[13 + c]; x10 = xr[8 * 13 + c]; x11 = xr[9 * 13 + c]; }
+            bad = bad || !(fabsf(x00) <= F16_MAX) || !(fabsf(x01) <= F16_MAX) || !(fabsf(x10) <= F16_MAX) || !(fabsf(x11) <= F16_MAX);
             uint32_t bhi[2], blo[2];
             split2(x00, x01, bhi[0], blo[0]);
             split2(x10, x11, bhi[1], blo[1]);
             hmma_split(z[nt], ahi, alo, bhi, blo);
           }
         }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bad = bad || !(fabsf(z[nt][i]) <= F16_MAX);
         if (t4 == 2) { z[1][1] = 1.f; z[1][3] = 1.f; }       // column c = 13
         split2(z[0][0], z[0][1], zfr[2 * mt][0][0], zfr[2 * mt][1][0]);
         split2(z[1][0], z[1][1], zfr[2 * mt][0][1], zfr[2 * mt][1][1]);
@@ -428,7 +439,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         hand_off();                                            // the accumulator of this GEMM must not wait for the next one
       }
     }  // items
-    if (!(amax <= F16_MAX) && P.error_flag) atomicOr(P.error_flag, 2);   // an activation left the fp16 range (or NaN input)
+    if ((bad || !(amax <= F16_MAX)) && P.error_flag) atomicOr(P.error_flag, 2);   // an activation left the fp16 range (or NaN input)
   } else if (warp < NGENW + NEPIW) {
     // =================================================== epilogue =============================================
     const int ew = warp - NGENW, q = ew & 3, half = ew >> 2;

@@ -171,9 +171,10 @@ int tfem_step(tfem_handle_t h, int B, const tfem_step_in* in, const tfem_step_ou
   if (!h || !in || !out) return fail(TFEM_ERR_ARG, "null argument");
   if (B < 0) return fail(TFEM_ERR_ARG, "negative batch");
   if (B == 0) return TFEM_OK;
-  if (!in->set_node || !in->set_element || !in->a_geo || !in->a_topo || !in->move_range)
-    return fail(TFEM_ERR_ARG, "set_node, set_element, a_geo, a_topo and move_range are required");
-  if (!aligned16(in->set_node) || !aligned16(in->set_element) || !aligned16(in->a_geo) ||
+  if ((!in->set_node && !in->set_node_y) || (!in->set_element && !in->set_element_section) || !in->a_geo || !in->a_topo ||
+      !in->move_range)
+    return fail(TFEM_ERR_ARG, "set_node (or set_node_y), set_element (or set_element_section), a_geo, a_topo and move_range are required");
+  if ((in->set_node && !aligned16(in->set_node)) || (in->set_element && !aligned16(in->set_element)) || !aligned16(in->a_geo) ||
       !aligned16(in->a_topo) || !aligned16(in->move_range))
     return fail(TFEM_ERR_ALIGN, "input buffers must be 16-byte aligned");
   if (int rc = check_out_alignment(out)) return rc;

@@ -174,9 +174,13 @@ tfem_step_kernel(const StepArgs args) {
   float in_y = 0.f, in_at0 = 0.f, in_at1 = 0.f, in_at2 = 0.f, in_sec[EPL];
   float2 in_mr = make_float2(0.f, 0.f), in_ag = make_float2(0.f, 0.f);
   int in_coin = 0;
+  // the two live columns of the parent tables: compact arrays when the caller has them, else column 1 / column 0
+  const float* const col_y = args.in.set_node_y ? args.in.set_node_y : args.in.set_node + 1;
+  const float* const col_sec = args.in.set_element_section ? args.in.set_element_section : args.in.set_element;
+  const int col_y_stride = args.in.set_node_y ? 1 : 12, col_sec_stride = args.in.set_element_section ? 1 : 21;
   auto fetch_inputs = [&](int b) {
     if (mode != MODE_STEP || b >= args.B) return;
-    in_y = args.in.set_node[((size_t)b * N + node) * 12 + 1];
+    in_y = col_y[((size_t)b * N + node) * col_y_stride];
     in_mr = reinterpret_cast<const float2*>(args.in.move_range)[(size_t)b * N + node];
     in_ag = reinterpret_cast<const float2*>(args.in.a_geo)[(size_t)b * N + node];
     const float* atp = args.in.a_topo + ((size_t)b * N + node) * 3;
@@ -184,7 +188,7 @@ tfem_step_kernel(const StepArgs args) {
 #pragma unroll
     for (int p = 0; p < EPL; ++p) {
       const int e = lane + 32 * p;
-      in_sec[p] = (e < E) ? args.in.set_element[((size_t)b * E + e) * 21] : 0.f;
+      in_sec[p] = (e < E) ? col_sec[((size_t)b * E + e) * col_sec_stride] : 0.f;
     }
     in_coin = args.in.coin ? (int)args.in.coin[b] : 0;
   };
@@ -559,6 +563,7 @@ tfem_step_kernel(const StepArgs args) {
         if (node_lane) dyn[k * N + node] = norm_f32(cols[k], mn, mx);
       }
       if (node_lane) {
+        if (args.out.node_y) args.out.node_y[(size_t)b * N + node] = y32o;
         float* rawd = dyn + 7 * N;
         rawd[0 * N + node] = y32o; rawd[1 * N + node] = up32; rawd[2 * N + node] = down32;
         rawd[3 * N + node] = x9; rawd[4 * N + node] = dy32; rawd[5 * N + node] = raw11;
@@ -615,6 +620,7 @@ tfem_step_kernel(const StepArgs args) {
         const double py = ratio[p];
         const float val = __double2float_rn(fmin(py, 1.0) * (py > 1.0 ? 1.0 : 0.5));
         el[EL_SEC * E + e] = (float)sec[p];
+        if (args.out.element_section) args.out.element_section[(size_t)b * E + e] = (float)sec[p];
         el[EL_A * E + e] = fam->sec_area32[sec[p]];
         el[EL_L * E + e] = __double2float_rn(eL[p]);
         el[EL_TENS * E + e] = comp ? 0.f : 1.f;

@@ -15,6 +15,7 @@ namespace {
 struct Dev {
   float *x_n = nullptr, *A_s = nullptr, *A_ts = nullptr, *A_cs = nullptr, *raw_n = nullptr, *raw_e = nullptr, *mr = nullptr;
   float *point = nullptr, *a_geo = nullptr, *a_topo = nullptr, *x_p = nullptr, *A_p = nullptr, *A_n = nullptr;
+  float *node_y = nullptr, *elem_sec = nullptr;     // compact live columns of the raw tables
   int32_t *status = nullptr, *n_pf = nullptr;
   uint8_t* coin = nullptr;
 };
@@ -91,6 +92,8 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
   if (e == cudaSuccess) e = dalloc(h, &h->d.raw_n, B * N * 12);
   if (e == cudaSuccess) e = dalloc(h, &h->d.raw_e, B * E * 21);
   if (e == cudaSuccess) e = dalloc(h, &h->d.mr, B * N * 2);
+  if (e == cudaSuccess) e = dalloc(h, &h->d.node_y, B * N);
+  if (e == cudaSuccess) e = dalloc(h, &h->d.elem_sec, B * E);
   if (e == cudaSuccess) e = dalloc(h, &h->d.point, B * 4);
   if (e == cudaSuccess) e = dalloc(h, &h->d.a_geo, B * N * 2);
   if (e == cudaSuccess) e = dalloc(h, &h->d.a_topo, B * N * 3);
@@ -144,12 +147,20 @@ int trollout_destroy(trollout_handle_t h) {
   return TFEM_OK;
 }
 
-int trollout_bytes_per_env(trollout_handle_t h, int P, size_t* h2d, size_t* d2h) {
+int trollout_bytes_per_env(trollout_handle_t h, int P, int compact_columns, size_t* h2d, size_t* d2h) {
   if (!h) return rfail(TFEM_ERR_ARG, "null argument");
   const size_t N = h->dims.N, E = h->dims.E;
-  const size_t state = 4 * (N * 13 + 3 * N * N + N * 12 + E * 21 + N * 2);
-  if (h2d) *h2d = state + 1 + 4 * ((size_t)P * 4 + (size_t)P * P);
-  if (d2h) *d2h = state + 4 * 4 + 4 + 4 * (N * 2 + N * 3);
+  const size_t graph = 4 * (N * 13 + 3 * N * N + N * 2), tables = 4 * (N * 12 + E * 21), cols = 4 * (N + E);
+  if (h2d) *h2d = graph + (compact_columns ? cols : tables) + 1 + 4 * ((size_t)P * 4 + (size_t)P * P);
+  if (d2h) *d2h = graph + tables + (compact_columns ? cols : 0) + 4 * 4 + 4 + 4 * (N * 2 + N * 3);
+  return TFEM_OK;
+}
+
+int trollout_forget_buffers(trollout_handle_t h) {
+  if (!h) return rfail(TFEM_ERR_ARG, "null argument");
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+  h->seen_once.clear();
   return TFEM_OK;
 }
 
@@ -161,7 +172,11 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
   const trollout_state &si = io->in, &so = io->out;
   const size_t N = h->dims.N, E = h->dims.E, P = (size_t)io->P;
   const Dev& d = h->d;
+  const bool compact = si.node_y && si.element_section;
   cudaError_t e = cudaSuccess;
+  // a failure in the middle of a step must not return while copies issued for earlier pieces still touch the
+  // caller's host buffers
+  auto drain = [&]() { cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_run); cudaStreamSynchronize(h->s_out); };
   auto up = [&](void* dst, const void* src, size_t bytes) {
     if (e == cudaSuccess && src) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->s_in);
   };
@@ -182,8 +197,13 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
     up(d.A_s + l * N * N, si.A_s + l * N * N, nb * N * N * 4);
     up(d.A_ts + l * N * N, si.A_n_ts + l * N * N, nb * N * N * 4);
     up(d.A_cs + l * N * N, si.A_n_cs + l * N * N, nb * N * N * 4);
-    up(d.raw_n + l * N * 12, si.nN_x_n + l * N * 12, nb * N * 12 * 4);
-    up(d.raw_e + l * E * 21, si.nN_x_e + l * E * 21, nb * E * 21 * 4);
+    if (compact) {                                   // only the two columns _set_model reads
+      up(d.node_y + l * N, si.node_y + l * N, nb * N * 4);
+      up(d.elem_sec + l * E, si.element_section + l * E, nb * E * 4);
+    } else {
+      up(d.raw_n + l * N * 12, si.nN_x_n + l * N * 12, nb * N * 12 * 4);
+      up(d.raw_e + l * E * 21, si.nN_x_e + l * E * 21, nb * E * 21 * 4);
+    }
     up(d.mr + l * N * 2, si.move_range + l * N * 2, nb * N * 2 * 4);
     up(d.x_p + l * P * 4, io->x_p + l * P * 4, nb * P * 4 * 4);
     up(d.A_p + l * P * P, io->A_p + l * P * P, nb * P * P * 4);
@@ -202,15 +222,18 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
                                       ctr_dev, (uint32_t)piece_idx, h->s_run)
                      : tactor_act(h->actor, (int)nb, &ai, d.a_geo + l * N * 2, d.a_topo + l * N * 3, mu, theta, sigma, seed,
                                   h->s_run);
-    if (rc != TFEM_OK) return rfail(rc, std::string("rollout: ") + tactor_last_error());
+    if (rc != TFEM_OK) { if (!ctr_dev) drain(); return rfail(rc, std::string("rollout: ") + tactor_last_error()); }
     tfem_step_in in{};
+    if (compact) { in.set_node_y = d.node_y + l * N; in.set_element_section = d.elem_sec + l * E; }
     in.set_node = d.raw_n + l * N * 12; in.set_element = d.raw_e + l * E * 21; in.a_geo = d.a_geo + l * N * 2;
     in.a_topo = d.a_topo + l * N * 3; in.coin = io->coin ? d.coin + l : nullptr; in.move_range = d.mr + l * N * 2;
     tfem_step_out o{};
     o.x_n = d.x_n + l * N * 13; o.A_s = d.A_s + l * N * N; o.A_n_ts = d.A_ts + l * N * N; o.A_n_cs = d.A_cs + l * N * N;
     o.nN_x_n = d.raw_n + l * N * 12; o.nN_x_e = d.raw_e + l * E * 21; o.point = d.point + l * 4; o.status = d.status + l;
+    if (so.node_y) o.node_y = d.node_y + l * N;
+    if (so.element_section) o.element_section = d.elem_sec + l * E;
     rc = tfem_step(h->env, (int)nb, &in, &o, h->s_run);
-    if (rc != TFEM_OK) return rfail(rc, std::string("rollout: ") + tfem_last_error());
+    if (rc != TFEM_OK) { if (!ctr_dev) drain(); return rfail(rc, std::string("rollout: ") + tfem_last_error()); }
     e = cudaEventRecord(h->ev_run[piece_idx], h->s_run);
     if (h->timeline && !ctr_dev) cudaEventRecord(h->tl[1 + 4 * piece_idx + 1], h->s_run);
     // ---- download ----
@@ -222,6 +245,8 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
     down(so.nN_x_n ? so.nN_x_n + l * N * 12 : nullptr, d.raw_n + l * N * 12, nb * N * 12 * 4);
     down(so.nN_x_e ? so.nN_x_e + l * E * 21 : nullptr, d.raw_e + l * E * 21, nb * E * 21 * 4);
     down(so.move_range ? so.move_range + l * N * 2 : nullptr, d.mr + l * N * 2, nb * N * 2 * 4);
+    down(so.node_y ? so.node_y + l * N : nullptr, d.node_y + l * N, nb * N * 4);
+    down(so.element_section ? so.element_section + l * E : nullptr, d.elem_sec + l * E, nb * E * 4);
     down(io->point ? io->point + l * 4 : nullptr, d.point + l * 4, nb * 4 * 4);
     down(io->status ? io->status + l : nullptr, d.status + l, nb * 4);
     down(io->a_geo ? io->a_geo + l * N * 2 : nullptr, d.a_geo + l * N * 2, nb * N * 2 * 4);
@@ -233,7 +258,10 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
     if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_in, h->ev_join, 0);
   }
   if (pieces_out) *pieces_out = piece_idx;
-  if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout step: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    if (!ctr_dev) drain();
+    return rfail(TFEM_ERR_CUDA, std::string("rollout step: ") + cudaGetErrorString(e));
+  }
   return TFEM_OK;
 }
 
@@ -250,8 +278,10 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
   if (B < 0 || B > h->max_batch) return rfail(TFEM_ERR_ARG, "batch exceeds max_batch");
   if (B == 0) return TFEM_OK;
   const trollout_state &si = io->in, &so = io->out;
-  if (!si.x_n || !si.A_s || !si.A_n_ts || !si.A_n_cs || !si.nN_x_n || !si.nN_x_e || !si.move_range || !io->x_p || !io->A_p)
-    return rfail(TFEM_ERR_ARG, "the parent state tuple, x_p and A_p are required");
+  const bool compact_in = si.node_y && si.element_section;
+  if (!si.x_n || !si.A_s || !si.A_n_ts || !si.A_n_cs || (!compact_in && (!si.nN_x_n || !si.nN_x_e)) || !si.move_range ||
+      !io->x_p || !io->A_p)
+    return rfail(TFEM_ERR_ARG, "the parent state tuple (tables or their compact columns), x_p and A_p are required");
   if (io->P < 1 || io->P > PMAX) return rfail(TFEM_ERR_ARG, "P must be in 1..50");
   int prev_dev = -1;
   cudaGetDevice(&prev_dev);
@@ -260,9 +290,10 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
   if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout step: ") + cudaGetErrorString(e));
 
   // ---- graph path: same pinned buffers as the captured step -> one cudaGraphLaunch instead of ~30 API calls a piece ----
-  const void* ptrs[] = {si.x_n, si.A_s, si.A_n_ts, si.A_n_cs, si.nN_x_n, si.nN_x_e, si.move_range, io->coin, io->x_p, io->A_p,
-                        io->n_pf, so.x_n, so.A_s, so.A_n_ts, so.A_n_cs, so.nN_x_n, so.nN_x_e, so.move_range, io->point,
-                        io->status, io->a_geo, io->a_topo};
+  const void* ptrs[] = {si.x_n, si.A_s, si.A_n_ts, si.A_n_cs, compact_in ? nullptr : si.nN_x_n, compact_in ? nullptr : si.nN_x_e,
+                        si.move_range, si.node_y, si.element_section, io->coin, io->x_p, io->A_p,
+                        io->n_pf, so.x_n, so.A_s, so.A_n_ts, so.A_n_cs, so.nN_x_n, so.nN_x_e, so.move_range, so.node_y,
+                        so.element_section, io->point, io->status, io->a_geo, io->a_topo};
   const bool noise = !(sigma == 0.f && theta == 0.f);
   if (h->use_graph) {
     std::vector<uintptr_t> key;
@@ -311,6 +342,16 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
             hit = &h->graphs.back();
           }
         }
+      }
+    }
+    if (hit) {
+      // the graph's copy nodes were captured for pinned memory: a buffer that was freed and whose address now belongs
+      // to a pageable allocation must not be replayed against
+      bool still_pinned = true;
+      for (const void* p : ptrs) still_pinned = still_pinned && pinned(p);
+      if (!still_pinned) {
+        trollout_forget_buffers(h);
+        hit = nullptr;
       }
     }
     if (hit) {

@@ -17,12 +17,15 @@ from . import capi
 
 STATE_IN = ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range")
 STATE_OUT = ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range", "point", "status")
+# compact copies of the two table columns ``_set_model`` reads (``nN_x_n[:, :, 1]``, ``nN_x_e[:, :, 0]``): a state tuple
+# that carries them uploads 208 instead of 3 792 bytes per small environment for the two raw tables
+COMPACT = ("node_y", "element_section")
 ROLLOUT_EXPORTS = ("trollout_last_error", "trollout_create", "trollout_destroy", "trollout_step_host",
-                   "trollout_bytes_per_env")
+                   "trollout_bytes_per_env", "trollout_forget_buffers")
 
 
 class _State(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in STATE_IN]
+    _fields_ = [(k, C.c_void_p) for k in STATE_IN + COMPACT]
 
 
 class _IO(C.Structure):
@@ -36,7 +39,8 @@ _lib.trollout_last_error.restype = C.c_char_p
 _lib.trollout_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
 _lib.trollout_destroy.argtypes = [C.c_void_p]
 _lib.trollout_step_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(_IO), C.c_float, C.c_float, C.c_float, C.c_uint64]
-_lib.trollout_bytes_per_env.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+_lib.trollout_bytes_per_env.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+_lib.trollout_forget_buffers.argtypes = [C.c_void_p]
 
 
 def _check(rc):
@@ -73,17 +77,31 @@ class HostRollout:
         except Exception:
             pass
 
-    def alloc_host(self):
-        """pinned host buffers for one state tuple (+ point, status, actions)"""
+    def alloc_host(self, compact: bool = True):
+        """pinned host buffers for one state tuple (+ point, status, actions); ``compact``: also the compact copies of
+        the two live table columns (``COMPACT``), which the next step uploads instead of the full raw tables"""
         env = self.env
         h = {k: torch.empty(getattr(env, k).shape, dtype=getattr(env, k).dtype).pin_memory() for k in STATE_OUT}
         h["a_geo"] = torch.empty(env.B, env.N, 2).pin_memory()
         h["a_topo"] = torch.empty(env.B, env.N, 3).pin_memory()
+        if compact:
+            h["node_y"] = torch.empty(env.B, env.N).pin_memory()
+            h["element_section"] = torch.empty(env.B, env.E).pin_memory()
         return h
 
-    def bytes_per_step(self, P: int = 1):
+    @staticmethod
+    def fill_compact(state_host: dict):
+        """(re)derive the compact columns of a host state tuple from its raw tables (after the caller edited them)"""
+        state_host["node_y"].copy_(state_host["nN_x_n"][:, :, 1])
+        state_host["element_section"].copy_(state_host["nN_x_e"][:, :, 0])
+
+    def forget_buffers(self):
+        """drop the CUDA graphs cached for host buffers seen so far (call before freeing such buffers)"""
+        _check(_lib.trollout_forget_buffers(self._h))
+
+    def bytes_per_step(self, P: int = 1, compact: bool = True):
         a, b = C.c_size_t(), C.c_size_t()
-        _check(_lib.trollout_bytes_per_env(self._h, int(P), C.byref(a), C.byref(b)))
+        _check(_lib.trollout_bytes_per_env(self._h, int(P), 1 if compact else 0, C.byref(a), C.byref(b)))
         return a.value * self.env.B, b.value * self.env.B
 
     def step(self, state_host: dict, coin_host, x_p_host: torch.Tensor, A_p_host: torch.Tensor, out_host: dict,
@@ -103,9 +121,17 @@ class HostRollout:
                 raise ValueError("expected a contiguous host %s tensor of shape %s" % (dtype, shape))
             return _hp(t)
         io = _IO()
+        shapes["node_y"], shapes["element_section"] = (B, N), (B, E)
+        compact_in = all(k in state_host for k in COMPACT)
         for k in STATE_IN:
-            setattr(io.inp, k, chk(state_host[k], shapes[k]))
+            if not (compact_in and k in ("nN_x_n", "nN_x_e")):     # not read when the compact columns travel
+                setattr(io.inp, k, chk(state_host[k], shapes[k]))
             setattr(io.out, k, chk(out_host[k], shapes[k]))
+        for k in COMPACT:
+            if compact_in:
+                setattr(io.inp, k, chk(state_host[k], shapes[k]))
+            if k in out_host:
+                setattr(io.out, k, chk(out_host[k], shapes[k]))
         io.coin = chk(coin_host, (B,), torch.uint8) if coin_host is not None else C.c_void_p(0)
         io.x_p, io.A_p, io.P = chk(x_p_host, (B, P, 4)), chk(A_p_host, (B, P, P)), P
         io.n_pf = chk(n_pf_host, (B,), torch.int32) if n_pf_host is not None else C.c_void_p(0)

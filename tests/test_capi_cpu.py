@@ -43,7 +43,7 @@ def test_exports_match_header():
 
 def test_struct_sizes():
     assert C.sizeof(capi.FamilyDesc) == 16 + 8 * (15 + 1 + 16 + 2 + 5 + 5 + 2)
-    assert C.sizeof(capi.StepIn) == 6 * 8 and C.sizeof(capi.StepOut) == 16 * 8 and C.sizeof(capi.Dims) == 32
+    assert C.sizeof(capi.StepIn) == 8 * 8 and C.sizeof(capi.StepOut) == 18 * 8 and C.sizeof(capi.Dims) == 32
 
 
 @pytest.mark.parametrize("name", FAMILY_NAMES)

@@ -223,7 +223,8 @@ def test_tmem_store_layout_selftest():
 @pytest.mark.parametrize("variant", ["1", "2"])
 def test_generator_variants_match_production(variant, monkeypatch):
     """TACTOR_VARIANT selects other (generator phases, epilogue warps) builds of the fused kernel, kept for A/B timing;
-    every row's arithmetic is the same in all of them, so the outputs must be bit-identical"""
+    the hidden layers are the same arithmetic in all of them, only the head's 200-term sum is split differently between
+    one and two epilogue warps per row group"""
     from mop_truss_marl_b200 import actor, tf_checkpoint
     w = tf_checkpoint.random_actor_weights(seed=11)
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -240,4 +241,4 @@ def test_generator_variants_match_production(variant, monkeypatch):
             torch.cuda.synchronize()
             pol.check()
             outs.append((geo.clone(), topo.clone()))
-        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert float((outs[0][0] - outs[1][0]).abs().max()) <= 1e-6 and float((outs[0][1] - outs[1][1]).abs().max()) <= 1e-6

@@ -7,8 +7,12 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-@pytest.mark.parametrize("family,B,pieces", [("small_bridge", 77, 3), ("large_roof", 70, 2), ("small_roof", 8, 1)])
-def test_host_rollout_equals_resident_path(family, B, pieces):
+@pytest.mark.parametrize("family,B,pieces,compact", [("small_bridge", 77, 3, True), ("large_roof", 70, 2, True),
+                                                     ("small_roof", 8, 1, True), ("small_bridge", 77, 3, False),
+                                                     ("large_bridge", 40, 2, False)])
+def test_host_rollout_equals_resident_path(family, B, pieces, compact):
+    """compact: the state tuple carries node_y / element_section (the two table columns _set_model reads) and uploads
+    those instead of the full raw tables; without them the full tables go up.  Same bits either way."""
     from mop_truss_marl_b200 import actor, batched_env, tf_checkpoint
     from mop_truss_marl_b200.host_pipeline import HostRollout, STATE_IN, STATE_OUT
     w = tf_checkpoint.random_actor_weights(seed=11)
@@ -24,10 +28,14 @@ def test_host_rollout_equals_resident_path(family, B, pieces):
     x_p_host, A_p_host = x_p.cpu().pin_memory(), A_p.cpu().pin_memory()
     roll = HostRollout(envs[1], pols[1], pieces=pieces)
     assert len(roll.ranges) == pieces and roll.ranges[0][0] == 0 and roll.ranges[-1][1] == B
-    bufs = [roll.alloc_host(), roll.alloc_host()]
+    bufs = [roll.alloc_host(compact), roll.alloc_host(compact)]
     for k in STATE_IN:
         bufs[0][k].copy_(getattr(envs[1], k))
     torch.cuda.synchronize()
+    if compact:
+        HostRollout.fill_compact(bufs[0])
+        for k in ("nN_x_n", "nN_x_e"):                  # not read on this path: poison them to prove it
+            bufs[0][k].fill_(float("nan"))
     rng = np.random.RandomState(5)
     for it in range(4):
         coin = torch.from_numpy((rng.rand(B) >= 0.5).astype(np.uint8))
@@ -44,8 +52,11 @@ def test_host_rollout_equals_resident_path(family, B, pieces):
         assert torch.equal(dst["a_geo"], a_geo.cpu()) and torch.equal(dst["a_topo"], a_topo.cpu())
         assert torch.all((dst["a_geo"] >= 0) & (dst["a_geo"] <= 1))            # clipped in place by the step
         assert a_geo_in.shape == a_geo.shape
-    h2d, d2h = roll.bytes_per_step()
-    assert h2d > 0 and d2h > h2d
+        if compact:
+            assert torch.equal(dst["node_y"], dst["nN_x_n"][:, :, 1]) and torch.equal(dst["element_section"], dst["nN_x_e"][:, :, 0])
+    h2d, d2h = roll.bytes_per_step(compact=compact)
+    h2d_full, d2h_full = roll.bytes_per_step(compact=False)
+    assert h2d > 0 and d2h > h2d and h2d_full >= h2d and (not compact or h2d_full - h2d == 4 * B * (11 * N + 20 * envs[0].E))
 
 
 @pytest.mark.parametrize("family,B,pieces", [("small_bridge", 200, 4), ("large_bridge", 96, 2)])
@@ -66,6 +77,8 @@ def test_graph_replay_equals_direct_enqueue(family, B, pieces, monkeypatch):
         b = [roll.alloc_host(), roll.alloc_host()]
         for k in STATE_IN:
             b[0][k].copy_(getattr(env, k))
+        torch.cuda.synchronize()
+        HostRollout.fill_compact(b[0])
         rolls.append(roll); bufs.append(b); envs.append(env); pols.append(pol)
     torch.cuda.synchronize()
     x_p = torch.tensor([1.0, 1.0, 1.0, 1.0 / 50]).repeat(B, 1, 1).contiguous().pin_memory()
@@ -86,6 +99,49 @@ def test_graph_replay_equals_direct_enqueue(family, B, pieces, monkeypatch):
     assert all(p == (pieces, 2 * pieces) for p in per_step), per_step
     assert int(bufs[0][0]["status"].abs().max()) == 0
     pols[0].check()
+
+
+def test_graph_replay_follows_set_weights(monkeypatch):
+    """a CUDA graph captured by trollout_step_host must act with the weights of the moment it is REPLAYED: the power-of-two
+    scales of the fp16 operand images are read from device memory, so tactor_set_weights with 4x larger weights (every
+    layer's scale exponent changes) is seen by the replayed kernels exactly as by directly enqueued ones"""
+    from mop_truss_marl_b200 import actor, batched_env, tf_checkpoint
+    from mop_truss_marl_b200.host_pipeline import HostRollout, STATE_IN, STATE_OUT
+    family, B = "small_bridge", 96
+    w0 = tf_checkpoint.random_actor_weights(seed=5)
+    w1 = {k: (v[0] * 4.0, v[1] * 4.0) for k, v in tf_checkpoint.random_actor_weights(seed=6).items()}
+    rolls, bufs, pols = [], [], []
+    for use_graph in (True, False):
+        monkeypatch.setenv("TROLLOUT_NO_GRAPH", "0" if use_graph else "1")
+        env = batched_env.BatchedTrussEnv(family, B)
+        env.reset()
+        pol = actor.BatchedActor(w0, env.N, B, sigma=0.0, theta=0.0)
+        roll = HostRollout(env, pol, pieces=2)
+        b = [roll.alloc_host(), roll.alloc_host()]
+        for k in STATE_IN:
+            b[0][k].copy_(getattr(env, k))
+        torch.cuda.synchronize()
+        HostRollout.fill_compact(b[0])
+        rolls.append(roll); bufs.append(b); pols.append(pol)
+    x_p = torch.tensor([1.0, 1.0, 1.0, 1.0 / 50]).repeat(B, 1, 1).contiguous().pin_memory()
+    A_p = torch.ones(B, 1, 1).pin_memory()
+    coin = torch.zeros(B, dtype=torch.uint8).pin_memory()
+    for it in range(10):
+        if it == 6:                                         # both buffer sets have been captured by now
+            for pol in pols:
+                pol.set_weights(w1)
+        for r in range(2):
+            rolls[r].step(bufs[r][it & 1], coin, x_p, A_p, bufs[r][1 - (it & 1)])
+        torch.cuda.synchronize()
+        for k in STATE_OUT + ("a_geo", "a_topo"):
+            assert torch.equal(bufs[0][1 - (it & 1)][k], bufs[1][1 - (it & 1)][k]), (it, k)
+        if it == 5:
+            before = bufs[0][1 - (it & 1)]["a_geo"].clone()
+    assert not torch.equal(before, bufs[0][0]["a_geo"])     # the new weights really act
+    rolls[0].forget_buffers()
+    rolls[0].step(bufs[0][0], coin, x_p, A_p, bufs[0][1])   # works after the cached graphs were dropped
+    for pol in pols:
+        pol.check()
 
 
 @pytest.mark.parametrize("family,B", [("small_bridge", 1024), ("large_roof", 256)])
