@@ -39,6 +39,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+PROF_LIB_PATH = os.path.join(LIB_DIR, "libtfem_prof.so")
+
+
+def build_prof() -> str:
+    """development build with the actor kernel's per-warp cycle counters (-DTACTOR_PROF); used through TFEM_LIB by
+    scripts/actor_prof.py, never by the product path"""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.run([os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-DTACTOR_PROF", "-o", PROF_LIB_PATH] + srcs, check=True)
+    return PROF_LIB_PATH
+
+
 PEAKS_SRC = os.path.join(os.path.dirname(HERE), "scripts", "peaks.cu")
 PEAKS_BIN = os.path.join(LIB_DIR, "tfem_peaks")
 
@@ -55,3 +67,5 @@ def build_peaks(force: bool = False) -> str:
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_peaks(force="--force" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build_prof())

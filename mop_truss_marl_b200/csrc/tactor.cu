@@ -213,6 +213,7 @@ struct tactor_handle_s {
   float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
   uint32_t* d_w1frag = nullptr;        // mma.sync A-fragment image of the three layer-1 kernels (tactor_pipe.cuh)
   float* d_wscale_inv = nullptr;       // [NGEMM + 3] 1 / power-of-two scale of d_wimg[4 + g] and of the three layer-1 images
+  int dev_flags = 0;                   // TACTOR_FLAGS (development switches of the actor kernel)
   int variant = 0;                     // generator phases / epilogue warps of actor_pipe_kernel (TACTOR_VARIANT, A/B timing)
   int* d_error = nullptr;              // set by a kernel whose mbarrier wait timed out
   int ncta = 1;                        // CTAs per tcgen05 group (2 = CTA pair, cta_group::2)
@@ -278,6 +279,8 @@ cudaError_t set_pipe_smem_variant(int ncta, int variant) {
   switch (variant) {
     case 1: return set_pipe_smem<NODES, 1, 3, 4>();
     case 2: return set_pipe_smem<NODES, 1, 2, 4>();
+    case 3: return set_pipe_smem<NODES, 1, 3, 8>();
+    case 4: return set_pipe_smem<NODES, 1, 4, 4>();
     default: return set_pipe_smem<NODES, 1, 2, 8>();
   }
 }
@@ -287,6 +290,8 @@ cudaError_t launch_pipe_variant(int ncta, int variant, tactor::tc::fused::Params
   switch (variant) {
     case 1: return launch_pipe<NODES, 1, 3, 4>(p, M, sms, st);
     case 2: return launch_pipe<NODES, 1, 2, 4>(p, M, sms, st);
+    case 3: return launch_pipe<NODES, 1, 3, 8>(p, M, sms, st);
+    case 4: return launch_pipe<NODES, 1, 4, 4>(p, M, sms, st);
     default: return launch_pipe<NODES, 1, 2, 8>(p, M, sms, st);
   }
 }
@@ -418,7 +423,7 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   for (int g = 0; g < tc::fused::NGEMM; ++g) { p.wimg[g] = h->d_wimg[4 + g]; p.bias[g] = h->d_b[4 + g]; }
   p.wscale_inv = h->d_wscale_inv; p.w1frag = h->d_w1frag;
   p.w_head[0] = h->d_w[11]; p.w_head[1] = h->d_w[12]; p.b_head[0] = h->d_b[11]; p.b_head[1] = h->d_b[12];
-  p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error;
+  p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error; p.dev_flags = h->dev_flags;
   p.noise = nz.on; p.mu = nz.mu; p.theta = nz.theta; p.sigma = nz.sigma; p.seed = nz.seed; p.call = nz.call; p.seed_call = nz.seed_call;
   cudaError_t e = launch_pipe_variant<NODES>(h->ncta, h->variant, p, M, h->sms, st);
   h->launches.fetch_add(2);
@@ -443,14 +448,15 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   h->device = device; h->nodes = nodes; h->max_batch = max_batch;
   if (const char* v = getenv("TACTOR_NCTA")) h->ncta = (atoi(v) == 2) ? 2 : 1;     // development switches (A/B timing)
   if (const char* v = getenv("TACTOR_VARIANT")) h->variant = atoi(v);
+  if (const char* v = getenv("TACTOR_FLAGS")) h->dev_flags = atoi(v);
   Guard g(device);
   for (int l = 0; l < TACTOR_NLAYERS; ++l)
     if (!w->kernel[l] || !w->bias[l]) { tactor_destroy(h); return afail(TFEM_ERR_ARG, "missing layer weights"); }
   cudaError_t e = upload_weights(h, w);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
   if (const char* v = getenv("TACTOR_NO_SPLIT")) { if (v[0] == '1') h->sms = 0; }
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 4096);
-  if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 4096);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 16384);
+  if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 16384);
   if (e == cudaSuccess) e = (nodes == 16) ? set_pipe_smem_variant<16>(h->ncta, h->variant) : set_pipe_smem_variant<32>(h->ncta, h->variant);
   if (e == cudaSuccess)
     e = (nodes == 16) ? cudaFuncSetAttribute(tactor::pareto_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM)
@@ -586,5 +592,17 @@ int tactor_status(tactor_handle_t h) {
   if (flag & 2) return afail(TFEM_ERR_UNSUPPORTED, "an activation left the fp16 range of the split tensor-core product (|A.X| > 65504 or NaN input)");
   return TFEM_OK;
 }
+
+#ifdef TACTOR_PROF
+// development build only (python -m mop_truss_marl_b200.build --prof -> lib/libtfem_prof.so, scripts/actor_prof.py): the
+// per-warp cycle counters CTA 0 of the last actor_pipe_kernel launch left behind the error flag
+int tactor_prof_read(tactor_handle_t h, long long* out, int n) {
+  if (!h || !out || n < 0 || n > 2000) return afail(TFEM_ERR_ARG, "bad argument");
+  Guard g(h->device);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, h->d_error + 32, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? TFEM_OK : afail(TFEM_ERR_CUDA, cudaGetErrorString(e));
+}
+#endif
 
 }  // extern "C"

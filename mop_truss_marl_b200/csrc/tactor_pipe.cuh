@@ -82,6 +82,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// -DTACTOR_PROF: per-warp wait / work cycle counters of CTA 0 (development build only: python -m mop_truss_marl_b200.build
+// --prof, scripts/actor_prof.py); the counters land behind the error flag: [warp][8] long long at error_flag + 32 ints
+#ifdef TACTOR_PROF
+#define PROF_DECL long long prof_c[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_start = clock64();
+#define PROF_WAIT(slot, expr) do { const long long t0_ = clock64(); expr; prof_c[slot] += clock64() - t0_; } while (0)
+#define PROF_ADD(slot, v) prof_c[slot] += (v)
+#define PROF_NOW() clock64()
+#define PROF_FLUSH() do { if (blockIdx.x == 0 && lane == 0 && P.error_flag) { prof_c[7] = clock64() - prof_start; \
+    long long* dst_ = reinterpret_cast<long long*>(P.error_flag + 32) + warp * 8; for (int i_ = 0; i_ < 8; ++i_) dst_[i_] = prof_c[i_]; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_WAIT(slot, expr) do { expr; } while (0)
+#define PROF_ADD(slot, v) do { } while (0)
+#define PROF_NOW() 0ll
+#define PROF_FLUSH() do { } while (0)
+#endif
+
 template <int NODES, int NCTA, int NPH, int NEPIW>
 __global__ void __launch_bounds__(pipe_threads<NPH, NEPIW>(), 1)
 actor_pipe_kernel(const __grid_constant__ Params P) {
@@ -186,6 +203,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   bool ok = true;
+  PROF_DECL
   // programmatic dependent launch: the env-step kernel that follows in the stream may be scheduled as soon as SMs free up
   // (it waits in griddepcontrol.wait for this grid to finish before it reads the actions)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -245,7 +263,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         stage_item(item, 0);
       }
       if (item + (int)gridDim.x < P.n_items) stage_item(item + (int)gridDim.x, (it + 1) & 1);
-      ok = mbar_wait(x_full + 8 * (it & 1), (uint32_t)((it >> 1) & 1)) && ok;
+      PROF_WAIT(0, ok = mbar_wait(x_full + 8 * (it & 1), (uint32_t)((it >> 1) & 1)) && ok);
       const float* Xraw = Xr2 + (it & 1) * TCM * 13;
       const float* Pl = Pl2 + (it & 1) * ENVS * 208;
       if (32 * q >= rows_here) {
@@ -254,7 +272,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         for (int uu = 0; uu < NGEMM * NCH; ++uu) {
           const uint32_t u = ubase + (uint32_t)uu, sa = u % PAST;
           if ((int)(u % NPH) != ph) continue;
-          if (u >= PAST) ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok;
+          if (u >= PAST) PROF_WAIT(3, ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok);
           __syncwarp();
           if (lane == 0) {
             if (is_leader) mbar_arrive(a_full + 8 * sa);
@@ -333,7 +351,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       int pending = -1;                                        // stage written but not yet published
       auto hand_off = [&]() {
         if (pending < 0) return;                               // warp-uniform
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        PROF_WAIT(4, asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"));
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -355,7 +373,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
             if (nxt) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)(lane & (NODES * NODES / 32 - 1)) * 32));
           }
         }
-        if (g == 5) { ok = mbar_wait(h_ready, (uint32_t)(it & 1)) && ok; }      // H complete (epilogue of GEMM 4)
+        if (g == 5) { PROF_WAIT(1, ok = mbar_wait(h_ready, (uint32_t)(it & 1)) && ok); }      // H complete (epilogue of GEMM 4)
         const float w1si = (g == 0) ? w1si0 : (g <= 2 ? w1si1 : w1si2);
         const uint32_t* w1f = W1f + ((g == 0) ? 0 : (g <= 2 ? 1 : 2)) * (NCH * 2 * 32 * 4);   // gcn_l1_1 | gcn_l1_2 (g = 1, 2) | gcn_l1_3
         // ---- this warp's chunks of the GEMM ----
@@ -363,6 +381,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           const uint32_t u = ubase + (uint32_t)(g * NCH + c), sa = u % PAST;
           if ((int)(u % NPH) != ph) continue;                  // another phase's warps own this chunk
           const int k0 = c * KCH;
+          const long long prof_t1 = PROF_NOW();
           // X fragments of the chunk: xb[16-row block][8-feature half][hi | lo][rows 2t.. | rows 8 + 2t..]
           uint32_t xb[2][2][2][2];
           if (g <= 3) {
@@ -406,7 +425,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
                 split2(v[1][0], v[1][1], xb[kr][nt][0][1], xb[kr][nt][1][1]);
               }
           }
+          PROF_ADD(5, PROF_NOW() - prof_t1);
           hand_off();                                          // publish the previous chunk's stage
+          const long long prof_t2 = PROF_NOW();
           // ---- Y = A_g . X on the tensor core, split, store from the accumulator layout ----
           uint32_t oh[2][4], ol[2][4];
 #pragma unroll
@@ -426,7 +447,8 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
               split2(y[0], y[1], oh[mt][2 * nt], ol[mt][2 * nt]);              // lane g8,     column 4 nt + t4
               split2(y[2], y[3], oh[mt][2 * nt + 1], ol[mt][2 * nt + 1]);      // lane g8 + 8, column 4 nt + t4
             }
-          if (u >= PAST) ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok;        // chunk u-PAST consumed
+          PROF_ADD(6, PROF_NOW() - prof_t2);
+          if (u >= PAST) PROF_WAIT(2, ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok);        // chunk u-PAST consumed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
@@ -455,7 +477,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       const bool live = 32 * q < rows_here;                    // dead row group of a split tile: barriers only
       for (int g = 0; g < NGEMM; ++g) {
         const int G = it * NGEMM + g, b = G & 1;               // GEMM counter across items: accumulator and parity
-        ok = mbar_wait(acc_full + 8 * b, (uint32_t)((G >> 1) & 1)) && ok;
+        PROF_WAIT(0, ok = mbar_wait(acc_full + 8 * b, (uint32_t)((G >> 1) & 1)) && ok);
         if (!live) {
           __syncwarp();
           if (lane == 0) {
@@ -466,6 +488,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           continue;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long prof_t1 = PROF_NOW();
         const uint32_t tacc = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b ? TM_ACC1 : 0) + (uint32_t)(8 * cb0);
         const float wsi = __ldg(P.wscale_inv + g);             // undoes the power-of-two scale folded into W (exact)
         float* hrow = H + r * LDH + 8 * cb0;
@@ -498,6 +521,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
+        PROF_ADD(1, PROF_NOW() - prof_t1);
         if (lane == 0) {
           if (is_leader) mbar_arrive(acc_empty + 8 * b);
           else mbar_arrive_remote(acc_empty + 8 * b, 0);
@@ -539,53 +563,54 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     }  // items
   } else if (warp == W_ISSUER) {
     // =================================================== MMA issuer / W forwarder =============================
-    if (lane == 0) {
-      if (is_leader) {
-        uint64_t db[WST][2];                                 // [stage][hi, lo]: one K = 16 step spans the chunk's two core-matrix columns
-#pragma unroll
-        for (int st = 0; st < WST; ++st) {
-          const uint32_t b_hi = smem_u32(smem + st * STAGE_BYTES);
-          db[st][0] = make_desc(b_hi, B_LBO);
-          db[st][1] = make_desc(b_hi + NKB * B_LBO, B_LBO);
-        }
-        for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
-          const uint32_t ubase = (uint32_t)it * (uint32_t)(NGEMM * NCH);
-          for (int g = 0; g < NGEMM; ++g) {
-            const int G = it * NGEMM + g, b = G & 1;
-            const uint32_t dacc = tmem_base + (uint32_t)(b ? TM_ACC1 : 0);
-            if (G >= 2) {                                      // the epilogue of GEMM G-2 has drained this accumulator
-              ok = mbar_wait_cluster(acc_empty + 8 * b, (uint32_t)(((G >> 1) - 1) & 1)) && ok;
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            for (int c = 0; c < NCH; ++c) {
-              const uint32_t u = ubase + (uint32_t)(g * NCH + c), sw = u % WST, sa = u % PAST;
-              if constexpr (NCTA == 2) ok = mbar_wait_cluster(a_full + 8 * sa, (u / PAST) & 1) && ok;
-              else ok = mbar_wait(a_full + 8 * sa, (u / PAST) & 1) && ok;
-              ok = mbar_wait(w_full + 8 * sw, (u / WST) & 1) && ok;
-              if constexpr (NCTA == 2) ok = mbar_wait_cluster(w_peer + 8 * sw, (u / WST) & 1) && ok;
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t a_hi = tmem_base + (uint32_t)(TM_AHI + ACOLS * sa), a_lo = tmem_base + (uint32_t)(TM_ALO + ACOLS * sa);
-#pragma unroll
-              for (int st = 0; st < WST; ++st) {
-                if (st != (int)sw) continue;                   // compile-time stage index keeps the descriptors in registers
-                mma_split<NCTA>(dacc, a_hi, db[st][0], c != 0);  // Yhi.Whi + Yhi.Wlo + Ylo.Whi (the tail chunk is zero-padded)
-                mma_split<NCTA>(dacc, a_hi, db[st][1], 1);
-                mma_split<NCTA>(dacc, a_lo, db[st][0], 1);
-              }
+    // The whole warp walks the chunk sequence converged (all lanes poll the barriers); ONE elected lane issues the three
+    // MMAs and the commits of a chunk.  Stage indices and barrier parities are running counters (no division), and the
+    // shared-memory descriptor of a W stage is the stage-0 descriptor plus a constant (its address field counts 16-byte
+    // units), so a chunk costs the issuer a few dozen instructions: it is the one serial thread every chunk passes through
+    // (the first form -- one lane inside `if (lane == 0)`, u % WST / u % PAST, a switch over per-stage descriptors -- made
+    // ptxas wrap every tcgen05 instruction in an elect / branch sequence: ~140 instructions and ~760 cycles per chunk).
+    if (is_leader) {
+      const uint64_t d_hi0 = make_desc(smem_u32(smem), B_LBO);
+      constexpr uint64_t D_STAGE = (uint64_t)(STAGE_BYTES >> 4), D_LO = (uint64_t)((NKB * B_LBO) >> 4);
+      static_assert((WST * STAGE_BYTES >> 4) < 0x4000, "the W ring must stay inside the descriptor's 14-bit address field");
+      uint32_t sw = 0, pw = 0, sa = 0, pa = 0, G = 0;
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        for (int g = 0; g < NGEMM; ++g, ++G) {
+          const uint32_t b = G & 1u;
+          const uint32_t dacc = tmem_base + (b ? (uint32_t)TM_ACC1 : 0u);
+          if (G >= 2) {                                        // the epilogue of GEMM G-2 has drained this accumulator
+            PROF_WAIT(2, ok = mbar_wait_cluster(acc_empty + 8 * b, ((G >> 1) - 1u) & 1u) && ok);
+          }
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            if constexpr (NCTA == 2) ok = mbar_wait_cluster(a_full + 8 * sa, pa) && ok;
+            else PROF_WAIT(0, ok = mbar_wait(a_full + 8 * sa, pa) && ok);
+            PROF_WAIT(1, ok = mbar_wait(w_full + 8 * sw, pw) && ok);
+            if constexpr (NCTA == 2) ok = mbar_wait_cluster(w_peer + 8 * sw, pw) && ok;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint32_t a_hi = tmem_base + (uint32_t)TM_AHI + (uint32_t)ACOLS * sa, a_lo = tmem_base + (uint32_t)TM_ALO + (uint32_t)ACOLS * sa;
+              const uint64_t d_hi = d_hi0 + D_STAGE * sw, d_lo = d_hi + D_LO;
+              mma_split<NCTA>(dacc, a_hi, d_hi, c != 0);       // Yhi.Whi + Yhi.Wlo + Ylo.Whi (the tail chunk is zero-padded)
+              mma_split<NCTA>(dacc, a_hi, d_lo, 1);
+              mma_split<NCTA>(dacc, a_lo, d_hi, 1);
               mma_commit<NCTA>(w_empty + 8 * sw);
               mma_commit<NCTA>(a_empty + 8 * sa);
               if (c + 1 == NCH) mma_commit<NCTA>(acc_full + 8 * b);
             }
+            __syncwarp();
+            if (++sw == (uint32_t)WST) { sw = 0; pw ^= 1u; }
+            if (++sa == (uint32_t)PAST) { sa = 0; pa ^= 1u; }
           }
-        }  // items
-      } else {
-        for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it)
-          for (int uu = 0; uu < NGEMM * NCH; ++uu) {           // peer CTA: tell the leader that W chunk u has landed here
-            const uint32_t u = (uint32_t)it * (uint32_t)(NGEMM * NCH) + (uint32_t)uu, sw = u % WST;
-            ok = mbar_wait(w_full + 8 * sw, (u / WST) & 1) && ok;
-            mbar_arrive_remote(w_peer + 8 * sw, 0);
-          }
-      }
+        }
+      }  // items
+    } else if (lane == 0) {
+      for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it)
+        for (int uu = 0; uu < NGEMM * NCH; ++uu) {             // peer CTA: tell the leader that W chunk u has landed here
+          const uint32_t u = (uint32_t)it * (uint32_t)(NGEMM * NCH) + (uint32_t)uu, sw = u % WST;
+          ok = mbar_wait(w_full + 8 * sw, (u / WST) & 1) && ok;
+          mbar_arrive_remote(w_peer + 8 * sw, 0);
+        }
     }
     __syncwarp();
   } else {
@@ -595,7 +620,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         for (int g = 0; g < NGEMM; ++g)
           for (int c = 0; c < NCH; ++c) {
             const uint32_t u = (uint32_t)it * (uint32_t)(NGEMM * NCH) + (uint32_t)(g * NCH + c), s = u % WST;
-            if (u >= WST) ok = mbar_wait(w_empty + 8 * s, ((u / WST) - 1) & 1) && ok;       // chunk u-WST consumed
+            if (u >= WST) PROF_WAIT(0, ok = mbar_wait(w_empty + 8 * s, ((u / WST) - 1) & 1) && ok);       // chunk u-WST consumed
             const uint32_t bytes = (uint32_t)STAGE_BYTES;                                    // this CTA's half: hi then lo
             const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg[g]) +
                                        (size_t)c * Cfg<NCTA>::CHUNK_IMG_BYTES + (size_t)cta_rank * bytes;
@@ -606,6 +631,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     __syncwarp();
   }
 
+  PROF_FLUSH();
   if (!ok && P.error_flag) atomicOr(P.error_flag, 1);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

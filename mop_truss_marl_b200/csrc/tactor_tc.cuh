@@ -91,6 +91,12 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
                  "h"((uint16_t)3)
                  : "memory");
 }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -166,6 +172,8 @@ __device__ __forceinline__ void hmma16816(float* c, const uint32_t* a, uint32_t 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // three-term split product: c += (ahi + alo).(bhi + blo) without the lo.lo term
+// (three independent accumulators joined by FADDs were measured slower: 0.201 against 0.195 ms -- the generators are bound
+// by their instruction count, not by the tensor-pipe round trip of the dependent chain)
 __device__ __forceinline__ void hmma_split(float* c, const uint32_t* ahi, const uint32_t* alo, const uint32_t* bhi, const uint32_t* blo) {
   hmma16816(c, ahi, bhi[0], bhi[1]);
   hmma16816(c, ahi, blo[0], blo[1]);
@@ -232,6 +240,7 @@ struct Params {
   int split_from;         // first work item that is a piece of a tile (tiles of the last partial wave), n_items if none
   int split_f;            // pieces per split tile: 1, 2 or 4
   int* error_flag;
+  int dev_flags;          // development switches (TACTOR_FLAGS, A/B timing): bit 0 = publish an A stage right after its store
 };
 
 }  // namespace fused
