@@ -447,6 +447,7 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   if (!h) return afail(TFEM_ERR_ARG, "out of host memory");
   h->device = device; h->nodes = nodes; h->max_batch = max_batch;
   if (const char* v = getenv("TACTOR_NCTA")) h->ncta = (atoi(v) == 2) ? 2 : 1;     // development switches (A/B timing)
+  if (nodes == 32) h->variant = 2;   // 32-node families: 4 epilogue warps, so that the generators' 32 + 32 adjacency registers fit without spills
   if (const char* v = getenv("TACTOR_VARIANT")) h->variant = atoi(v);
   if (const char* v = getenv("TACTOR_FLAGS")) h->dev_flags = atoi(v);
   Guard g(device);
@@ -455,8 +456,8 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   cudaError_t e = upload_weights(h, w);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
   if (const char* v = getenv("TACTOR_NO_SPLIT")) { if (v[0] == '1') h->sms = 0; }
-  if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 16384);
-  if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 16384);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 65536);
+  if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 65536);
   if (e == cudaSuccess) e = (nodes == 16) ? set_pipe_smem_variant<16>(h->ncta, h->variant) : set_pipe_smem_variant<32>(h->ncta, h->variant);
   if (e == cudaSuccess)
     e = (nodes == 16) ? cudaFuncSetAttribute(tactor::pareto_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM)
@@ -597,7 +598,7 @@ int tactor_status(tactor_handle_t h) {
 // development build only (python -m mop_truss_marl_b200.build --prof -> lib/libtfem_prof.so, scripts/actor_prof.py): the
 // per-warp cycle counters CTA 0 of the last actor_pipe_kernel launch left behind the error flag
 int tactor_prof_read(tactor_handle_t h, long long* out, int n) {
-  if (!h || !out || n < 0 || n > 2000) return afail(TFEM_ERR_ARG, "bad argument");
+  if (!h || !out || n < 0 || n > 8000) return afail(TFEM_ERR_ARG, "bad argument");
   Guard g(h->device);
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(out, h->d_error + 32, (size_t)n * 8, cudaMemcpyDeviceToHost);

@@ -89,6 +89,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 #define PROF_WAIT(slot, expr) do { const long long t0_ = clock64(); expr; prof_c[slot] += clock64() - t0_; } while (0)
 #define PROF_ADD(slot, v) prof_c[slot] += (v)
 #define PROF_NOW() clock64()
+// time line of item 1 of CTA 0 (raw SM clock, 32 bits): words [w][48 visits][4] per generator warp, then the issuer's
+// [91 chunks][4] at word 4096 and the epilogue warps' [8][7][2] at word 4608, all behind error_flag + 2048 ints
+#define PROF_TRACE(word, value_expr) do { if (blockIdx.x == 0 && lane == 0 && P.error_flag) \
+    reinterpret_cast<uint32_t*>(P.error_flag + 2048)[word] = (uint32_t)(value_expr); } while (0)
 #define PROF_FLUSH() do { if (blockIdx.x == 0 && lane == 0 && P.error_flag) { prof_c[7] = clock64() - prof_start; \
     long long* dst_ = reinterpret_cast<long long*>(P.error_flag + 32) + warp * 8; for (int i_ = 0; i_ < 8; ++i_) dst_[i_] = prof_c[i_]; } } while (0)
 #else
@@ -96,6 +100,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 #define PROF_WAIT(slot, expr) do { expr; } while (0)
 #define PROF_ADD(slot, v) do { } while (0)
 #define PROF_NOW() 0ll
+#define PROF_TRACE(word, value_expr) do { } while (0)
 #define PROF_FLUSH() do { } while (0)
 #endif
 
@@ -116,11 +121,15 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   float* Pl2 = reinterpret_cast<float*>(W1f + W1F_WORDS);                    // [2][ENVS][208] pooled Pareto embedding of the item / the next item
   float* Xr2 = Pl2 + 2 * ENVS * 208;                                         // [2][128][13] raw x_n rows of the item / the next item
   float* AnT = Xr2 + 2 * TCM * 13;                                           // [N(j)][N(n)] shared A_n, transposed (heads)
-  float* AnN = AnT + NODES * NODES;                                          // [N(n)][N(j)] shared A_n (generator fragments)
-  float* Wh = AnN + NODES * NODES;                                           // [2][201][4] head kernels, row 200 = bias
+  uint32_t* AnF = reinterpret_cast<uint32_t*>(AnT + NODES * NODES);         // [KB * KB blocks][hi | lo][32 lanes][4] mma A fragments of the shared A_n
+  float* Wh = AnT + 2 * NODES * NODES;                                           // [2][201][4] head kernels, row 200 = bias
   float* Us = Wh + 2 * 201 * 4;                                              // [2 heads][2 column halves][128][4] head pre-activations
   uint64_t* bars = reinterpret_cast<uint64_t*>(Us + 4 * TCM * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * MAXST + 8);
+  // h_prog[row group][epilogue warp of the group]: 32 * item + 8-column blocks of GEMM 4 (the last term of the five-way sum
+  // H) this warp has stored; the generators of layer 3 start on a column chunk as soon as their rows of it are there
+  volatile int* h_prog = reinterpret_cast<volatile int*>(tmem_slot + 2);
+  constexpr int NCB = KH / 8;                                // 25 blocks of 8 accumulator columns
 
   // the shuffle tells the compiler that `warp` is warp-uniform: role branches become uniform branches
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -146,11 +155,10 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
   // A ring (s < PAST): a_full  A stage written (leader's copy; one arrive per generator warp of the chunk, 4 per CTA)
   //                    a_empty stage consumed (commit)
   // acc_full[b] accumulator b complete (commit)   acc_empty[b] drained by the epilogue warps (leader's copy)
-  // h_ready     the five-way sum H is complete (epilogue of GEMM 4 -> generators of GEMM 5)
   static_assert(WST <= MAXST && PAST <= MAXST, "barrier slots");
   const uint32_t w_full = smem_u32(&bars[0]), w_peer = smem_u32(&bars[MAXST]), w_empty = smem_u32(&bars[2 * MAXST]);
   const uint32_t a_full = smem_u32(&bars[3 * MAXST]), a_empty = smem_u32(&bars[4 * MAXST]);
-  const uint32_t acc_full = smem_u32(&bars[5 * MAXST]), acc_empty = smem_u32(&bars[5 * MAXST + 2]), h_ready = smem_u32(&bars[5 * MAXST + 4]);
+  const uint32_t acc_full = smem_u32(&bars[5 * MAXST]), acc_empty = smem_u32(&bars[5 * MAXST + 2]);
   const uint32_t x_full = smem_u32(&bars[5 * MAXST + 6]);      // [2] the item's x_n / pooled rows have landed (cp.async arrivals of all generator threads)
   const uint32_t cta_rank = (NCTA == 1) ? 0u : cluster_ctarank();
   const bool is_leader = (cta_rank == 0);
@@ -178,17 +186,30 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       mbar_init(acc_full + 8 * b, 1);
       mbar_init(acc_empty + 8 * b, NEPIW * NCTA);
     }
-    mbar_init(h_ready, NEPIW);
     mbar_init(x_full, NGENW * 32);
     mbar_init(x_full + 8, NGENW * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // item-independent constants: A_n (both orientations), the head kernels and the layer-1 fragment image; the
   // generators stage the per-item data
-  for (int idx = tid; idx < NODES * NODES; idx += PTHREADS) {
-    const float a = P.A_n[idx];
-    AnN[idx] = a;
-    AnT[(idx % NODES) * NODES + idx / NODES] = a;
+  if (tid < 8) h_prog[tid] = 0;
+  for (int idx = tid; idx < NODES * NODES; idx += PTHREADS) AnT[(idx % NODES) * NODES + idx / NODES] = P.A_n[idx];
+  for (int idx = tid; idx < KB * KB * 32; idx += PTHREADS) {
+    // fp16 hi/lo A fragments of the 16 x 16 blocks of A_n (block (mt, kb): rows 16 mt.., columns 16 kb..), computed once
+    const int blk = idx >> 5, ln = idx & 31, fg = ln >> 2, ft = ln & 3;
+    const float* p0 = P.A_n + (16 * (blk / KB) + fg) * NODES + 16 * (blk % KB) + 2 * ft;
+    const float2 v[4] = {*reinterpret_cast<const float2*>(p0), *reinterpret_cast<const float2*>(p0 + 8 * NODES),
+                         *reinterpret_cast<const float2*>(p0 + 8), *reinterpret_cast<const float2*>(p0 + 8 * NODES + 8)};
+    bool badn = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t hi, lo;
+      split2(v[i].x, v[i].y, hi, lo);
+      AnF[((blk * 2 + 0) * 32 + ln) * 4 + i] = hi;
+      AnF[((blk * 2 + 1) * 32 + ln) * 4 + i] = lo;
+      badn = badn || !(fabsf(v[i].x) <= F16_MAX) || !(fabsf(v[i].y) <= F16_MAX);
+    }
+    if (badn && P.error_flag) atomicOr(P.error_flag, 2);
   }
   for (int idx = tid; idx < 2 * 201; idx += PTHREADS) {
     const int hd = idx / 201, k = idx % 201;
@@ -212,9 +233,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     // =================================================== generators ===========================================
     const int q = warp & 3, ph = warp >> 2;
     const int g8 = lane >> 2, t4 = lane & 3;                 // mma fragment coordinates
-    float amax = 0.f;                                        // largest |X|, |A.X| this thread split (f16 range check)
     bool bad = false;                                        // an input / adjacency entry / Z outside the fp16 range, or NaN (the ReLU
-                                                             // behind Z would hide it from amax)
+                                                             // behind Z would hide it; everything downstream shows up as a
+                                                             // non-finite accumulator entry, which the epilogue checks)
     // asynchronous copy of one item's x_n rows and pooled rows into buffer `buf` (all generator threads take part)
     auto stage_item = [&](int item_s, int buf) {
       int row0s, rows_s;
@@ -285,31 +306,46 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       // itself only (KB = 1); NODES = 32: both blocks belong to environment q and every (mt, kb) pair of 16 x 16 sub-blocks of
       // the adjacency matrix takes part.  kr(mt, kb) = the 16-row block of the warp that holds the k rows of the pair.
       auto kr_of = [](int mt, int kb) { return NODES == 16 ? mt : kb; };
-      // fp16 hi/lo A fragments of the 16 x 16 block (rows nb.., columns 16 kb..) of a row-major [N][N] matrix
-      auto adj_frag = [&](const float* base, bool in_smem, int mt, int kb, uint32_t* hi, uint32_t* lo) {
+      // the 16 x 16 block (rows nb.., columns 16 kb..) of a row-major [N][N] matrix in global memory, as the four float2 of this
+      // lane's A fragment
+      auto adj_load = [&](const float* base, int mt, int kb, float2* v) {
         const int nb = (16 * mt) % NODES;
         const float* p0 = base + (nb + g8) * NODES + 16 * kb + 2 * t4;
-        float2 v0, v1, v2, v3;
-        if (in_smem) {
-          v0 = *reinterpret_cast<const float2*>(p0); v1 = *reinterpret_cast<const float2*>(p0 + 8 * NODES);
-          v2 = *reinterpret_cast<const float2*>(p0 + 8); v3 = *reinterpret_cast<const float2*>(p0 + 8 * NODES + 8);
-        } else {
-          v0 = __ldg(reinterpret_cast<const float2*>(p0)); v1 = __ldg(reinterpret_cast<const float2*>(p0 + 8 * NODES));
-          v2 = __ldg(reinterpret_cast<const float2*>(p0 + 8)); v3 = __ldg(reinterpret_cast<const float2*>(p0 + 8 * NODES + 8));
+        v[0] = __ldg(reinterpret_cast<const float2*>(p0)); v[1] = __ldg(reinterpret_cast<const float2*>(p0 + 8 * NODES));
+        v[2] = __ldg(reinterpret_cast<const float2*>(p0 + 8)); v[3] = __ldg(reinterpret_cast<const float2*>(p0 + 8 * NODES + 8));
+      };
+      // ... split into fp16 hi/lo fragments (range / NaN check: the sum of the eight entries is finite iff every entry is)
+      auto adj_split = [&](const float2* v, uint32_t* hi, uint32_t* lo) {
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(v[0].x), fabsf(v[0].y)), fmaxf(fabsf(v[1].x), fabsf(v[1].y))),
+                              fmaxf(fmaxf(fabsf(v[2].x), fabsf(v[2].y)), fmaxf(fabsf(v[3].x), fabsf(v[3].y))));
+        const float sum = ((v[0].x + v[0].y) + (v[1].x + v[1].y)) + ((v[2].x + v[2].y) + (v[3].x + v[3].y));
+        bad = bad || !(m <= F16_MAX) || (sum != sum);
+        split2(v[0].x, v[0].y, hi[0], lo[0]); split2(v[1].x, v[1].y, hi[1], lo[1]);
+        split2(v[2].x, v[2].y, hi[2], lo[2]); split2(v[3].x, v[3].y, hi[3], lo[3]);
+      };
+      // fragments of the shared A_n: precomputed image (hi | lo) in shared memory
+      auto an_frag = [&](int mt, int kb, uint32_t* hi, uint32_t* lo) {
+        const int blk = (NODES == 16) ? 0 : 2 * mt + kb;
+        const uint4 h = *reinterpret_cast<const uint4*>(AnF + ((blk * 2 + 0) * 32 + lane) * 4);
+        const uint4 l = *reinterpret_cast<const uint4*>(AnF + ((blk * 2 + 1) * 32 + lane) * 4);
+        hi[0] = h.x; hi[1] = h.y; hi[2] = h.z; hi[3] = h.w;
+        lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; lo[3] = l.w;
+      };
+      // per-environment adjacency tensor of GEMM g (nullptr: the shared A_n); its raw entries are fetched one such GEMM ahead
+      // (GEMM 1's at the start of the item), so that no global latency sits between two GEMMs
+      auto adj_tensor = [&](int g) -> const float* { return (g == 1) ? P.A_ts : (g == 2) ? P.A_cs : (g == 3 || g == 6) ? P.A_s : nullptr; };
+      float2 araw[2][KB][4];
+      auto fetch_adj = [&](int g) {
+        const float* t = adj_tensor(g);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          int env = env0 + (32 * q + 16 * mt) / NODES;       // clamped into the batch (rows past the batch are never written)
+          env = env * NODES < M ? env : (M / NODES - 1);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) adj_load(t + (size_t)env * NODES * NODES, mt, kb, araw[mt][kb]);
         }
-        const float m = fmaxf(fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v1.x), fabsf(v1.y))),
-                              fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v3.x), fabsf(v3.y))));
-        bad = bad || !(m <= F16_MAX) || (v0.x != v0.x) || (v0.y != v0.y) || (v1.x != v1.x) || (v1.y != v1.y) || (v2.x != v2.x) ||
-              (v2.y != v2.y) || (v3.x != v3.x) || (v3.y != v3.y);
-        split2(v0.x, v0.y, hi[0], lo[0]); split2(v1.x, v1.y, hi[1], lo[1]);
-        split2(v2.x, v2.y, hi[2], lo[2]); split2(v3.x, v3.y, hi[3], lo[3]);
       };
-      // adjacency matrix of GEMM g for row block mt: nullptr = the shared A_n (also for environments past the batch)
-      auto adj_of = [&](int g, int mt) -> const float* {
-        const float* adj = (g == 1) ? P.A_ts : (g == 2) ? P.A_cs : (g == 3 || g == 6) ? P.A_s : nullptr;
-        const int env = env0 + (32 * q + 16 * mt) / NODES;
-        return (adj != nullptr && env * NODES < M) ? adj + (size_t)env * NODES * NODES : nullptr;
-      };
+      fetch_adj(1);
       // ---- Z = A_n . x_n (gcn_l1_1..3 share input and adjacency), kept as the B fragments of [Z, 1]^T:
       //      zfr[8-row block of the warp][hi | lo][c 0..7 | c 8..15 (c = 13: the constant 1 that multiplies the bias row)] ----
       uint32_t zfr[4][2][2];
@@ -321,7 +357,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           uint32_t ahi[4], alo[4];
-          adj_frag(AnN, true, mt, kb, ahi, alo);
+          an_frag(mt, kb, ahi, alo);
           const float* xr = Xraw + (32 * q + 16 * kr_of(mt, kb) + 2 * t4) * 13;
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt) {
@@ -363,17 +399,18 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       uint32_t afr[2][KB][2][4];                               // [mt][kb][hi | lo][a0..a3] of the GEMM's adjacency matrix
       for (int g = 0; g < NGEMM; ++g) {
         // ---- per-GEMM setup: adjacency fragments; pull the next GEMM's rows towards the SM ----
+        if (g == 1 || g == 2 || g == 3 || g == 6) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const float* adj = adj_of(g, mt);
+          for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb) adj_frag(adj ? adj : AnN, adj == nullptr, mt, kb, afr[mt][kb][0], afr[mt][kb][1]);
-          if (g + 1 < NGEMM) {
-            const float* nxt = adj_of(g + 1, mt);
-            if (nxt) asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)(lane & (NODES * NODES / 32 - 1)) * 32));
-          }
+            for (int kb = 0; kb < KB; ++kb) adj_split(araw[mt][kb], afr[mt][kb][0], afr[mt][kb][1]);
+          if (g < 6) fetch_adj(g < 3 ? g + 1 : 6);
+        } else {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) an_frag(mt, kb, afr[mt][kb][0], afr[mt][kb][1]);
         }
-        if (g == 5) { PROF_WAIT(1, ok = mbar_wait(h_ready, (uint32_t)(it & 1)) && ok); }      // H complete (epilogue of GEMM 4)
         const float w1si = (g == 0) ? w1si0 : (g <= 2 ? w1si1 : w1si2);
         const uint32_t* w1f = W1f + ((g == 0) ? 0 : (g <= 2 ? 1 : 2)) * (NCH * 2 * 32 * 4);   // gcn_l1_1 | gcn_l1_2 (g = 1, 2) | gcn_l1_3
         // ---- this warp's chunks of the GEMM ----
@@ -382,6 +419,21 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           if ((int)(u % NPH) != ph) continue;                  // another phase's warps own this chunk
           const int k0 = c * KCH;
           const long long prof_t1 = PROF_NOW();
+          const int prof_v = (g * NCH + c) / NPH;
+          if (it == 1) PROF_TRACE((warp * 48 + prof_v) * 4 + 0, prof_t1);
+          // the five-way sum H is handed over row group by row group, 16 columns at a time: the two epilogue warps of this
+          // warp's rows publish how many of their 8-column blocks of GEMM 4 are stored (h_prog), so layer 3 starts on
+          // column chunk c as soon as blocks 2c, 2c + 1 are there instead of after the whole drain
+          if (g == 5) {
+            const int want0 = it * 32 + (NEPIW == 8 ? min(c + 1, (NCB + 1) / 2) : min(2 * c + 2, NCB));
+            const int want1 = it * 32 + (NEPIW == 8 ? min(c + 1, NCB / 2) : min(2 * c + 2, NCB));
+            const long long t0_ = PROF_NOW();
+            uint32_t spin = 0;
+            while ((h_prog[q * 2] < want0 || h_prog[q * 2 + 1] < want1) && ++spin < SPIN_LIMIT) { }
+            ok = ok && spin < SPIN_LIMIT;
+            __threadfence_block();
+            PROF_ADD(1, PROF_NOW() - t0_);
+          }
           // X fragments of the chunk: xb[16-row block][8-feature half][hi | lo][rows 2t.. | rows 8 + 2t..]
           uint32_t xb[2][2][2][2];
           if (g <= 3) {
@@ -395,7 +447,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
               float xt[4] = {0.f, 0.f, 0.f, 0.f};
               hmma_split(xt, whi, wlo, zfr[ntr][0], zfr[ntr][1]);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { xt[i] = fmaxf(xt[i] * w1si, 0.f); amax = fmaxf(amax, xt[i]); }
+              for (int i = 0; i < 4; ++i) xt[i] = fmaxf(xt[i] * w1si, 0.f);
               split2(xt[0], xt[1], xb[ntr >> 1][0][0][ntr & 1], xb[ntr >> 1][0][1][ntr & 1]);
               split2(xt[2], xt[3], xb[ntr >> 1][1][0][ntr & 1], xb[ntr >> 1][1][1][ntr & 1]);
             }
@@ -420,12 +472,12 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
                       }
                     }
                 }
-                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[0][0]), fabsf(v[0][1])), fmaxf(fabsf(v[1][0]), fabsf(v[1][1]))));
                 split2(v[0][0], v[0][1], xb[kr][nt][0][0], xb[kr][nt][1][0]);
                 split2(v[1][0], v[1][1], xb[kr][nt][0][1], xb[kr][nt][1][1]);
               }
           }
           PROF_ADD(5, PROF_NOW() - prof_t1);
+          if (it == 1) PROF_TRACE((warp * 48 + prof_v) * 4 + 1, PROF_NOW());
           hand_off();                                          // publish the previous chunk's stage
           const long long prof_t2 = PROF_NOW();
           // ---- Y = A_g . X on the tensor core, split, store from the accumulator layout ----
@@ -443,11 +495,11 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
               // column 200 of A is the constant 1 that multiplies the bias row of the W image (columns 201..207 are zero
               // because X is)
               if (k0 + 8 * nt == KH && t4 == 0) { y[0] = 1.f; y[2] = 1.f; }
-              amax = fmaxf(amax, fmaxf(fmaxf(fabsf(y[0]), fabsf(y[1])), fmaxf(fabsf(y[2]), fabsf(y[3]))));
               split2(y[0], y[1], oh[mt][2 * nt], ol[mt][2 * nt]);              // lane g8,     column 4 nt + t4
               split2(y[2], y[3], oh[mt][2 * nt + 1], ol[mt][2 * nt + 1]);      // lane g8 + 8, column 4 nt + t4
             }
           PROF_ADD(6, PROF_NOW() - prof_t2);
+          if (it == 1) PROF_TRACE((warp * 48 + prof_v) * 4 + 2, PROF_NOW());
           if (u >= PAST) PROF_WAIT(2, ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok);        // chunk u-PAST consumed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -457,20 +509,27 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
             tmem_st_16x128b_x2(tmem_base + lane_sel + (uint32_t)(TM_ALO + ACOLS * sa), ol[mt]);
           }
           pending = (int)sa;
+          if (it == 1) PROF_TRACE((warp * 48 + prof_v) * 4 + 3, PROF_NOW());
+          // the tensor core runs dry at the head of every GEMM (the generators paid the GEMM's set-up, and layer 3 waited for
+          // the five-way sum): publish its first chunks at once instead of in the middle of the warp's next chunk
+          if (c < NPH) hand_off();
         }
         hand_off();                                            // the accumulator of this GEMM must not wait for the next one
       }
     }  // items
-    if ((bad || !(amax <= F16_MAX)) && P.error_flag) atomicOr(P.error_flag, 2);   // an activation left the fp16 range (or NaN input)
+    if (bad && P.error_flag) atomicOr(P.error_flag, 2);        // an input left the fp16 range (or NaN)
   } else if (warp < NGENW + NEPIW) {
     // =================================================== epilogue =============================================
     const int ew = warp - NGENW, q = ew & 3, half = ew >> 2;
     const int r = 32 * q + lane;
     const int n = r % NODES;
     const int lane_env0 = lane & ~(NODES - 1);
-    constexpr int NCB = KH / 8;                                // 25 blocks of 8 accumulator columns
-    const int cb0 = (NEPIW == 8 && half) ? (NCB + 1) / 2 : 0;
-    const int ncb = (NEPIW == 8) ? (half ? NCB - (NCB + 1) / 2 : (NCB + 1) / 2) : NCB;
+    // the 25 blocks of 8 accumulator columns: with two warps per row group, warp `half` takes blocks half, half + 2, ... so
+    // that both advance through the columns together (the generators of layer 3 follow them chunk by chunk, see h_prog)
+    constexpr int CBS = (NEPIW == 8) ? 2 : 1;                  // block stride
+    const int cb0 = (NEPIW == 8) ? half : 0;
+    const int ncb = (NEPIW == 8) ? (half ? NCB / 2 : (NCB + 1) / 2) : NCB;
+    float nonfinite = 0.f;                                     // stays 0 while every accumulator entry is finite (x * 0 is NaN otherwise)
     for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
       int row0, rows_here;
       item_rows(item, row0, rows_here);
@@ -483,12 +542,12 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           if (lane == 0) {
             if (is_leader) mbar_arrive(acc_empty + 8 * b);
             else mbar_arrive_remote(acc_empty + 8 * b, 0);
-            if (g == 4) mbar_arrive(h_ready);
           }
           continue;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const long long prof_t1 = PROF_NOW();
+        if (it == 1) PROF_TRACE(4608 + (ew * 7 + g) * 2, prof_t1);
         const uint32_t tacc = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(b ? TM_ACC1 : 0) + (uint32_t)(8 * cb0);
         const float wsi = __ldg(P.wscale_inv + g);             // undoes the power-of-two scale folded into W (exact)
         float* hrow = H + r * LDH + 8 * cb0;
@@ -502,19 +561,31 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           float v[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(vr[i & 1][t]);
-          if (i + 1 < ncb) tmem_ld8_async(tacc + (uint32_t)(8 * (i + 1)), vr[(i + 1) & 1]);   // in flight while block i is processed
+          if (i + 1 < ncb) tmem_ld8_async(tacc + (uint32_t)(8 * CBS * (i + 1)), vr[(i + 1) & 1]);   // in flight while block i is processed
+          // an operand that left the fp16 range (|A.X| > 65504 became inf in the split) or a NaN shows up as a non-finite
+          // accumulator entry here, before the ReLU can hide it: one FFMA per entry instead of range tracking in the generators
+#pragma unroll
+          for (int t = 0; t < 8; ++t) nonfinite = fmaf(v[t], 0.f, nonfinite);
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t] * wsi, 0.f);   // the bias rode along as row 200 of the W image
           if (g <= 4) {
-            float4* dst = reinterpret_cast<float4*>(hrow + 8 * i);
+            float4* dst = reinterpret_cast<float4*>(hrow + 8 * CBS * i);
             float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
             if (g > 0) { o0 = dst[0]; o1 = dst[1]; }
             dst[0] = make_float4(v[0] + o0.x, v[1] + o0.y, v[2] + o0.z, v[3] + o0.w);
             dst[1] = make_float4(v[4] + o1.x, v[5] + o1.y, v[6] + o1.z, v[7] + o1.w);
+            if (g == 4) {                                      // H is complete in these 8 columns of this warp's rows
+              __threadfence_block();
+              __syncwarp();
+              if (lane == 0) {
+                h_prog[q * 2 + half] = it * 32 + i + 1;
+                if (NEPIW == 4) h_prog[q * 2 + 1] = it * 32 + i + 1;
+              }
+            }
           } else {
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-              const float4 w = *reinterpret_cast<const float4*>(wh + (8 * (cb0 + i) + t) * 4);
+              const float4 w = *reinterpret_cast<const float4*>(wh + (8 * (cb0 + CBS * i) + t) * 4);
               u0 = fmaf(v[t], w.x, u0); u1 = fmaf(v[t], w.y, u1); u2 = fmaf(v[t], w.z, u2);
             }
           }
@@ -522,10 +593,10 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         PROF_ADD(1, PROF_NOW() - prof_t1);
+        if (it == 1) PROF_TRACE(4608 + (ew * 7 + g) * 2 + 1, PROF_NOW());
         if (lane == 0) {
           if (is_leader) mbar_arrive(acc_empty + 8 * b);
           else mbar_arrive_remote(acc_empty + 8 * b, 0);
-          if (g == 4) mbar_arrive(h_ready);
         }
         if (g >= 5) {
           // output heads (truss2D_RL.py:121-125): sigmoid(A_n (x3 W4) + b4); the 16/32 rows of an environment are
@@ -561,6 +632,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         }
       }
     }  // items
+    if (!(nonfinite == 0.f) && P.error_flag) atomicOr(P.error_flag, 2);   // an activation left the fp16 range (or NaN)
   } else if (warp == W_ISSUER) {
     // =================================================== MMA issuer / W forwarder =============================
     // The whole warp walks the chunk sequence converged (all lanes poll the barriers); ONE elected lane issues the three
@@ -575,6 +647,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       static_assert((WST * STAGE_BYTES >> 4) < 0x4000, "the W ring must stay inside the descriptor's 14-bit address field");
       uint32_t sw = 0, pw = 0, sa = 0, pa = 0, G = 0;
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const bool prof_tr = (G == (uint32_t)NGEMM);          // item 1 of this CTA
         for (int g = 0; g < NGEMM; ++g, ++G) {
           const uint32_t b = G & 1u;
           const uint32_t dacc = tmem_base + (b ? (uint32_t)TM_ACC1 : 0u);
@@ -585,7 +658,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           for (int c = 0; c < NCH; ++c) {
             if constexpr (NCTA == 2) ok = mbar_wait_cluster(a_full + 8 * sa, pa) && ok;
             else PROF_WAIT(0, ok = mbar_wait(a_full + 8 * sa, pa) && ok);
+            if (prof_tr) PROF_TRACE(4096 + (g * NCH + c) * 4 + 0, PROF_NOW());
             PROF_WAIT(1, ok = mbar_wait(w_full + 8 * sw, pw) && ok);
+            if (prof_tr) PROF_TRACE(4096 + (g * NCH + c) * 4 + 1, PROF_NOW());
             if constexpr (NCTA == 2) ok = mbar_wait_cluster(w_peer + 8 * sw, pw) && ok;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
@@ -599,6 +674,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
               if (c + 1 == NCH) mma_commit<NCTA>(acc_full + 8 * b);
             }
             __syncwarp();
+            if (prof_tr) PROF_TRACE(4096 + (g * NCH + c) * 4 + 2, PROF_NOW());
             if (++sw == (uint32_t)WST) { sw = 0; pw ^= 1u; }
             if (++sa == (uint32_t)PAST) { sa = 0; pa ^= 1u; }
           }

@@ -116,6 +116,21 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
+// the same with a pause between polls: a warp that expects to wait long (epilogue between GEMMs, W producer) should not
+// keep taking issue slots and mbarrier-unit bandwidth from the warps it waits for
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if (ns) __nanosleep(ns);
+  }
+  return false;
+}
 // the same for a barrier that peer-CTA threads arrive on
 __device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
@@ -167,6 +182,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 //   B [16 x 8]  col-major: b0 (k 2t..2t+1, col g)  b1 (k 2t+8.., col g)
 //   C [16 x 8]           : c0 c1 (row g, cols 2t, 2t+1)  c2 c3 (row g+8, same cols)
 __device__ __forceinline__ void hmma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+#ifdef TACTOR_ABLATE_HMMA   // timing experiment only (wrong results): the generators without their warp-level tensor-core products
+  c[0] += __uint_as_float(a[0] ^ b0); c[1] += __uint_as_float(a[1] ^ b1); c[2] += __uint_as_float(a[2] ^ b0); c[3] += __uint_as_float(a[3] ^ b1);
+  return;
+#endif
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));

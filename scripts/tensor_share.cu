@@ -45,7 +45,19 @@ __global__ void __launch_bounds__(544, 1) share_kernel(long long* out, int nutc,
 #pragma unroll
       for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
     const uint32_t a[4] = {0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u};
-    if (chain) {
+    if (chain == 2) {                                       // no tensor work at all: scale / max / convert (the split sequence's pipes)
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = (float)(threadIdx.x + i);
+      for (int it = 0; it < nh / 4; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(fmaf(x[i], 1.0001f, 0.5f), 1.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(__float_as_uint(x[i]) & 0xffffe000u) + 1e-3f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c[0][0] += x[i];
+    } else if (chain) {
       for (int it = 0; it < nh / 4; ++it)
 #pragma unroll
         for (int i = 0; i < 4; ++i) hmma16816(c[0], a, 0x3c003c00u, 0x3c003c00u);     // one dependent chain
@@ -150,6 +162,11 @@ int main() {
            nutc, nh, nw, chain, h[0], nutc ? (double)h[0] / nutc : 0.0, hm, (nh && nw) ? (double)hm / ((double)nh * ((nw + 3) / 4)) : 0.0);
   };
   run(3000, 0, 0, 0);
+  for (int nw : {4, 8, 16}) {                                 // ALU-only warps next to the tcgen05 stream
+    run(0, 8192, nw, 2);
+    run(3000, 8192, nw, 2);
+    run(3000, 32768, nw, 2);
+  }
   for (int chain = 0; chain < 2; ++chain)
     for (int nw : {4, 8, 16}) {
       run(0, 8192, nw, chain);

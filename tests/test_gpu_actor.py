@@ -242,3 +242,70 @@ def test_generator_variants_match_production(variant, monkeypatch):
             pol.check()
             outs.append((geo.clone(), topo.clone()))
         assert float((outs[0][0] - outs[1][0]).abs().max()) <= 1e-6 and float((outs[0][1] - outs[1][1]).abs().max()) <= 1e-6
+
+
+def trained_weights(agent):
+    """the reference's trained actor ``model/2000pickle_base/Agent<agent>_Actor_pickle`` from the committed fixture
+    (tests/golden/make_actor_golden.py)"""
+    import os
+    from mop_truss_marl_b200 import tf_checkpoint
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "actor_2000pickle_base.npz"))
+    return {name: (z["agent%d/%s/kernel" % (agent, name)], z["agent%d/%s/bias" % (agent, name)]) for name in tf_checkpoint.ACTOR_LAYERS}
+
+
+def padded_pareto_graph(rng, B, P, front_sizes):
+    """Pareto graphs as the driver feeds them: ``pareto_state_data`` of a front of n points (chain graph, normalised), zero
+    rows / columns up to P (``master_DDPG_truss2D_MO.py:499-517``); the network then pools over ALL P rows"""
+    from oracle.truss_oracle import pareto_state_data
+    x_p = np.zeros((B, P, 4), np.float32)
+    A_p = np.zeros((B, P, P), np.float32)
+    for b in range(B):
+        n = int(front_sizes[b])
+        obj1 = np.sort(rng.rand(n)).astype(np.float32)
+        obj2 = np.sort(rng.rand(n))[::-1].astype(np.float32)
+        x, A = pareto_state_data([(obj1[i], obj2[i]) for i in range(n)], index=int(rng.randint(0, n)))
+        x_p[b, :n], A_p[b, :n, :n] = x, A
+    return x_p, A_p
+
+
+@pytest.mark.parametrize("agent", [1, 2, 3])
+@pytest.mark.parametrize("family,P", [("small_bridge", 1), ("small_bridge", 17), ("small_roof", 50), ("large_bridge", 50), ("large_roof", 17)])
+def test_trained_checkpoint_on_golden_states(agent, family, P):
+    """The trained 2000pickle_base actors (the checkpoint every test/ driver loads) on states recorded from the reference
+    environment, with Pareto graphs of 1, 17 and 50 rows where the front fills only part of the rows (zero padding).  The
+    fp16 hi/lo operand split must stay in range on the real weights (status 0) and agree with the float64 oracle."""
+    from mop_truss_marl_b200 import actor
+    from oracle.actor_oracle import actor_forward
+    from util import load_golden
+    g = load_golden(family)
+    w = trained_weights(agent)
+    rng = np.random.RandomState(100 * agent + P)
+    x_n = np.concatenate([g["reset_x_n"][None], g["tr_out_x_n"]]).astype(np.float32)
+    A_s = np.concatenate([g["reset_A_s"][None], g["tr_out_A_s"]]).astype(np.float32)
+    A_ts = np.concatenate([g["reset_A_n_ts"][None], g["tr_out_A_n_ts"]]).astype(np.float32)
+    A_cs = np.concatenate([g["reset_A_n_cs"][None], g["tr_out_A_n_cs"]]).astype(np.float32)
+    B, N = x_n.shape[0], x_n.shape[1]
+    sizes = rng.randint(1, P + 1, size=B)
+    sizes[0] = P                                      # one full front
+    x_p, A_p = padded_pareto_graph(rng, B, P, sizes)
+    a = actor.BatchedActor(w, N, max_batch=B)
+    dev = [torch.from_numpy(np.ascontiguousarray(t)).cuda() for t in (x_n, g["A_n"], A_s, A_ts, A_cs, x_p, A_p)]
+    geo, topo = a.forward(*dev)
+    a.check()                                         # tactor_status == 0: no activation left the fp16 range
+    g64, t64 = actor_forward(w, x_n, g["A_n"], A_s, A_ts, A_cs, x_p, A_p)
+    assert np.abs(geo.cpu().numpy() - g64).max() <= ATOL
+    assert np.abs(topo.cpu().numpy() - t64).max() <= ATOL
+    # both the float32 restatement (what TensorFlow computes in) and the kernel stay within 1e-5 of float64
+    g32, t32 = actor_forward(w, x_n, g["A_n"], A_s, A_ts, A_cs, x_p, A_p, dtype=np.float32)
+    err_kernel = max(np.abs(geo.cpu().numpy() - g64).max(), np.abs(topo.cpu().numpy() - t64).max())
+    err_f32 = max(np.abs(g32 - g64).max(), np.abs(t32 - t64).max())
+    assert err_kernel <= 1e-5 and err_f32 <= 1e-5, (err_kernel, err_f32)
+    # optional pin against TensorFlow + spektral outputs recorded elsewhere (scripts/make_actor_golden_tf.py)
+    import os
+    tf_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "actor_tf.npz")
+    if os.path.exists(tf_path):
+        z = np.load(tf_path)
+        key = "agent%d/%s/P%d" % (agent, family, P)
+        if key + "/geo" in z.files:
+            gt, tt = actor_forward(w, z[key + "/x_n"], g["A_n"], z[key + "/A_s"], z[key + "/A_n_ts"], z[key + "/A_n_cs"], z[key + "/x_p"], z[key + "/A_p"])
+            assert np.abs(gt - z[key + "/geo"]).max() <= 1e-5 and np.abs(tt - z[key + "/topo"]).max() <= 1e-5
