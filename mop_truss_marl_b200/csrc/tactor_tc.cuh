@@ -182,8 +182,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 //   B [16 x 8]  col-major: b0 (k 2t..2t+1, col g)  b1 (k 2t+8.., col g)
 //   C [16 x 8]           : c0 c1 (row g, cols 2t, 2t+1)  c2 c3 (row g+8, same cols)
 __device__ __forceinline__ void hmma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-#ifdef TACTOR_ABLATE_HMMA   // timing experiment only (wrong results): the generators without their warp-level tensor-core products
-  c[0] += __uint_as_float(a[0] ^ b0); c[1] += __uint_as_float(a[1] ^ b1); c[2] += __uint_as_float(a[2] ^ b0); c[3] += __uint_as_float(a[3] ^ b1);
+#ifdef TACTOR_ABLATE_HMMA   // timing experiment only (wrong results): the generators without their warp-level tensor-core products;
+  // the empty asm keeps the accumulators opaque to the optimiser and emits nothing
+  asm volatile("" : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   return;
 #endif
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"

@@ -220,7 +220,7 @@ def test_tmem_store_layout_selftest():
     actor.selftest_tmem_layout(0)
 
 
-@pytest.mark.parametrize("variant", ["1", "2"])
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4"])
 def test_generator_variants_match_production(variant, monkeypatch):
     """TACTOR_VARIANT selects other (generator phases, epilogue warps) builds of the fused kernel, kept for A/B timing;
     the hidden layers are the same arithmetic in all of them, only the head's 200-term sum is split differently between
