@@ -103,7 +103,7 @@ def oracle_steps_per_sec(family, seconds, seed=0, with_actor=False):
     if with_actor:
         from oracle import actor_oracle
         from mop_truss_marl_b200.tf_checkpoint import random_actor_weights
-        w = random_actor_weights(seed=20)
+        w = trained_actor_weights(1) or random_actor_weights(seed=20)
         x_p = np.array([[1, 1, 1, 1 / 50]], dtype=np.float32)
         A_p = np.ones((1, 1), dtype=np.float32)
 
@@ -182,7 +182,7 @@ def run_reference_arm(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_seconds * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 (FEM) + f32 (actor)" if with_actor else "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "family": args.family, "envs_per_gpu": args.batch},
+        "config": bench_config(args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d processes x %.2f s of oracle env-steps per bench step (one env each, %s, own "
                                    "state fed back)" % (cores, per_step_seconds,
@@ -201,11 +201,270 @@ def workload_name(args):
         args.family, args.batch)
 
 
+def cpu_baselines(args):
+    """(cpu_baseline, cpu_baseline_c_env_step) of the JSON line: the Python oracle port on one core (numpy actor + env-step)
+    and the C port of the env-step on every host core, each on a bounded sample"""
+    use_actor = not args.no_actor
+    n_cpu, t_cpu = oracle_steps_per_sec(args.family, args.cpu_seconds, with_actor=use_actor)
+    factor = ""
+    fpath = os.path.join(ROOT, "profiles", "r2_port_vs_reference.json")
+    if os.path.exists(fpath):
+        try:
+            f = json.load(open(fpath)).get(args.family)
+            if f:
+                factor = ("; the port runs %.2fx the steps/s of the reference's own _game_modify loop (measured once in the "
+                          "build container, scripts/port_vs_reference.py: %.0f vs %.0f env-steps/s on one core, env-step only)"
+                          % (f["port_over_reference"], f["port_steps_per_s"], f["reference_steps_per_s"]))
+        except Exception:
+            pass
+    cpu_line = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "%d oracle steps (%s) of %s in %.1f s, one process%s" % (
+                    n_cpu, "numpy actor + env-step" if use_actor else "env-step", args.family, t_cpu, factor)}
+    try:
+        nc, tc, cores_c = c_oracle_env_steps_per_sec(args.family, seconds=min(3.0, max(0.3, args.cpu_seconds / 4)))
+        c_line = {"value": nc / tc, "unit": UNIT, "cores": cores_c, "kind": "port",
+                  "sample": "%d env-steps of %s in %.2f s: oracle/truss_oracle.c (C, OpenMP), FEM env-step only "
+                            "(transition + solve + objectives, no observation tensors, no actor)" % (nc, args.family, tc)}
+    except Exception as exc:                          # no gcc on the box: the Python port above is the baseline
+        c_line = {"unavailable": str(exc)[:200]}
+    return cpu_line, c_line
+
+
+def family_dims(family):
+    """(nodes, elements, free dofs) of a family from the oracle's mesh tables (no GPU needed: both arms print them)"""
+    from oracle.truss_oracle import FAMILIES, build_mesh
+    m = build_mesh(FAMILIES[family])
+    return int(m.N), int(m.E), int(m.ndof)
+
+
+def trained_actor_weights(agent):
+    """the reference's trained checkpoint model/2000pickle_base/Agent<agent>_Actor_pickle, from the committed fixture
+    tests/golden/actor_2000pickle_base.npz (tests/golden/make_actor_golden.py); None when the fixture is absent"""
+    from mop_truss_marl_b200.tf_checkpoint import ACTOR_LAYERS
+    path = os.path.join(ROOT, "tests", "golden", "actor_2000pickle_base.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    return {name: (z["agent%d/%s/kernel" % (agent, name)], z["agent%d/%s/bias" % (agent, name)]) for name in ACTOR_LAYERS}
+
+
+def bench_config(args, world):
+    """the `config` object of the JSON line: identical for the B200 arm and the reference arm"""
+    N, E, ndof = family_dims(args.family)
+    use_actor = not args.no_actor
+    trained = use_actor and trained_actor_weights(1) is not None
+    return {"workload": workload_name(args), "family": args.family, "envs_per_gpu": args.batch,
+            "nodes": N, "elements": E, "free_dofs": ndof,
+            "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB write; B200 arm only: the CPU arm has no such cache to flush)",
+            "actions": (("actor outputs (trained 2000pickle_base checkpoint, agent 1 + rank % 3)" if trained else
+                         "actor outputs (random-init weights of the reference architecture)") + " + OU noise"
+                        if use_actor else "uniform [0,1) float32") + ", coin Bernoulli(1/2), own state fed back",
+            "parallelism": "env-parallel, %d independent shard(s), no collective" % world}
+
+
 def actor_flops(N, P=1, H=200):
     """multiply-adds x2 of one actor forward for one environment (GEMMs + adjacency products)"""
     gemm = 3 * N * 13 * H + P * 4 * H + 7 * N * H * H + N * H * 5
     adj = 10 * N * N * H + P * P * H + 2 * N * N * 5
     return 2 * (gemm + adj)
+
+
+def _max_over_ranks(ms, dev, world):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def fem_leg(family, B, rank, world, dev, flush, what, steps=50, warmup=5):
+    """FEM env-step alone (resident uniform actions, own state fed back) at one of BASELINE.json's named shapes"""
+    import torch
+    import torch.distributed as dist
+    from mop_truss_marl_b200 import batched_env
+    env = batched_env.BatchedTrussEnv(family, B, device=dev, fp64_outputs=True)
+    env.reset()
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    acts = [(torch.rand(B, env.N, 2, device=dev, generator=gen), torch.rand(B, env.N, 3, device=dev, generator=gen),
+             (torch.rand(B, device=dev, generator=gen) >= 0.5).to(torch.uint8)) for _ in range(8)]
+    for i in range(8 + warmup):
+        env.step(acts[i % 8][0].clone(), acts[i % 8][1].clone(), acts[i % 8][2])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total = 0.0
+    for i in range(steps):
+        a_geo, a_topo = acts[i % 8][0].clone(), acts[i % 8][1].clone()     # the step clips its actions in place
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env.step(a_geo, a_topo, acts[i % 8][2])
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    ms = _max_over_ranks(total / steps, dev, world)
+    bad = int((env.status != 0).sum().item())
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    abytes = algorithmic_bytes(env.N, env.E, env.ndof)
+    return {"workload": what, "family": family, "envs_per_gpu": B, "n_gpus": world, "value": B * world / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "scaling": "strong" if family == "small_roof" else "weak",
+            "roofline_fem": {"bound": "hbm", "achieved": abytes * B / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": abytes * B / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_env": abytes},
+            "status_nonzero_envs": bad}
+
+
+def actor_leg(env, pol, P, dev, flush, world, steps=30, warmup=5):
+    """the actor stage alone with a Pareto graph of P rows (a chain graph over a full front, truss2D_ENV.py:22-41)"""
+    import torch
+    from mop_truss_marl_b200.pareto_graph import chain_graph
+    B, N = env.B, env.N
+    x_p_np, A_p_np = chain_graph(P)
+    x_p = torch.from_numpy(x_p_np).to(dev).repeat(B, 1, 1).contiguous()
+    A_p = torch.from_numpy(A_p_np).to(dev).repeat(B, 1, 1).contiguous()
+    geo, topo = torch.empty(B, N, 2, device=dev), torch.empty(B, N, 3, device=dev)
+    for _ in range(warmup):
+        pol.act(env.x_n, env.A_n, env.A_s, env.A_n_ts, env.A_n_cs, x_p, A_p, out=(geo, topo))
+    torch.cuda.synchronize()
+    total = 0.0
+    for i in range(steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pol.act(env.x_n, env.A_n, env.A_s, env.A_n_ts, env.A_n_cs, x_p, A_p, out=(geo, topo))
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    pol.check()
+    ms = _max_over_ranks(total / steps, dev, world)
+    return {"workload": "actor stage (Pareto branch + fused network + OU noise) with a %d-row Pareto graph" % P, "P": P,
+            "envs_per_gpu": B, "actor_ms": ms, "actor_forwards_per_s": B * world / (ms * 1e-3)}
+
+
+def train_leg(args, rank, local_rank, world, dev, steps=10, standalone=False, family="large_roof", B=1024, P=50):
+    """BASELINE.json configs[4]: the multi-agent DDPG training loop on the large roof -- per step the three agents' CUDA
+    actors act on the batch's parent state, the three child states are evaluated by three env-steps, a slice of the
+    transitions enters the device-resident replay, and one MADDPG.train() + update() follows (one update per game step,
+    train/code/master_DDPG_truss2D_MO.py:647-649) with the gradients of every model averaged over the ranks by one
+    flat-buffer NCCL all-reduce each (learner.allreduce_flat); the updated actors are pushed into the CUDA actor handles.
+    Rewards are synthetic (minus the child's two objectives and their sum): the driver's Pareto / hypervolume reward is outside
+    the hot path."""
+    import torch
+    import torch.distributed as dist
+    from mop_truss_marl_b200 import actor as actor_mod
+    from mop_truss_marl_b200 import batched_env, learner as learner_mod
+    from mop_truss_marl_b200.pareto_graph import chain_graph
+    parent = batched_env.BatchedTrussEnv(family, B, device=dev, fp64_outputs=False)
+    parent.reset()
+    children = [batched_env.BatchedTrussEnv(family, B, device=dev, fp64_outputs=False) for _ in range(3)]
+    N = parent.N
+    lrn = learner_mod.MADDPGLearner(lr=1e-7, batch_size=32, device=dev, seed=20)       # same seed on every rank: identical models
+    lrn.keep_losses_on_device = True
+    lrn.device_replay = learner_mod.DeviceReplay(4096, N, P, dev, seed=1000 + rank)     # each rank holds its own replay shard
+    for k in range(3):
+        w = trained_actor_weights(k + 1)
+        if w is not None:
+            lrn.agents[k].actor.import_weights(w)
+        lrn.agents[k].update_init()
+    pols = [actor_mod.BatchedActor(lrn.actor_weights(k), N, B, device=dev, seed=20 + 1000 * rank + k) for k in range(3)]
+    x_p_np, A_p_np = chain_graph(P)
+    x_p = torch.from_numpy(x_p_np).to(dev).repeat(B, 1, 1).contiguous()
+    A_p = torch.from_numpy(A_p_np).to(dev).repeat(B, 1, 1).contiguous()
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    keep = torch.arange(0, B, B // 64, device=dev)[:64]                                   # 64 transitions per step enter the replay
+    acts = [(torch.empty(B, N, 2, device=dev), torch.empty(B, N, 3, device=dev)) for _ in range(3)]
+    ev = lambda: torch.cuda.Event(enable_timing=True)                                    # noqa: E731
+    ar_events = []
+    orig_allreduce = learner_mod.allreduce_flat
+
+    def timed_allreduce(params, group=None):
+        e0, e1 = ev(), ev()
+        e0.record()
+        n = orig_allreduce(params, group)
+        e1.record()
+        ar_events.append((e0, e1))
+        return n
+    learner_mod.allreduce_flat = timed_allreduce
+
+    def state_of(e):
+        return {"x_n": e.x_n, "A_n": e.A_n, "A_s": e.A_s, "A_n_ts": e.A_n_ts, "A_n_cs": e.A_n_cs, "x_p": x_p, "A_p": A_p}
+
+    def one_step(timed):
+        t = [ev() for _ in range(5)] if timed else None
+        if timed:
+            t[0].record()
+        coin = (torch.rand(B, device=dev, generator=gen) >= 0.5).to(torch.uint8)
+        for k in range(3):
+            pols[k].act(parent.x_n, parent.A_n, parent.A_s, parent.A_n_ts, parent.A_n_cs, x_p, A_p, out=acts[k])
+            children[k].step(acts[k][0], acts[k][1], coin, parent=parent)
+        if timed:
+            t[1].record()
+        rewards = torch.stack([-children[0].point[:, 0], -children[1].point[:, 1],
+                               -(children[2].point[:, 0] + children[2].point[:, 1])], dim=1)
+        lrn.device_replay.push(state_of(parent), acts, rewards, [state_of(c) for c in children], 0.0, rows=keep)
+        if timed:
+            t[2].record()
+        trained = lrn.train()
+        lrn.update()
+        if timed:
+            t[3].record()
+        if trained:
+            for k in range(3):
+                pols[k].set_weights(lrn.actor_weights(k))
+        # the game moves on along agent 0's child (the driver keeps a front of candidates; one parent per environment here)
+        for name in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range", "point"):
+            getattr(parent, name).copy_(getattr(children[0], name))
+        if timed:
+            t[4].record()
+        return t
+    for _ in range(3):
+        one_step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ar_events.clear()
+    el0 = lrn.allreduced_elements
+    t0 = time.perf_counter()
+    stamps = [one_step(True) for _ in range(steps)]
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    learner_mod.allreduce_flat = orig_allreduce
+    seg = lambda a, b: float(np.mean([s[a].elapsed_time(s[b]) for s in stamps]))       # noqa: E731
+    ar_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in ar_events)) / steps
+    step_ms = _max_over_ranks(wall_ms, dev, world)
+    for p_ in pols:
+        p_.check()
+    # every rank must hold the same models after the same all-reduced updates
+    chk = torch.cat([p.detach().reshape(-1) for p in lrn.agents[0].actor.parameters()]).double().sum()
+    same = True
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(lo.item() == hi.item())
+    line = {
+        "workload": "%s B=%d per GPU: three-agent DDPG training loop (3 x actor act + 3 x FEM env-step, device replay, "
+                    "MADDPG train + update per game step, gradient all-reduce, actor weights pushed to the CUDA actors)" % (family, B),
+        "family": family, "envs_per_gpu": B, "n_gpus": world, "steps": steps,
+        "value": 3 * B * world / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms,
+        "updates_per_s": 1e3 / step_ms, "replay_transitions_per_step": int(keep.numel()), "learner_batch": lrn.batch_size,
+        "stages_ms": {"rollout_3x_act_3x_env_step": seg(0, 1), "replay_push": seg(1, 2), "learner_train_update": seg(2, 3),
+                      "of_which_all_reduce": ar_ms, "weight_push_and_state_advance": seg(3, 4)},
+        "all_reduce": {"backend": dist.get_backend() if world > 1 else None, "ranks": world,
+                       "calls_per_step": len(ar_events) / steps,
+                       "bytes_per_step": 4 * (lrn.allreduced_elements - el0) / steps,
+                       "share_of_step": ar_ms / step_ms},
+        "models_identical_across_ranks": same,
+        "rewards": "synthetic (minus the child's objectives)", "data": "synthetic",
+    }
+    if standalone:
+        line = {"metric": METRIC + ", training loop", "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 (FEM) + f32 (actor, learner)", **line}
+    return line
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -222,6 +481,9 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--e2e-pieces", type=int, default=2, help="pieces the batch is cut into on the end-to-end path")
     ap.add_argument("--no-actor", action="store_true", help="drive the env with resident uniform actions instead of the actor")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (BASELINE configs 3 and 4 shapes, actor at P = 50, training leg)")
+    ap.add_argument("--train", action="store_true", help="only the training loop of BASELINE config 5 (large roof, MADDPG update with gradient all-reduce)")
+    ap.add_argument("--train-steps", type=int, default=0, help="timed steps of the training leg (default: 10, or --steps with --train)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -239,10 +501,22 @@ def main():
     from mop_truss_marl_b200 import actor as actor_mod
     from mop_truss_marl_b200 import batched_env, capi, tf_checkpoint
 
+    # the CPU baselines run on rank 0 BEFORE the process group exists: the other ranks wait in the TCP rendezvous of
+    # init_process_group, not in an NCCL barrier that would keep their GPUs spinning for the 15 s this takes
+    cpu_lines = cpu_baselines(args) if (rank == 0 and not args.train) else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=20))
+    if args.train:
+        line = train_leg(args, rank, local_rank, world, dev, steps=args.train_steps or args.steps, standalone=True)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     B, K, W = args.batch, args.steps, max(3, args.warmup)
     env = batched_env.BatchedTrussEnv(args.family, B, device=dev)
@@ -261,7 +535,10 @@ def main():
     if use_actor:
         # random-init weights of the reference architecture (no checkpoint travels to the GPU box); the
         # Pareto-front graph is the reset-time one-node graph of _game_get_1_state (truss2D_ENV.py:346-352)
-        pol = actor_mod.BatchedActor(tf_checkpoint.random_actor_weights(seed=20 + rank), N, B, device=dev)
+        # the trained checkpoint when its fixture travelled with the repository, else random-init weights of the
+        # reference architecture; OU-noise seeds differ per rank (the noise field is a function of seed and call index)
+        weights = trained_actor_weights(1 + rank % 3) or tf_checkpoint.random_actor_weights(seed=20 + rank)
+        pol = actor_mod.BatchedActor(weights, N, B, device=dev, seed=20 + 1000 * rank)
         x_p = torch.tensor([1.0, 1.0, 1.0, 1.0 / 50], device=dev).repeat(B, 1, 1).contiguous()
         A_p = torch.ones(B, 1, 1, device=dev)
         a_geo_buf = torch.empty(B, N, 2, device=dev)
@@ -416,6 +693,19 @@ def main():
                    "path": "state tuple resident in HBM (BatchedTrussEnv); per step: pinned coins + Pareto graph -> device, "
                            "BatchedActor.act + BatchedTrussEnv.step, point + status -> pinned host, stream sync"}
     clocks = sampler.result()
+    extra = None
+    if not args.no_extras:
+        # the shapes BASELINE.json configs 3 and 4 name, FEM env-step only, and the actor with a full Pareto graph
+        extra = {
+            "config3": fem_leg("small_roof", max(1, 16384 // world), rank, world, dev, flush,
+                               "small roof, 16384 environments in TOTAL split over the ranks (strong scaling)"),
+            "config4": fem_leg("large_bridge", 1024, rank, world, dev, flush,
+                               "large bridge, 1024 environments per GPU (8192 across 8)"),
+        }
+        if use_actor:
+            extra["actor_pareto_P50"] = actor_leg(env, pol, 50, dev, flush, world)
+        if world == 8:
+            extra["config5"] = train_leg(args, rank, local_rank, world, dev, steps=args.train_steps or 10, standalone=False)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -459,37 +749,25 @@ def main():
                                 "flops vs the bf16 tensor roof (formulation ceiling = roof/3)"}
         else:
             roofline = roof_fem
-        n_cpu, t_cpu = oracle_steps_per_sec(args.family, args.cpu_seconds, with_actor=use_actor)
-        try:
-            nc, tc, cores_c = c_oracle_env_steps_per_sec(args.family, seconds=min(3.0, max(0.3, args.cpu_seconds / 4)))
-            c_line = {"value": nc / tc, "unit": UNIT, "cores": cores_c, "kind": "port",
-                      "sample": "%d env-steps of %s in %.2f s: oracle/truss_oracle.c (C, OpenMP), FEM env-step only "
-                                "(transition + solve + objectives, no observation tensors, no actor)" % (nc, args.family, tc)}
-        except Exception as exc:                          # no gcc on the box: the Python port above is the baseline
-            c_line = {"unavailable": str(exc)[:200]}
+        cpu_line, c_line = cpu_lines
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 (FEM) + f32 (actor)" if use_actor else "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "family": args.family, "envs_per_gpu": B,
-                       "nodes": N, "elements": E, "free_dofs": env.ndof,
-                       "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
-                       "actions": ("actor outputs (random-init weights of the reference architecture) + OU noise"
-                                   if use_actor else "uniform [0,1) float32") + ", coin Bernoulli(1/2), own state fed back",
-                       "parallelism": "env-parallel, %d independent shard(s), no collective" % world},
+            "config": bench_config(args, world),
             "roofline": roofline,
             "roofline_fem": roof_fem,
             "stages": stages,
-            "cpu_baseline": {"value": n_cpu / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "%d oracle steps (%s) of %s in %.1f s, one process" % (
-                                 n_cpu, "numpy actor + env-step" if use_actor else "env-step", args.family, t_cpu)},
+            "cpu_baseline": cpu_line,
             "cpu_baseline_c_env_step": c_line,
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "path": e2e_path},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "path": e2e_path,
+                    "h2d_gbs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9, "d2h_gbs_per_rank": d2h / (e2e_ms * 1e-3) / 1e9},
             "e2e_resident_state": e2e_res,
             "gpu_launches": launches,
             "clocks": clocks,
             "status_nonzero_envs": status_bad,
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

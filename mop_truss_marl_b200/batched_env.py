@@ -98,12 +98,15 @@ class BatchedTrussEnv:
         return self.state()
 
     def step(self, a_geo: torch.Tensor, a_topo: torch.Tensor, coin: torch.Tensor | None = None,
-             rows: tuple | None = None):
+             rows: tuple | None = None, parent: "BatchedTrussEnv | None" = None):
         """a_geo [B,N,2], a_topo [B,N,3] float32 CUDA tensors (clipped in place, like the reference);
         coin [B] uint8/bool (1 = ``random.random() >= 0.5``).  Updates the state in place and returns
         ``point`` [B,4].  ``rows=(lo, hi)`` steps only environments lo..hi-1 (the action / coin tensors then
         hold hi-lo environments): the environments are independent, so a batch can be stepped in pieces on
-        different streams (``host_pipeline.HostRollout``)."""
+        different streams (``host_pipeline.HostRollout``).  ``parent``: read the parent geometry (raw tables + the
+        stale move range) from another environment batch of the same family and size and leave it untouched -- the
+        driver's "three agents act on the same parent state" (``master_DDPG_truss2D_MO.py:262-330``): this batch
+        becomes the child state."""
         lo, hi = (0, self.B) if rows is None else rows
         if not (0 <= lo < hi <= self.B):
             raise ValueError("rows must satisfy 0 <= lo < hi <= batch")
@@ -115,9 +118,15 @@ class BatchedTrussEnv:
                 coin = coin.to(torch.uint8)
             if coin.dtype != torch.uint8 or coin.shape != (nb,) or coin.device != self.device or not coin.is_contiguous():
                 raise ValueError("coin must be a contiguous uint8 [B] tensor on the env device")
+        src = self
+        if parent is not None:
+            if parent.B != self.B or parent.N != self.N or parent.E != self.E or parent.device != self.device:
+                raise ValueError("parent must be a batch of the same family, size and device")
+            self.move_range[lo:hi].copy_(parent.move_range[lo:hi])
+            src = parent
         sin = capi.StepIn()
-        sin.set_node = _ptr(self.nN_x_n[lo:hi])
-        sin.set_element = _ptr(self.nN_x_e[lo:hi])
+        sin.set_node = _ptr(src.nN_x_n[lo:hi])
+        sin.set_element = _ptr(src.nN_x_e[lo:hi])
         sin.a_geo = _ptr(a_geo)
         sin.a_topo = _ptr(a_topo)
         sin.coin = _ptr(coin)

@@ -39,8 +39,12 @@ template <int NODES>
 __global__ void __launch_bounds__(256)
 pareto_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
               int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out,
-              int B) {
+              int B, const int* __restrict__ only_flagged) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (only_flagged) {                      // second pass behind pareto_tri_kernel: only the environments it could not take
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x < B && only_flagged[blockIdx.x] == 0) return;
+  }
   extern __shared__ __align__(16) float psm[];
   float* ts = psm;                        // [P][LD]   x_p W14          (the launch sizes the buffer for this P: a
   float* red = ts + P * LD;               // [4][LD]   per-slice sums     small front keeps many CTAs per SM)
@@ -106,8 +110,12 @@ template <int NODES>
 __global__ void __launch_bounds__(256)
 pareto_small_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
                     int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out,
-                    int B) {
+                    int B, const int* __restrict__ only_flagged) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (only_flagged) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x < B && only_flagged[blockIdx.x] == 0) return;
+  }
   __shared__ float xs[PSMALL * 4];
   __shared__ float as[PSMALL * PSMALL];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -165,6 +173,88 @@ pareto_p1_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, c
   }
 }
 
+// Tridiagonal A_p -- the only Pareto graph the reference builds (pareto_state_data: a chain over the front with self loops,
+// symmetrically normalised, zero rows / columns as padding; truss2D_ENV.py:22-41, master_DDPG_truss2D_MO.py:499-517).
+// U[p] = a[p][p-1] T[p-1] + a[p][p] T[p] + a[p][p+1] T[p+1] instead of the dense P x P product: one WARP per environment, a
+// lane owns the feature columns lane, lane + 32, ..., T slides through three registers per column.  The whole of A_p is still
+// read (once, coalesced): an entry outside the band sends the environment to the dense kernel (flag[b] = 1), so any A_p
+// gives the same result as before.  Same operation order as the dense kernels (the skipped terms are exact zeros), same
+// grouping of the pooled sum, hence bit-identical pooled rows.
+constexpr int TRI_WARPS = 8;
+__global__ void __launch_bounds__(TRI_WARPS * 32)
+pareto_tri_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, const int32_t* __restrict__ n_pf,
+                  int P, const float* __restrict__ W14, const float* __restrict__ b14, float* __restrict__ pooled_out,
+                  int B, int* __restrict__ flag) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __shared__ float diag_s[TRI_WARPS][3][52];
+  __shared__ float4 x_s[TRI_WARPS][52];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * TRI_WARPS + warp;
+  if (b >= B) return;
+  float (*dg)[52] = diag_s[warp];
+  // ---- A_p: the three diagonals into shared memory, anything else must be zero ----
+  const float* A = A_p + (size_t)b * P * P;
+  bool off = false;
+  for (int i = lane; i < 3 * 52; i += 32) (&dg[0][0])[i] = 0.f;
+  __syncwarp();
+  int i = 0, j = lane;
+  while (j >= P) { j -= P; ++i; }
+  for (int idx = lane; idx < P * P; idx += 32) {
+    const float v = __ldg(A + idx);
+    const int dj = j - i;
+    if (dj >= -1 && dj <= 1) dg[dj + 1][i] = v;
+    else off = off || (v != 0.f);
+    j += 32;
+    while (j >= P) { j -= P; ++i; }
+  }
+  for (int p = lane; p < P; p += 32) x_s[warp][p] = __ldg(reinterpret_cast<const float4*>(x_p + (size_t)b * P * 4) + p);
+  off = __any_sync(0xffffffffu, off);
+  if (lane == 0) flag[b] = off ? 1 : 0;
+  if (off) return;                                           // the dense kernel behind this one takes it
+  __syncwarp();
+  const int valid = n_pf ? min(max(n_pf[b], 0), P) : P;
+  constexpr int NC = 7;                                      // columns per lane: lane + 32 k < 200
+  float w0[NC], w1[NC], w2[NC], w3[NC], bias[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int h = lane + 32 * k;
+    const bool in = h < HID;
+    w0[k] = in ? W14[0 * LD + h] : 0.f; w1[k] = in ? W14[1 * LD + h] : 0.f;
+    w2[k] = in ? W14[2 * LD + h] : 0.f; w3[k] = in ? W14[3 * LD + h] : 0.f;
+    bias[k] = in ? b14[h] : 0.f;
+  }
+  auto trow = [&](int p, float* t) {                         // T[p][h] = x_p[p] . W14[:, h], the kernels' common operation order
+    const float4 x = (p >= 0 && p < P) ? x_s[warp][p] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) t[k] = fmaf(x.w, w3[k], fmaf(x.z, w2[k], fmaf(x.y, w1[k], x.x * w0[k])));
+  };
+  float tp[NC], tc[NC], tn[NC], sum[4][NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) { tp[k] = 0.f; sum[0][k] = sum[1][k] = sum[2][k] = sum[3][k] = 0.f; }
+  trow(0, tc);
+  const bool sliced = P > PSMALL;                            // the dense kernel for P > 16 pools in four slices of 13 rows
+  for (int p = 0; p < valid; ++p) {
+    trow(p + 1, tn);
+    const float al = dg[0][p], ad = dg[1][p], au = dg[2][p];
+    const int sl = sliced ? p / PSL : 0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      float u = 0.f;
+      if (p > 0) u = fmaf(al, tp[k], u);
+      u = fmaf(ad, tc[k], u);
+      if (p + 1 < P) u = fmaf(au, tn[k], u);
+      const float r = fmaxf(u + bias[k], 0.f);
+      if (sl == 0) sum[0][k] += r; else if (sl == 1) sum[1][k] += r; else if (sl == 2) sum[2][k] += r; else sum[3][k] += r;
+      tp[k] = tc[k]; tc[k] = tn[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int h = lane + 32 * k;
+    if (h < LD) pooled_out[(size_t)b * LD + h] = (h < HID) ? ((sum[0][k] + sum[1][k]) + (sum[2][k] + sum[3][k])) : 0.f;
+  }
+}
+
 // tactor_selftest_tmem_layout: every warp stores a tagged accumulator-layout fragment with tcgen05.st.16x128b.x2 at lane
 // offsets 0 and 16 and reads its 32 lanes back with the row-per-thread shape (tcgen05.ld.32x32b.x8)
 __global__ void __launch_bounds__(128) tmem_layout_selftest_kernel(uint32_t* out) {
@@ -210,6 +300,8 @@ struct tactor_handle_s {
   float* d_w[TACTOR_NLAYERS] = {};     // packed [Kpad, 208]
   float* d_b[TACTOR_NLAYERS] = {};     // [208]
   float* pooled = nullptr;             // [max_batch, 208] Pareto embedding
+  int* pareto_flag = nullptr;          // [max_batch] 1 = A_p of this environment is not tridiagonal (dense kernel takes it)
+  int pareto_dense = 0;                // TACTOR_PARETO_DENSE=1: always the dense kernels (A/B timing, tests)
   float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
   uint32_t* d_w1frag = nullptr;        // mma.sync A-fragment image of the three layer-1 kernels (tactor_pipe.cuh)
   float* d_wscale_inv = nullptr;       // [NGEMM + 3] 1 / power-of-two scale of d_wimg[4 + g] and of the three layer-1 images
@@ -414,10 +506,30 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   float* pooled = h->pooled;
   if (in->P == 1 && (reinterpret_cast<uintptr_t>(in->x_p) & 15u) == 0)
     pareto_p1_kernel<<<(B + P1_ENVS - 1) / P1_ENVS, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, h->d_w[3], h->d_b[3], pooled, B);
-  else if (in->P <= PSMALL)
-    pareto_small_kernel<NODES><<<B, 256, 0, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
-  else
-    pareto_kernel<NODES><<<B, 256, pareto_smem(in->P), st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3], h->d_b[3], pooled, B);
+  else {
+    // the chain graph of pareto_state_data is tridiagonal: one warp per environment; environments with any entry outside
+    // the band are flagged and redone by the dense kernel, which returns at once for the others
+    const int* only = nullptr;
+    if (!h->pareto_dense && (reinterpret_cast<uintptr_t>(in->x_p) & 15u) == 0) {
+      pareto_tri_kernel<<<(B + TRI_WARPS - 1) / TRI_WARPS, TRI_WARPS * 32, 0, st>>>(in->x_p, in->A_p, in->n_pf, in->P, h->d_w[3],
+                                                                                   h->d_b[3], pooled, B, h->pareto_flag);
+      only = h->pareto_flag;
+      h->launches.fetch_add(1);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)B); cfg.blockDim = dim3(256); cfg.stream = st;
+    cfg.dynamicSmemBytes = in->P <= PSMALL ? 0 : pareto_smem(in->P);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = only ? 1 : 0;
+    if (in->P <= PSMALL)
+      cudaLaunchKernelEx(&cfg, pareto_small_kernel<NODES>, in->x_p, in->A_p, in->n_pf, (int)in->P, (const float*)h->d_w[3],
+                         (const float*)h->d_b[3], pooled, B, only);
+    else
+      cudaLaunchKernelEx(&cfg, pareto_kernel<NODES>, in->x_p, in->A_p, in->n_pf, (int)in->P, (const float*)h->d_w[3],
+                         (const float*)h->d_b[3], pooled, B, only);
+  }
   tc::fused::Params p{};
   p.x_n = in->x_n; p.A_n = in->A_n; p.A_s = in->A_s; p.A_ts = in->A_n_ts; p.A_cs = in->A_n_cs; p.pooled = pooled;
   for (int k = 0; k < 3; ++k) { p.w1[k] = h->d_w[k]; p.b1[k] = h->d_b[k]; }
@@ -463,6 +575,8 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
     e = (nodes == 16) ? cudaFuncSetAttribute(tactor::pareto_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM)
                       : cudaFuncSetAttribute(tactor::pareto_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM);
   if (e == cudaSuccess) e = cudaMalloc(&h->pooled, (size_t)max_batch * tactor::LD * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&h->pareto_flag, (size_t)max_batch * sizeof(int));
+  if (const char* v = getenv("TACTOR_PARETO_DENSE")) h->pareto_dense = (v[0] == '1');
   if (e != cudaSuccess) { tactor_destroy(h); return afail(TFEM_ERR_CUDA, std::string("actor setup: ") + cudaGetErrorString(e)); }
   *out = h;
   return TFEM_OK;
@@ -484,6 +598,7 @@ int tactor_destroy(tactor_handle_t h) {
   Guard g(h->device);
   for (int l = 0; l < TACTOR_NLAYERS; ++l) { if (h->d_w[l]) cudaFree(h->d_w[l]); if (h->d_b[l]) cudaFree(h->d_b[l]); }
   if (h->pooled) cudaFree(h->pooled);
+  if (h->pareto_flag) cudaFree(h->pareto_flag);
   for (int l = 0; l < TACTOR_NLAYERS; ++l) if (h->d_wimg[l]) cudaFree(h->d_wimg[l]);
   if (h->d_error) cudaFree(h->d_error);
   if (h->d_w1frag) cudaFree(h->d_w1frag);

@@ -9,7 +9,8 @@ Restates ``train/code/truss2D_RL.py``:
 
 ``GCNConv`` = ``A . (X . W) + b`` (spektral 1.2.0), ``GlobalSumPool`` = sum over nodes.  Quirks kept on purpose:
 the Pareto embedding is tiled and ``tf.reshape``-d, not transposed (:89-95, :190-195); the critic target averages the
-three per-agent next states (:611-618); the actor step builds a NEW Adam every call (:625, so every step is Adam's
+three per-agent next states (:611-618) and ALWAYS bootstraps (the terminal test at :606 compares an action array with
+``1``); the actor step builds a NEW Adam every call (:625, so every step is Adam's
 first step) with ``lr * 0.1`` and ``clipnorm=1``; targets move by ``tau = 0.005`` only every 1000 calls (:392-398).
 
 When the replay / learner is partitioned over ranks, gradients are averaged with ONE flat-buffer all-reduce per model
@@ -175,6 +176,66 @@ class _Agent:
 STATE_KEYS = ("x_n", "A_n", "A_s", "A_n_ts", "A_n_cs", "x_p", "A_p")
 
 
+class DeviceReplay:
+    """Replay memory resident on the learner's device: a ring of ``capacity`` transitions in preallocated tensors, filled
+    from whole environment batches without a host round trip (``push``) and sampled by index (``sample``).  Same content
+    as ``MADDPG.remember`` rows (``train/code/truss2D_RL.py:439-456``): state, the three agents' actions, the three rewards,
+    the three next states, done.  ``A_n`` is a topology constant and kept once."""
+
+    def __init__(self, capacity, N, P, device, seed=0):
+        self.capacity, self.N, self.P, self.device = int(capacity), int(N), int(P), torch.device(device)
+        f = dict(dtype=torch.float32, device=self.device)
+        C_ = self.capacity
+
+        def state():
+            return {"x_n": torch.zeros(C_, N, 13, **f), "A_s": torch.zeros(C_, N, N, **f), "A_n_ts": torch.zeros(C_, N, N, **f),
+                    "A_n_cs": torch.zeros(C_, N, N, **f), "x_p": torch.zeros(C_, P, 4, **f), "A_p": torch.zeros(C_, P, P, **f)}
+        self.state, self.next_states = state(), [state() for _ in range(3)]
+        self.geo = [torch.zeros(C_, N, 2, **f) for _ in range(3)]
+        self.topo = [torch.zeros(C_, N, 3, **f) for _ in range(3)]
+        self.rewards, self.done = torch.zeros(C_, 3, **f), torch.zeros(C_, **f)
+        self.A_n = None
+        self.size, self.head = 0, 0
+        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+
+    def __len__(self):
+        return self.size
+
+    def push(self, state, actions, rewards, next_states, done, rows=None):
+        """``state`` / ``next_states[k]``: dicts (or 7-tuples in STATE_KEYS order) of device tensors with a leading batch
+        axis; ``rows``: optional index tensor selecting which environments of the batch are stored"""
+        def as_dict(s):
+            return s if isinstance(s, dict) else dict(zip(STATE_KEYS, s))
+        state, next_states = as_dict(state), [as_dict(s) for s in next_states]
+        if self.A_n is None:
+            self.A_n = state["A_n"].detach().clone()
+        pick = (lambda t: t) if rows is None else (lambda t: t.index_select(0, rows))
+        n = int(rewards.shape[0] if rows is None else rows.numel())
+        if n > self.capacity:
+            raise ValueError("more transitions than the replay holds")
+        idx = (torch.arange(n, device=self.device) + self.head) % self.capacity
+        for k in self.state:
+            self.state[k].index_copy_(0, idx, pick(state[k]))
+            for j in range(3):
+                self.next_states[j][k].index_copy_(0, idx, pick(next_states[j][k]))
+        for j in range(3):
+            self.geo[j].index_copy_(0, idx, pick(actions[j][0]))
+            self.topo[j].index_copy_(0, idx, pick(actions[j][1]))
+        self.rewards.index_copy_(0, idx, pick(rewards))
+        d = done if torch.is_tensor(done) else torch.full((rewards.shape[0],), float(done), device=self.device)
+        self.done.index_copy_(0, idx, pick(d.to(torch.float32)))
+        self.head = (self.head + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def sample(self, batch_size):
+        idx = torch.randint(0, self.size, (batch_size,), device=self.device, generator=self.gen)
+
+        def st(d):
+            return (d["x_n"][idx], self.A_n, d["A_s"][idx], d["A_n_ts"][idx], d["A_n_cs"][idx], d["x_p"][idx], d["A_p"][idx])
+        return (st(self.state), [st(d) for d in self.next_states], [(self.geo[j][idx], self.topo[j][idx]) for j in range(3)],
+                self.rewards[idx], self.done[idx])
+
+
 class MADDPGLearner:
     """Replay + update of the three agents (``MADDPG.remember / train / update``).
 
@@ -192,6 +253,9 @@ class MADDPGLearner:
         self.rng = random.Random(seed)
         self.allreduced_elements = 0
         self.last_losses = None
+        self.honour_done = False           # False = the reference's behaviour (its terminal test never fires, see train())
+        self.device_replay = None          # a DeviceReplay: train() samples from it instead of the host-side deque
+        self.keep_losses_on_device = False  # True: no host synchronisation inside train() (last_losses holds tensors)
 
     # ------------------------------------------------------------------------------------------------
     def _to(self, a):
@@ -219,15 +283,20 @@ class MADDPGLearner:
 
     def train(self):
         """one ``MADDPG.train()`` call (:463-689); returns False while the replay holds fewer than ``batch_size``"""
-        if len(self.memory) < self.batch_size:
-            return False
-        samples = self.rng.sample(list(self.memory), self.batch_size)
-        S = self._stack_state([m[0] for m in samples])
-        NS = [self._stack_state([m[3][k] for m in samples]) for k in range(3)]
-        A = [(torch.stack([m[1][k][0] for m in samples]).to(self.device),
-              torch.stack([m[1][k][1] for m in samples]).to(self.device)) for k in range(3)]
-        R = torch.stack([m[2] for m in samples]).to(self.device)                    # [B,3]
-        done = torch.tensor([m[4] for m in samples], device=self.device)
+        if self.device_replay is not None:
+            if len(self.device_replay) < self.batch_size:
+                return False
+            S, NS, A, R, done = self.device_replay.sample(self.batch_size)
+        else:
+            if len(self.memory) < self.batch_size:
+                return False
+            samples = self.rng.sample(list(self.memory), self.batch_size)
+            S = self._stack_state([m[0] for m in samples])
+            NS = [self._stack_state([m[3][k] for m in samples]) for k in range(3)]
+            A = [(torch.stack([m[1][k][0] for m in samples]).to(self.device),
+                  torch.stack([m[1][k][1] for m in samples]).to(self.device)) for k in range(3)]
+            R = torch.stack([m[2] for m in samples]).to(self.device)                    # [B,3]
+            done = torch.tensor([m[4] for m in samples], device=self.device)
         order = {0: (0, 1, 2), 1: (1, 0, 2), 2: (2, 0, 1)}                           # own action first (:560-562)
         with torch.no_grad():
             # next actions of every target actor on every agent's next state, then the target critics (:564-606)
@@ -240,7 +309,12 @@ class MADDPGLearner:
         losses = []
         for k, ag in enumerate(self.agents):
             o = order[k]
-            y = torch.where(done.view(-1, 1) == 1.0, R[:, k:k + 1], R[:, k:k + 1] + self.gamma * q_next[k])
+            # the reference's terminal test reads row element 4 of the replay row -- an action array, never the int 1 -- so
+            # `done is 1` is always False and EVERY target bootstraps (:606-613); kept (``done`` is stored but not used),
+            # set ``self.honour_done = True`` for the textbook target
+            y = R[:, k:k + 1] + self.gamma * q_next[k]
+            if self.honour_done:
+                y = torch.where(done.view(-1, 1) == 1.0, R[:, k:k + 1], y)
             # critic: train_on_batch with mse, Adam(lr, clipnorm=1) (:619)
             ag.critic_opt.zero_grad(set_to_none=True)
             q = ag.critic(*S, *A[o[0]], *A[o[1]], *A[o[2]])
@@ -259,11 +333,13 @@ class MADDPGLearner:
                 p.grad = g if g is not None else torch.zeros_like(p)
             self.allreduced_elements += allreduce_flat(list(ag.actor.parameters()))
             _clip_global_norm(ag.actor.parameters(), 1.0)
-            # a NEW Adam every call (:625): its first step is lr * g / (|g| + eps)
+            # a NEW Adam every call (:625): Keras applies lr sqrt(1 - b2) / (1 - b1) * m / (sqrt(v) + eps) with m = (1 - b1) g,
+            # v = (1 - b2) g^2 on the first step, i.e. lr * g / (|g| + eps / sqrt(1 - b2)), eps = 1e-7, b2 = 0.999
             with torch.no_grad():
                 for p in ag.actor.parameters():
-                    p.add_(-(ag.lr * 0.1) * p.grad / (p.grad.abs() + 1e-7))
-            losses.append((float(c_loss.detach()), float(a_loss.detach())))
+                    p.add_(-(ag.lr * 0.1) * p.grad / (p.grad.abs() + 1e-7 / (1.0 - 0.999) ** 0.5))
+            losses.append((c_loss.detach(), a_loss.detach()) if self.keep_losses_on_device
+                          else (float(c_loss.detach()), float(a_loss.detach())))
         self.last_losses = losses
         return True
 
