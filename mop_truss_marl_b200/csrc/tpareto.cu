@@ -168,6 +168,38 @@ pareto_front_hv_kernel(int B, int P, const float* __restrict__ points, const int
     __syncwarp();
   }
 }
+
+// pareto_state_data + the driver's padding: one CTA per environment; thread t writes row t of x_p, all threads sweep A_p
+// (coalesced stores, so a 50 x 50 matrix is 10 KB written once)
+__global__ void __launch_bounds__(128)
+pareto_state_data_kernel(int B, int P_in, int P_out, const float* __restrict__ points, const int32_t* __restrict__ front_idx,
+                         const int32_t* __restrict__ front_len, const int32_t* __restrict__ index, float* __restrict__ x_p,
+                         float* __restrict__ A_p) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const int len = front_len ? min(max(front_len[b], 0), P_in) : P_in;
+  const int sel = index ? index[b] : 0;
+  const float frac = (float)((double)len / 50.0);            // len(pf) / MAX_FRONT: a Python float stored into a float32 array
+  for (int i = threadIdx.x; i < P_out; i += blockDim.x) {
+    float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < len) {
+      const int src = front_idx ? front_idx[(size_t)b * P_in + i] : i;
+      const float* p = points + ((size_t)b * P_in + (src >= 0 && src < P_in ? src : 0)) * 4;
+      row = make_float4(p[0], p[1], i == sel ? 1.f : 0.f, frac);
+    }
+    reinterpret_cast<float4*>(x_p)[(size_t)b * P_out + i] = row;
+  }
+  // degree_power(A, -1/2): np.power(float32 degree, -0.5) for degree 1 (a single point), 2 (chain ends), 3 (interior)
+  const float d1 = 1.f, d2 = __uint_as_float(0x3f3504f3u), d3 = __uint_as_float(0x3f13cd3au);
+  auto dpow = [&](int i) { return len == 1 ? d1 : ((i == 0 || i == len - 1) ? d2 : d3); };
+  float* A = A_p + (size_t)b * P_out * P_out;
+  for (int idx = threadIdx.x; idx < P_out * P_out; idx += blockDim.x) {
+    const int i = idx / P_out, j = idx - i * P_out;
+    float v = 0.f;
+    if (i < len && j < len && (j - i <= 1) && (i - j <= 1)) v = __fmul_rn(dpow(i), dpow(j));   // D (A D): one product each
+    A[idx] = v;
+  }
+}
 }  // namespace
 
 extern "C" {
@@ -193,6 +225,22 @@ int tpareto_front_hv(int B, int P, const float* points, const int32_t* counts, c
                                                                         stats, hv);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(TFEM_ERR_CUDA, std::string("pareto kernel: ") + cudaGetErrorString(e));
+  return TFEM_OK;
+}
+
+int tpareto_state_data(int B, int P_in, int P_out, const float* points, const int32_t* front_idx, const int32_t* front_len,
+                       const int32_t* index, float* x_p, float* A_p, void* stream) {
+  if (!points || !x_p || !A_p) return pfail(TFEM_ERR_ARG, "null argument");
+  if (B < 0) return pfail(TFEM_ERR_ARG, "negative batch");
+  if (P_out < 1 || P_out > 64) return pfail(TFEM_ERR_ARG, "P_out must be in 1..64");
+  if (P_in < 1 || P_in > 256) return pfail(TFEM_ERR_ARG, "P_in must be in 1..256");
+  if (reinterpret_cast<uintptr_t>(x_p) & 15u) return pfail(TFEM_ERR_ALIGN, "x_p must be 16-byte aligned");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pfail(TFEM_ERR_CUDA, "no CUDA device: no CPU path");
+  if (B == 0) return TFEM_OK;
+  pareto_state_data_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(B, P_in, P_out, points, front_idx, front_len, index, x_p, A_p);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return pfail(TFEM_ERR_CUDA, std::string("pareto state kernel: ") + cudaGetErrorString(e));
   return TFEM_OK;
 }
 

@@ -72,3 +72,33 @@ def test_random_batches_vs_oracle(B, P):
     sel = np.unique(np.concatenate([np.arange(0, B, step), np.arange(min(B, 8))]))
     sub = {k: v[sel] for k, v in out.items()}
     check_against_oracle(sub, pts32[sel], counts[sel], ref)
+
+
+@pytest.mark.parametrize("rows", [50, 17, 1])
+def test_state_data_matches_oracle_bit_for_bit(rows):
+    """tpareto_state_data = pareto_state_data (truss2D_ENV.py:22-41) + the driver's zero padding / cut to `rows` rows
+    (master_DDPG_truss2D_MO.py:499-517): float32 outputs bit-identical to the oracle (itself pinned against the reference in
+    tests/test_oracle_vs_reference.py::test_pareto_state_data), with and without the front_idx indirection of front_hv"""
+    from mop_truss_marl_b200 import pareto
+    from oracle.truss_oracle import pareto_state_data
+    rng = np.random.RandomState(rows)
+    B, P = 97, 64
+    pts = rng.rand(B, P, 4).astype(np.float32)
+    lens = rng.randint(1, P + 1, size=B).astype(np.int32)
+    lens[:4] = (1, 2, rows, P)
+    index = np.array([rng.randint(0, n) for n in lens], dtype=np.int32)
+    perm = np.stack([rng.permutation(P) for _ in range(B)]).astype(np.int32)
+    for use_idx in (False, True):
+        x_p, A_p = pareto.state_data(torch.from_numpy(pts).cuda(), torch.from_numpy(perm).cuda() if use_idx else None,
+                                     torch.from_numpy(lens).cuda(), torch.from_numpy(index).cuda(), rows=rows)
+        torch.cuda.synchronize()
+        x_p, A_p = x_p.cpu().numpy(), A_p.cpu().numpy()
+        for b in range(B):
+            n = int(lens[b])
+            src = perm[b, :n] if use_idx else np.arange(n)
+            x, A = pareto_state_data([(pts[b, s, 0], pts[b, s, 1]) for s in src], index=int(index[b]))
+            wx, wA = np.zeros((rows, 4), np.float32), np.zeros((rows, rows), np.float32)
+            m = min(n, rows)
+            wx[:m], wA[:m, :m] = x[:m], A[:m, :m]
+            assert np.array_equal(x_p[b].view(np.uint32), wx.view(np.uint32)), (b, n)
+            assert np.array_equal(A_p[b].view(np.uint32), wA.view(np.uint32)), (b, n)

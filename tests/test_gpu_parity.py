@@ -6,6 +6,7 @@ reference and against the CPU oracle on seeded random inputs (SURVEY.md section 
   2 ulp ...... float32 observation tensors and the objective point
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -319,6 +320,59 @@ def test_full_size_properties(envmod, name, B):
         assert torch.equal(getattr(half, k), getattr(env, k)[B // 2:]), k
 
 
+def record_parity_counts(name, counts):
+    """gpurun_out/r2_parity_counts.json (copied to profiles/ for the record): per family and step, how many environments
+    of the full batch sit outside the flat 1e-9 and what the extended-precision solve says about them"""
+    import json
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r2_parity_counts.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = counts
+        json.dump(data, open(path, "w"), indent=1)
+    except OSError:
+        pass
+
+
+@pytest.mark.parametrize("name", FAMILY_NAMES)
+def test_ill_conditioned_solves_vs_extended_precision(envmod, name):
+    """The golden transitions (geometries the REFERENCE visited, cond(K) up to 1.9e8 on the saturated walks; tr_out_d is
+    what its own float64 LU returned) solved by the kernel and, in extended precision, by oracle/exact_fem.py: wherever the
+    kernel is more than 1e-9 from the reference it is because the REFERENCE is that far from the exact displacements --
+    the kernel itself obeys the same eps * cond bound and is as close to the truth as the reference is."""
+    from oracle import exact_fem
+    from oracle.truss_oracle import FAMILIES, build_mesh
+    g = load_golden(name)
+    m = build_mesh(FAMILIES[name])
+    y, sec, d_ref = g["tr_out_y"], g["tr_out_section"].astype(np.int32), g["tr_out_d"]
+    env = make_env(envmod, name, len(y))
+    out = env.solve_only(torch.from_numpy(np.ascontiguousarray(y)).cuda(), torch.from_numpy(np.ascontiguousarray(sec)).cuda())
+    torch.cuda.synchronize()
+    assert int(out["status"].abs().max()) == 0
+    d_gpu = cpu(out["d"])
+    d_exact = exact_fem.exact_displacements(m, y, sec)
+    cond = exact_fem.cond2(m, y, sec)
+    e_gpu, e_ref = exact_fem.rel_err(d_gpu, d_exact), exact_fem.rel_err(d_ref, d_exact)
+    eps = np.finfo(np.float64).eps
+    assert (e_gpu <= np.maximum(20 * eps * cond, 1e-13)).all(), float((e_gpu / (eps * cond)).max())
+    assert e_gpu[cond <= 1e6].max() <= 1e-10                          # a decade inside the flat tolerance in normal play
+    hard = cond > 1e6
+    # case by case either solver can be the luckier one; as a population the kernel's error measured in units of eps * cond
+    # is no larger than the reference's
+    r_gpu, r_ref = e_gpu / (eps * cond), e_ref / (eps * cond)
+    assert r_gpu.max() <= 2 * r_ref.max() and np.median(r_gpu[hard]) <= 2 * np.median(r_ref[hard]) + 1e-3
+    gpu_vs_ref = np.abs(d_gpu - d_ref).max(axis=1) / np.abs(d_ref).max(axis=1)
+    assert (gpu_vs_ref <= e_gpu + e_ref + 1e-15).all()                  # triangle inequality: the whole difference is explained
+    assert (gpu_vs_ref[cond <= 1e6] <= FP64_TOL).all()
+    record_parity_counts("golden_" + name, {
+        "cases": int(len(y)), "cond>1e6": int(hard.sum()), "max cond": float(cond.max()),
+        "kernel vs reference: outside flat 1e-9": int((gpu_vs_ref > FP64_TOL).sum()),
+        "max kernel error vs exact": float(e_gpu.max()), "max reference error vs exact": float(e_ref.max()),
+        "cond>1e6: kernel closer to exact than the reference": int((e_gpu[hard] <= e_ref[hard]).sum()),
+        "max error / (eps cond): kernel": float((e_gpu / (eps * cond)).max()),
+        "max error / (eps cond): reference": float((e_ref / (eps * cond)).max())})
+
+
 def test_empty_batch_and_bad_args(envmod):
     env = make_env(envmod, "small_bridge", 4)
     env.reset()
@@ -338,11 +392,16 @@ def test_full_batch_against_c_oracle(envmod, name, B):
     pinned by tests/test_c_oracle.py): three env steps from reset, each step's inputs taken from the GPU state"""
     from oracle.c_oracle import COracle
     from util import ulp_diff
+    from oracle import exact_fem
+    from oracle.truss_oracle import FAMILIES, build_mesh
     co = COracle(name)
+    mesh = build_mesh(FAMILIES[name])
     env = make_env(envmod, name, B)
     env.reset()
     N, E, nx = env.N, env.E, env.N // 2
     g = torch.Generator(device="cuda").manual_seed(7)
+    rng_np = np.random.RandomState(11)
+    counts = {"family": name, "envs": B, "steps": []}
     for s in range(3):
         scale = (1.3, 0.6, 0.25)[s]                                   # out-of-range, ordinary and small actions
         a_geo = (torch.rand(B, N, 2, device="cuda", generator=g) * scale - 0.05).contiguous()
@@ -361,21 +420,48 @@ def test_full_batch_against_c_oracle(envmod, name, B):
         assert np.array_equal(cpu(env.y_weak), want["weak"]), tag + " weak"
         assert np.array_equal(cpu(env.nN_x_e)[:, :, 0].astype(np.int32), want["section"]), tag + " section"
         assert np.array_equal(cpu(env.move_range), want["move_range"]), tag + " move range"
-        # FP64: 1e-9 normwise per environment where the truss is at least 1 m deep everywhere (cond(K) < 1e6); the
-        # d_min-deep ones (cond up to ~1e8) get eps * cond
-        depth = (want["y"][:, nx:] - want["y"][:, :nx]).min(axis=1)
-        deep = depth >= 1.0
-        assert deep.sum() > B // 50, tag
+        # FP64: flat 1e-9 normwise against the oracle (north_star) is COUNTED per environment.  The environments outside it
+        # are the ill-conditioned ones (d_min-deep trusses, cond(K) up to 1e8), where the oracle's LU -- the reference's --
+        # is itself eps * cond away from the exact displacements: for every one of them the exact displacements are formed
+        # in extended precision (oracle/exact_fem.py) and the kernel must be as close to them as the oracle is.
+        errs = {}
         for k in ("d", "axial", "ratio"):
             got = cpu(getattr(env, k))
-            err = np.abs(got - want[k]).max(axis=1) / np.abs(want[k]).max(axis=1)
-            assert err[deep].max() <= FP64_TOL, "%s %s %.3e" % (tag, k, err[deep].max())
-            assert err.max() <= 1e-6, "%s %s %.3e" % (tag, k, err.max())
-        errU = np.abs(cpu(env.U) - want["U"]) / np.abs(want["U"])
-        assert errU[deep].max() <= FP64_TOL and errU.max() <= 1e-6, tag + " U"
-        # flags: compression flag wherever the member force is not a rounding-level zero
+            errs[k] = np.abs(got - want[k]).max(axis=1) / np.abs(want[k]).max(axis=1)
+            assert errs[k].max() <= 1e-6, "%s %s %.3e" % (tag, k, errs[k].max())
+        errs["U"] = np.abs(cpu(env.U) - want["U"]) / np.abs(want["U"])
+        assert errs["U"].max() <= 1e-6, tag + " U"
+        worst = np.maximum.reduce([errs[k] for k in ("d", "axial", "ratio", "U")])
+        outside = np.nonzero(worst > FP64_TOL)[0]
+        sample = np.concatenate([outside, rng_np.choice(B, size=min(B, 256), replace=False)])
+        d_exact = exact_fem.exact_displacements(mesh, want["y"][sample], want["section"][sample])
+        e_gpu = exact_fem.rel_err(cpu(env.d)[sample], d_exact)
+        e_orc = exact_fem.rel_err(want["d"][sample], d_exact)
+        cond = exact_fem.cond2(mesh, want["y"][sample], want["section"][sample])
+        bound = 20 * np.finfo(np.float64).eps * cond
+        assert (e_gpu <= np.maximum(bound, 1e-13)).all(), "%s: kernel beyond 20 eps cond (%.2e)" % (tag, (e_gpu / bound).max())
+        r_gpu, r_orc = e_gpu / (np.finfo(np.float64).eps * cond), e_orc / (np.finfo(np.float64).eps * cond)
+        assert r_gpu.max() <= 2 * r_orc.max(), "%s: kernel further from the exact solve than the oracle (%.2f vs %.2f eps cond)" % (
+            tag, r_gpu.max(), r_orc.max())
+        no = len(outside)
+        assert no <= B // 50, "%s: %d of %d environments outside the flat 1e-9" % (tag, no, B)      # measured: none
+        if no:
+            assert cond[:no].min() > 1e5, "%s: an environment outside 1e-9 is not ill-conditioned (cond %.1e)" % (tag, cond[:no].min())
+        # flags: compression flag; a mismatch is only legitimate where the member force is a rounding-level zero
         ax = want["axial"]
+        flags_gpu = cpu(env.nN_x_e)[:, :, 4].astype(np.int32)
+        mism = flags_gpu != want["iscompress"]
         clear = np.abs(ax) > 1e-7 * np.abs(ax).max(axis=1, keepdims=True)
-        assert np.array_equal(cpu(env.nN_x_e)[:, :, 4].astype(np.int32)[clear], want["iscompress"][clear]), tag + " iscompress"
+        assert not (mism & clear).any(), tag + " iscompress"
+        counts["steps"].append({
+            "step": s, "envs": B, "outside_flat_1e-9": int(no), "fraction_inside_flat_1e-9": float(1.0 - no / B),
+            "max_err_vs_oracle": {k: float(errs[k].max()) for k in errs},
+            "outside: min cond(K)": float(cond[:no].min()) if no else None,
+            "outside: max kernel error vs exact": float(e_gpu[:no].max()) if no else None,
+            "outside: max oracle error vs exact": float(e_orc[:no].max()) if no else None,
+            "outside: kernel closer to exact than the oracle": int((e_gpu[:no] <= e_orc[:no]).sum()) if no else None,
+            "sample(256): max kernel error vs exact": float(e_gpu[no:].max()), "sample(256): max oracle error vs exact": float(e_orc[no:].max()),
+            "iscompress flags": int(mism.size), "iscompress mismatches (all at rounding-level zero forces)": int(mism.sum())})
         # objective point: <= 2 ulp(float32)
         assert ulp_diff(cpu(env.point), want["point"]).max() <= 2, tag + " point"
+    record_parity_counts(name, counts)
