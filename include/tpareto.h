@@ -33,15 +33,16 @@ int tpareto_front_hv(int B, int P, const float* points, const int32_t* counts, c
 
 /* pareto_state_data (test/00_small_bridge/code/truss2D_ENV.py:22-41) for B fronts at once, padded / cut to P_out rows the
  * way the driver does before it feeds the actor (master_DDPG_truss2D_MO.py:499-517):
- *   x_p[b][i] = (obj1_i, obj2_i, i == index[b], len_b / MAX_FRONT)   for i < min(len_b, P_out), zero rows behind
+ *   x_p[b][i] = (obj1_i, obj2_i, i == index[b], len_b / max_front)   for i < min(len_b, P_out), zero rows behind
+ *               (max_front = the ENV module's MAX_FRONT: 50 in test/<run>/code/truss2D_ENV.py:15, 20 in train/code)
  *   A_p[b]    = D^-1/2 (chain + I) D^-1/2 of the len_b-point chain, float32 like np.matmul(D, np.matmul(A, D)), rows / columns
  *               beyond P_out cut, zero rows / columns as padding
  * points    [B,P_in,4] float32 device (obj1, obj2, ...), the `points` of tpareto_front_hv
  * front_idx [B,P_in] int32 device: member i of front b is points[b][front_idx[b][i]] (NULL: identity, points are in order)
  * front_len [B] int32 device (NULL: P_in);  index [B] int32 device: which member the state belongs to (NULL: 0)
  * x_p [B,P_out,4], A_p [B,P_out,P_out] float32 device.  1 <= P_out <= 64, 1 <= P_in <= 256.  Current device, on `stream`. */
-int tpareto_state_data(int B, int P_in, int P_out, const float* points, const int32_t* front_idx, const int32_t* front_len,
-                       const int32_t* index, float* x_p, float* A_p, void* stream);
+int tpareto_state_data(int B, int P_in, int P_out, int max_front, const float* points, const int32_t* front_idx,
+                       const int32_t* front_len, const int32_t* index, float* x_p, float* A_p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,8 +38,8 @@ static float norm_col(float v, float mn, float mx) {
 bool build_family(const tfem_family_desc& d, Family& f) {
   f.desc = d;
   const int nx = d.num_x;
-  if (nx != 8 && nx != 16) {
-    f.error = "num_x must be 8 or 16 (the shapes of test/00..03); got " + std::to_string(nx);
+  if (nx != 6 && nx != 8 && nx != 16) {
+    f.error = "num_x must be 6 (train/code), 8 or 16 (test/00..03): the compiled kernel shapes; got " + std::to_string(nx);
     return false;
   }
   if (d.truss_type != TFEM_BRIDGE && d.truss_type != TFEM_ROOF) {

@@ -158,7 +158,7 @@ __host__ __device__ constexpr int align16(int v) { return (v + 15) & ~15; }
 // GM = false: env-step / reset / solve-only (args.mode); GM = true: the gene-vector objective (MODE_GENES) -- a separate
 // instantiation so that the env-step keeps its register allocation
 template <int NX, bool GM>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (NX == 8) ? TFEM_MINB_SMALL : TFEM_MINB_LARGE)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (NX <= 8) ? TFEM_MINB_SMALL : TFEM_MINB_LARGE)
 tfem_step_kernel(const StepArgs args) {
   using D = Dims<NX>;
   constexpr int N = D::N, E = D::E, NI = D::NI, EPL = D::EPL;
@@ -638,11 +638,23 @@ tfem_step_kernel(const StepArgs args) {
       if (!dst) return;
       float4* o = reinterpret_cast<float4*>(dst + (size_t)b * count);
       const uint2* m = reinterpret_cast<const uint2*>(maps + map_off);
-      for (int q = lane; q < count / 4; q += 32) {
-        const uint2 mm = m[q];
-        o[q] = make_float4(pool[mm.x & 0xffffu], pool[mm.x >> 16], pool[mm.y & 0xffffu], pool[mm.y >> 16]);
+      if (count % 4 == 0) {
+        for (int q = lane; q < count / 4; q += 32) {
+          const uint2 mm = m[q];
+          o[q] = make_float4(pool[mm.x & 0xffffu], pool[mm.x >> 16], pool[mm.y & 0xffffu], pool[mm.y >> 16]);
+        }
+      } else {
+        // an environment's slice of this tensor is not a multiple of 16 bytes (nN_x_e of the 6 x 2 shapes: 26 x 21 floats),
+        // so neither are the slice addresses: 64-bit stores (every per-environment count is even)
+        float2* o2 = reinterpret_cast<float2*>(dst + (size_t)b * count);
+        const uint32_t* m1 = reinterpret_cast<const uint32_t*>(maps + map_off);
+        for (int q = lane; q < count / 2; q += 32) {
+          const uint32_t mm = m1[q];
+          o2[q] = make_float2(pool[mm & 0xffffu], pool[mm >> 16]);
+        }
       }
     };
+    static_assert((N * 13) % 4 == 0 && (N * N) % 4 == 0 && (N * 12) % 4 == 0 && (E * 21) % 2 == 0, "vector width of the output streams");
     emit(args.out.x_n, fam->map_xn, N * 13);
     emit(args.out.A_s, fam->map_as, N * N);
     emit(args.out.A_n_ts, fam->map_ts, N * N);
@@ -674,7 +686,11 @@ cudaError_t configure_one(int smem, int* ctas) {
 int step_kernel_configure(int nx, int device, int map_entries, LaunchInfo* info) {
   cudaError_t err;
   int smem = 0, ctas = 0, ctas_g = 0, sms = 0;
-  if (nx == 8) {
+  if (nx == 6) {                   // the 6 x 2 shapes of train/code/master_DDPG_truss2D_MO.py:787-795
+    smem = smem_bytes_for<6>(map_entries);
+    err = configure_one<6, false>(smem, &ctas);
+    if (err == cudaSuccess) err = configure_one<6, true>(smem, &ctas_g);
+  } else if (nx == 8) {
     smem = smem_bytes_for<8>(map_entries);
     err = configure_one<8, false>(smem, &ctas);
     if (err == cudaSuccess) err = configure_one<8, true>(smem, &ctas_g);
@@ -712,7 +728,9 @@ int step_kernel_launch(int nx, const StepArgs& args, const LaunchInfo& info, cud
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaError_t e;
-  if (nx == 8 && !gm) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<8, false>, args);
+  if (nx == 6 && !gm) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<6, false>, args);
+  else if (nx == 6) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<6, true>, args);
+  else if (nx == 8 && !gm) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<8, false>, args);
   else if (nx == 8) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<8, true>, args);
   else if (nx == 16 && !gm) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<16, false>, args);
   else if (nx == 16) e = cudaLaunchKernelEx(&cfg, tfem_step_kernel<16, true>, args);

@@ -172,14 +172,14 @@ pareto_front_hv_kernel(int B, int P, const float* __restrict__ points, const int
 // pareto_state_data + the driver's padding: one CTA per environment; thread t writes row t of x_p, all threads sweep A_p
 // (coalesced stores, so a 50 x 50 matrix is 10 KB written once)
 __global__ void __launch_bounds__(128)
-pareto_state_data_kernel(int B, int P_in, int P_out, const float* __restrict__ points, const int32_t* __restrict__ front_idx,
+pareto_state_data_kernel(int B, int P_in, int P_out, double max_front, const float* __restrict__ points, const int32_t* __restrict__ front_idx,
                          const int32_t* __restrict__ front_len, const int32_t* __restrict__ index, float* __restrict__ x_p,
                          float* __restrict__ A_p) {
   const int b = blockIdx.x;
   if (b >= B) return;
   const int len = front_len ? min(max(front_len[b], 0), P_in) : P_in;
   const int sel = index ? index[b] : 0;
-  const float frac = (float)((double)len / 50.0);            // len(pf) / MAX_FRONT: a Python float stored into a float32 array
+  const float frac = (float)((double)len / max_front);       // len(pf) / MAX_FRONT: a Python float stored into a float32 array
   for (int i = threadIdx.x; i < P_out; i += blockDim.x) {
     float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < len) {
@@ -228,8 +228,9 @@ int tpareto_front_hv(int B, int P, const float* points, const int32_t* counts, c
   return TFEM_OK;
 }
 
-int tpareto_state_data(int B, int P_in, int P_out, const float* points, const int32_t* front_idx, const int32_t* front_len,
-                       const int32_t* index, float* x_p, float* A_p, void* stream) {
+int tpareto_state_data(int B, int P_in, int P_out, int max_front, const float* points, const int32_t* front_idx,
+                       const int32_t* front_len, const int32_t* index, float* x_p, float* A_p, void* stream) {
+  if (max_front < 1) return pfail(TFEM_ERR_ARG, "max_front must be positive");
   if (!points || !x_p || !A_p) return pfail(TFEM_ERR_ARG, "null argument");
   if (B < 0) return pfail(TFEM_ERR_ARG, "negative batch");
   if (P_out < 1 || P_out > 64) return pfail(TFEM_ERR_ARG, "P_out must be in 1..64");
@@ -238,7 +239,7 @@ int tpareto_state_data(int B, int P_in, int P_out, const float* points, const in
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pfail(TFEM_ERR_CUDA, "no CUDA device: no CPU path");
   if (B == 0) return TFEM_OK;
-  pareto_state_data_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(B, P_in, P_out, points, front_idx, front_len, index, x_p, A_p);
+  pareto_state_data_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(B, P_in, P_out, (double)max_front, points, front_idx, front_len, index, x_p, A_p);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(TFEM_ERR_CUDA, std::string("pareto state kernel: ") + cudaGetErrorString(e));
   return TFEM_OK;

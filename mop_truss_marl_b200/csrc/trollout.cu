@@ -367,7 +367,11 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
   }
   // ---- direct path (pageable buffers, or TROLLOUT_NO_GRAPH=1) ----
   int np_done = 0;
-  if (int rc = enqueue_step(h, B, io, mu, theta, sigma, seed, nullptr, false, &np_done)) return rc;
+  if (int rc = enqueue_step(h, B, io, mu, theta, sigma, seed, nullptr, false, &np_done)) {
+    // a piece failed mid-step: copies of earlier pieces may still be reading / writing the caller's host buffers
+    cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_run); cudaStreamSynchronize(h->s_out);
+    return rc;
+  }
   e = cudaStreamSynchronize(h->s_out);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_in);
   if (h->timeline && e == cudaSuccess) {

@@ -56,6 +56,16 @@ FAMILIES = {
 }
 
 
+# the five 6 x 2 training shapes with mixed spans (train/code/master_DDPG_truss2D_MO.py:787-795: trainChoice; dmin = 0.2,
+# gen_load_y = -100000, support_case 1, truss type drawn per episode :809-815).  train/code/truss2D_ENV.py has no symmetry step.
+_TRAIN_TAR = ((1.0, 1.5, 2.0, 2.0, 1.5, 1.0), (1.0, 3.0, 3.0, 2.0, 1.5, 1.0), (1.0, 1.5, 2.0, 3.0, 3.0, 1.0),
+              (1.0, 3.0, 2.0, 2.0, 3.0, 1.0), (3.0, 2.0, 1.0, 1.0, 2.0, 3.0))
+for _i, _tar in enumerate(_TRAIN_TAR):
+    for _tt in ("roof", "bridge"):
+        FAMILIES["train%d_%s" % (_i, _tt)] = FamilySpec("train%d_%s" % (_i, _tt), 6, (4.0, 3.0, 5.0, 3.0, 5.0), (5,), _tar, 0.2, 0,
+                                                        -100000, _tt, 1, SYM_NONE)
+
+
 def family_desc(spec: FamilySpec):
     """FamilySpec -> ctypes ``tfem_family_desc``"""
     from . import capi

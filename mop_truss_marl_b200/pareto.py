@@ -15,7 +15,7 @@ MAX_POINTS = 64
 _lib = capi.lib
 _lib.tpareto_last_error.restype = C.c_char_p
 _lib.tpareto_front_hv.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 8
-_lib.tpareto_state_data.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+_lib.tpareto_state_data.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
 
 
 def _ptr(t):
@@ -48,11 +48,11 @@ def front_hv(points: torch.Tensor, counts: torch.Tensor | None = None, ref_point
 
 
 def state_data(points: torch.Tensor, front_idx: torch.Tensor | None = None, front_len: torch.Tensor | None = None,
-               index: torch.Tensor | None = None, rows: int = 50):
+               index: torch.Tensor | None = None, rows: int = 50, max_front: int = 50):
     """``pareto_state_data`` (``truss2D_ENV.py:22-41``) for B fronts, padded / cut to ``rows`` rows like the driver does
     (``master_DDPG_truss2D_MO.py:499-517``).  ``points`` [B,P,4] float32 CUDA; ``front_idx`` [B,P] / ``front_len`` [B] as
     returned by :func:`front_hv` (None: the points are the front, in order); ``index`` [B] int32: the front member whose
-    state is being built.  Returns ``x_p`` [B,rows,4], ``A_p`` [B,rows,rows]: the actor's Pareto-graph inputs."""
+    state is being built; ``max_front``: the ENV module's ``MAX_FRONT`` (50 in test/, 20 in train/).  Returns ``x_p`` [B,rows,4], ``A_p`` [B,rows,rows]: the actor's Pareto-graph inputs."""
     if not (points.is_cuda and points.dtype == torch.float32 and points.dim() == 3 and points.shape[2] == 4
             and points.is_contiguous()):
         raise ValueError("points must be a contiguous float32 CUDA tensor [B,P,4]")
@@ -64,7 +64,7 @@ def state_data(points: torch.Tensor, front_idx: torch.Tensor | None = None, fron
     x_p = torch.empty(B, rows, 4, dtype=torch.float32, device=dev)
     A_p = torch.empty(B, rows, rows, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        rc = _lib.tpareto_state_data(B, P, int(rows), _ptr(points), _ptr(front_idx), _ptr(front_len), _ptr(index), _ptr(x_p),
+        rc = _lib.tpareto_state_data(B, P, int(rows), int(max_front), _ptr(points), _ptr(front_idx), _ptr(front_len), _ptr(index), _ptr(x_p),
                                      _ptr(A_p), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     if rc != 0:
         raise capi.TfemError("libtfem pareto error %d: %s" % (rc, _lib.tpareto_last_error().decode()))

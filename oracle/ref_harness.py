@@ -156,6 +156,16 @@ DRIVER_ARGS = {
     "large_roof": (16, 2, [5] * 15, [6], _LARGE_TAR, 0.3, 0, -8 * 1000, "roof", 1, None),
 }
 
+# the 6 x 2 training shapes (train/code/master_DDPG_truss2D_MO.py:787-795, :809-823): the driver passes (..., truss_type,
+# gen_topo_code, support_case) positionally, so gen_model receives support_case = None (which generates the supports of
+# case 1) and topo_code = 1
+_TRAIN_TAR = ([1.0, 1.5, 2.0, 2.0, 1.5, 1.0], [1.0, 3.0, 3.0, 2.0, 1.5, 1.0], [1.0, 1.5, 2.0, 3.0, 3.0, 1.0],
+              [1.0, 3.0, 2.0, 2.0, 3.0, 1.0], [3.0, 2.0, 1.0, 1.0, 2.0, 3.0])
+for _i, _tar in enumerate(_TRAIN_TAR):
+    for _tt in ("roof", "bridge"):
+        RUN_DIRS["train%d_%s" % (_i, _tt)] = "train/code"
+        DRIVER_ARGS["train%d_%s" % (_i, _tt)] = (6, 2, [4.0, 3.0, 5.0, 3.0, 5.0], [5], list(_tar), 0.2, 0, -100000, _tt, None, 1)
+
 
 class RefGame:
     """One reference ``gen_model`` + ``Game_research04`` pair, driven with explicit coins."""
@@ -174,7 +184,9 @@ class RefGame:
     def step(self, set_node, set_element, nC_e, a_geo, a_topo, coin: bool):
         """``_game_modify`` with the symmetry coin forced (truss2D_ENV.py:460 draws
         ``random.random() >= 0.5``)."""
-        env_random = self.mods.ENV.random
+        env_random = getattr(self.mods.ENV, "random", None)
+        if env_random is None:                               # train/code's ENV draws no coin (no symmetry step)
+            return self.game._game_modify(set_node, set_element, nC_e, [a_geo, a_topo])
         orig = env_random.random
         env_random.random = (lambda: 0.75) if coin else (lambda: 0.25)
         try:

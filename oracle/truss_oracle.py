@@ -76,6 +76,15 @@ FAMILIES = {
 }
 
 
+# train/code/master_DDPG_truss2D_MO.py:787-795 (trainChoice), :809-815: 6 x 2, mixed spans, no symmetry step in train/code's ENV
+_TRAIN_TAR = ([1.0, 1.5, 2.0, 2.0, 1.5, 1.0], [1.0, 3.0, 3.0, 2.0, 1.5, 1.0], [1.0, 1.5, 2.0, 3.0, 3.0, 1.0],
+              [1.0, 3.0, 2.0, 2.0, 3.0, 1.0], [3.0, 2.0, 1.0, 1.0, 2.0, 3.0])
+for _i, _tar in enumerate(_TRAIN_TAR):
+    for _tt in ("roof", "bridge"):
+        FAMILIES["train%d_%s" % (_i, _tt)] = FamilySpec("train%d_%s" % (_i, _tt), 6, [4.0, 3.0, 5.0, 3.0, 5.0], [5], _tar, 0.2, 0,
+                                                        -100000, _tt, 1, "none")
+
+
 @dataclass
 class Mesh:
     spec: FamilySpec
@@ -620,15 +629,15 @@ class TrussOracle:
         return fem_solve(self.mesh, [float(v) for v in y64], [int(s) for s in sec])
 
 
-def pareto_state_data(pf, index=0):
-    """truss2D_ENV.py:22-41 -- chain graph over the current front."""
+def pareto_state_data(pf, index=0, max_front=MAX_FRONT):
+    """truss2D_ENV.py:22-41 -- chain graph over the current front (MAX_FRONT: 50 in test/*/code, 20 in train/code)."""
     n = len(pf)
     x_pf = np.zeros((n, 4), dtype=np.float32)
     for i in range(n):
         x_pf[i, 0] = pf[i][0]; x_pf[i, 1] = pf[i][1]
         if i == index:
             x_pf[i, 2] = 1
-        x_pf[i, 3] = n / MAX_FRONT
+        x_pf[i, 3] = n / max_front
     A = np.eye(n, dtype=np.float32)
     for i in range(n - 1):
         A[i, i + 1] = 1; A[i + 1, i] = 1

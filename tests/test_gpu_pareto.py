@@ -74,8 +74,8 @@ def test_random_batches_vs_oracle(B, P):
     check_against_oracle(sub, pts32[sel], counts[sel], ref)
 
 
-@pytest.mark.parametrize("rows", [50, 17, 1])
-def test_state_data_matches_oracle_bit_for_bit(rows):
+@pytest.mark.parametrize("rows,max_front", [(50, 50), (17, 50), (1, 50), (20, 20)])
+def test_state_data_matches_oracle_bit_for_bit(rows, max_front):
     """tpareto_state_data = pareto_state_data (truss2D_ENV.py:22-41) + the driver's zero padding / cut to `rows` rows
     (master_DDPG_truss2D_MO.py:499-517): float32 outputs bit-identical to the oracle (itself pinned against the reference in
     tests/test_oracle_vs_reference.py::test_pareto_state_data), with and without the front_idx indirection of front_hv"""
@@ -90,13 +90,13 @@ def test_state_data_matches_oracle_bit_for_bit(rows):
     perm = np.stack([rng.permutation(P) for _ in range(B)]).astype(np.int32)
     for use_idx in (False, True):
         x_p, A_p = pareto.state_data(torch.from_numpy(pts).cuda(), torch.from_numpy(perm).cuda() if use_idx else None,
-                                     torch.from_numpy(lens).cuda(), torch.from_numpy(index).cuda(), rows=rows)
+                                     torch.from_numpy(lens).cuda(), torch.from_numpy(index).cuda(), rows=rows, max_front=max_front)
         torch.cuda.synchronize()
         x_p, A_p = x_p.cpu().numpy(), A_p.cpu().numpy()
         for b in range(B):
             n = int(lens[b])
             src = perm[b, :n] if use_idx else np.arange(n)
-            x, A = pareto_state_data([(pts[b, s, 0], pts[b, s, 1]) for s in src], index=int(index[b]))
+            x, A = pareto_state_data([(pts[b, s, 0], pts[b, s, 1]) for s in src], index=int(index[b]), max_front=max_front)
             wx, wA = np.zeros((rows, 4), np.float32), np.zeros((rows, rows), np.float32)
             m = min(n, rows)
             wx[:m], wA[:m, :m] = x[:m], A[:m, :m]

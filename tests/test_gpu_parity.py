@@ -108,12 +108,13 @@ def test_transitions_vs_golden(envmod, name):
                     tag="%s tr[%d] mode %d" % (name, i, g["tr_mode"][i]))
 
 
-@pytest.mark.parametrize("name", FAMILY_NAMES)
+@pytest.mark.parametrize("name", FAMILY_NAMES + ("train0_roof", "train1_bridge", "train4_roof"))
 def test_random_walk_vs_oracle(envmod, name):
-    """every environment feeds its own state back; the oracle follows each one"""
+    """every environment feeds its own state back; the oracle follows each one (the four test/ families and three of the
+    6 x 2 train/code shapes: 12 nodes, mixed spans, no symmetry step)"""
     from oracle.truss_oracle import TrussOracle
     o = TrussOracle(name)
-    B = 48 if o.mesh.N == 16 else 16
+    B = 48 if o.mesh.N <= 16 else 16
     steps = 4
     env = make_env(envmod, name, B)
     env.reset()
