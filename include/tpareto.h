@@ -5,7 +5,8 @@
  *   utils.union_rectangles_fastest(front, +1, -1, ref_point)                          :463-530
  * (master_DDPG_truss2D_MO.py:263-368): feasibility cut (con1 > 1 or con2 > 1), strict two-objective dominance, the
  * front sorted by obj1, its spread statistics and its hypervolume against a moving reference point.
- * Each environment holds at most TPARETO_MAX_POINTS points (the reference keeps fronts of <= 50).
+ * Each environment holds at most TPARETO_MAX_POINTS points (the reference keeps fronts of <= 50 and culls up to 50 + 150
+ * accumulated candidates at the end of a step, master_DDPG_truss2D_MO.py:437).
  */
 #ifndef TPARETO_H_
 #define TPARETO_H_
@@ -16,7 +17,7 @@
 extern "C" {
 #endif
 
-#define TPARETO_MAX_POINTS 64
+#define TPARETO_MAX_POINTS 256
 
 const char* tpareto_last_error(void);
 
@@ -30,6 +31,17 @@ const char* tpareto_last_error(void);
  * Any output may be NULL.  Runs on the current device, on `stream`. */
 int tpareto_front_hv(int B, int P, const float* points, const int32_t* counts, const double* ref_point,
                      int32_t* front_idx, int32_t* front_len, double* stats, double* hv, void* stream);
+
+/* The same with the reference's thinning of fronts of more than MAX_FRONT members (utils.py:104-131): the first and the last
+ * member (by obj1) stay, max_front - 2 of the others are taken from the list sorted by crowd distance (descending, stable)
+ * and keep the order of the draw; statistics and hypervolume are those of the thinned list.  The reference draws with
+ * random.sample; here the draw is an input, so the result is deterministic:
+ * thin_pick [B, max_front - 2] int32 device = what random.sample(range(F - 2), max_front - 2) returned for that environment
+ * (positions in the crowd-sorted list; rows of environments whose front has <= max_front members are not read).
+ * tpareto_front_hv (no draw) leaves larger fronts unthinned.  3 <= max_front <= 64. */
+int tpareto_front_hv_thin(int B, int P, const float* points, const int32_t* counts, const double* ref_point,
+                          const int32_t* thin_pick, int max_front, int32_t* front_idx, int32_t* front_len, double* stats,
+                          double* hv, void* stream);
 
 /* pareto_state_data (test/00_small_bridge/code/truss2D_ENV.py:22-41) for B fronts at once, padded / cut to P_out rows the
  * way the driver does before it feeds the actor (master_DDPG_truss2D_MO.py:499-517):

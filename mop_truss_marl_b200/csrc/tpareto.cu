@@ -1,6 +1,6 @@
 // Batched Pareto front + spread statistics + hypervolume (include/tpareto.h): one warp per environment, points in
-// shared memory, every step O(P^2) or a warp reduction -- P <= 64, so an environment costs a few thousand
-// instructions and the kernel is bound by the load of its 16 P bytes.
+// shared memory, every step O(P^2 / 32) per lane or a warp reduction -- P <= 256 (the driver culls 50 + 150 accumulated
+// candidates at the end of a step), fronts beyond MAX_FRONT thinned with the caller's draw.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -13,7 +13,8 @@ namespace {
 thread_local std::string g_pareto_err;
 int pfail(int code, const std::string& m) { g_pareto_err = m; return code; }
 
-constexpr int MAXP = TPARETO_MAX_POINTS;
+constexpr int MAXP = TPARETO_MAX_POINTS;          // 256
+constexpr int SL = MAXP / 32;                     // point slots per lane
 constexpr int WARPS = 4;
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -28,66 +29,119 @@ __device__ __forceinline__ double warp_min(double v) {
   for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ int warp_isum(int v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
+// One warp per environment, points in shared memory; every step is O(P^2 / 32) per lane or a warp reduction.
 __global__ void __launch_bounds__(WARPS * 32)
 pareto_front_hv_kernel(int B, int P, const float* __restrict__ points, const int32_t* __restrict__ counts, double rx,
-                       double ry, int32_t* __restrict__ front_idx, int32_t* __restrict__ front_len,
-                       double* __restrict__ stats, double* __restrict__ hv) {
-  __shared__ float4 pt[WARPS][MAXP];       // the environment's points
-  __shared__ int order[WARPS][MAXP];       // front members in sorted order
+                       double ry, const int32_t* __restrict__ thin_pick, int max_front, int32_t* __restrict__ front_idx,
+                       int32_t* __restrict__ front_len, double* __restrict__ stats, double* __restrict__ hv) {
+  // scratch: the environment's points first; once the sorted front exists the same bytes hold the crowd distances and
+  // the crowd-sorted interior (thinning), then the x-sorted copy of the thinned front (hypervolume)
+  __shared__ __align__(16) unsigned char scratch[WARPS][MAXP * 16];
+  __shared__ int order[WARPS][MAXP];       // front members in list order
   __shared__ double fx[WARPS][MAXP], fy[WARPS][MAXP];
+  __shared__ unsigned char member[WARPS][MAXP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* pt = reinterpret_cast<float4*>(scratch[warp]);
   for (int b = blockIdx.x * WARPS + warp; b < B; b += gridDim.x * WARPS) {
     const int n = counts ? min(max(counts[b], 0), P) : P;
-    for (int i = lane; i < n; i += 32) pt[warp][i] = reinterpret_cast<const float4*>(points)[(size_t)b * P + i];
+    for (int i = lane; i < n; i += 32) pt[i] = reinterpret_cast<const float4*>(points)[(size_t)b * P + i];
     __syncwarp();
     // ---- feasibility, duplicates, dominance (utils.py:17-54) ----
-    bool on_front[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int i = lane + 32 * s;
+    int nf = 0;
+    for (int i = lane; i < MAXP; i += 32) {
       bool keep = false;
       if (i < n) {
-        const float4 p = pt[warp][i];
+        const float4 p = pt[i];
         keep = !(p.z > 1.f || p.w > 1.f);
         for (int j = 0; j < n && keep; ++j) {
-          const float4 q = pt[warp][j];
+          const float4 q = pt[j];
           if (q.z > 1.f || q.w > 1.f) continue;
           if (q.x < p.x && q.y < p.y) keep = false;                                      // dominated
           if (j < i && q.x == p.x && q.y == p.y && q.z == p.z && q.w == p.w) keep = false;   // same tuple: kept once
         }
       }
-      on_front[s] = keep;
+      member[warp][i] = keep ? 1 : 0;
+      nf += keep ? 1 : 0;
     }
+    int F = warp_isum(nf);
+    __syncwarp();
     // ---- rank among the front members by (obj1 ascending, obj2 descending, index) (:57) ----
-    const unsigned m0 = __ballot_sync(0xffffffffu, on_front[0]), m1 = __ballot_sync(0xffffffffu, on_front[1]);
-    const int F = __popc(m0) + __popc(m1);
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int i = lane + 32 * s;
-      if (on_front[s]) {
-        const float4 p = pt[warp][i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-          const bool member = (j < 32 ? (m0 >> j) : (m1 >> (j - 32))) & 1u;
-          if (!member || j == i) continue;
-          const float4 q = pt[warp][j];
-          if (q.x < p.x || (q.x == p.x && (q.y > p.y || (q.y == p.y && j < i)))) ++rank;
-        }
-        order[warp][rank] = i;
-        fx[warp][rank] = (double)p.x;
-        fy[warp][rank] = (double)p.y;
+    for (int i = lane; i < n; i += 32) {
+      if (!member[warp][i]) continue;
+      const float4 p = pt[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        if (!member[warp][j] || j == i) continue;
+        const float4 q = pt[j];
+        if (q.x < p.x || (q.x == p.x && (q.y > p.y || (q.y == p.y && j < i)))) ++rank;
       }
+      order[warp][rank] = i;
+      fx[warp][rank] = (double)p.x;
+      fy[warp][rank] = (double)p.y;
     }
     __syncwarp();
+    // ---- more than MAX_FRONT members (:104-131): first and last stay, MAX_FRONT - 2 of the others are taken from the list
+    //      sorted by crowd distance (descending, stable) at the positions the caller drew, in the order of the draw ----
+    bool resort = false;
+    if (F > max_front && thin_pick && max_front >= 3 && max_front <= 64) {
+      double* crowd = reinterpret_cast<double*>(scratch[warp]);              // [MAXP]
+      int* sorted = reinterpret_cast<int*>(scratch[warp] + MAXP * 8);        // [MAXP] interior members by crowd distance
+      for (int k = lane; k < F; k += 32) {
+        auto dist = [&](int a) {
+          const double ax = fx[warp][a] - fx[warp][a + 1], ay = fy[warp][a] - fy[warp][a + 1];
+          return sqrt(ax * ax + ay * ay);
+        };
+        crowd[k] = (k == 0) ? dist(0) : (k == F - 1) ? dist(F - 2) : dist(k - 1) + dist(k);
+      }
+      __syncwarp();
+      for (int k = 1 + lane; k < F - 1; k += 32) {
+        int r = 0;
+        const double ck = crowd[k];
+        for (int j = 1; j < F - 1; ++j) r += (crowd[j] > ck || (crowd[j] == ck && j < k)) ? 1 : 0;
+        sorted[r] = k;
+      }
+      __syncwarp();
+      int src[2];
+      double nx[2], ny[2];
+      int no[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int t = lane + 32 * s;
+        src[s] = -1;
+        if (t < max_front) {
+          int k = 0;
+          if (t == max_front - 1) k = F - 1;
+          else if (t > 0) {
+            const int pk = thin_pick[(size_t)b * (max_front - 2) + (t - 1)];
+            k = sorted[min(max(pk, 0), F - 3)];
+          }
+          src[s] = k; nx[s] = fx[warp][k]; ny[s] = fy[warp][k]; no[s] = order[warp][k];
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int t = lane + 32 * s;
+        if (src[s] >= 0) { fx[warp][t] = nx[s]; fy[warp][t] = ny[s]; order[warp][t] = no[s]; }
+      }
+      F = max_front;
+      resort = true;
+      __syncwarp();
+    }
     if (front_len && lane == 0) front_len[b] = F;
     if (front_idx)
       for (int i = lane; i < P; i += 32) front_idx[(size_t)b * P + i] = (i < F) ? order[warp][i] : -1;
-    // ---- spread statistics (:159-195) ----
-    double dsum = 0.0, dmax = 0.0, d[2] = {0.0, 0.0};
+    // ---- spread statistics (:159-195), over the list in its order ----
+    double dsum = 0.0, dmax = 0.0, d[SL];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < SL; ++s) {
       const int k = lane + 32 * s;
+      d[s] = 0.0;
       if (k + 1 < F) {
         const double ax = fx[warp][k] - fx[warp][k + 1], ay = fy[warp][k] - fy[warp][k + 1];
         d[s] = sqrt(ax * ax + ay * ay);
@@ -102,17 +156,18 @@ pareto_front_hv_kernel(int B, int P, const float* __restrict__ points, const int
       const double nd = (double)(F - 1), centre = dmax / nd;
       double acc = 0.0;
 #pragma unroll
-      for (int s = 0; s < 2; ++s)
+      for (int s = 0; s < SL; ++s)
         if (lane + 32 * s + 1 < F) acc += (d[s] - centre) * (d[s] - centre);
       acc = warp_sum(acc);
       max_d = dmax; sum_d = dsum; dis_d = sqrt(acc / nd);
     }
     double std_cd = 1.0, p_inv = 0.0;
     if (F > 3) {
-      double c[2] = {0.0, 0.0}, csum = 0.0, cmax = 0.0;
+      double c[SL], csum = 0.0, cmax = 0.0;
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < SL; ++s) {
         const int k = lane + 32 * s;                        // interior point k+1
+        c[s] = 0.0;
         if (k + 2 < F) {
           c[s] = fabs(fx[warp][k] - fx[warp][k + 2]) + fabs(fy[warp][k] - fy[warp][k + 2]);
           csum += c[s];
@@ -125,13 +180,13 @@ pareto_front_hv_kernel(int B, int P, const float* __restrict__ points, const int
         const double nc = (double)(F - 2);
         double mean = 0.0, p10 = 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < SL; ++s)
           if (lane + 32 * s + 2 < F) { c[s] /= cmax; mean += c[s]; const double c2 = c[s] * c[s], c4 = c2 * c2; p10 += c4 * c4 * c2; }
         mean = warp_sum(mean) / nc;
         p10 = warp_sum(p10);
         double var = 0.0;
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < SL; ++s)
           if (lane + 32 * s + 2 < F) var += (c[s] - mean) * (c[s] - mean);
         var = warp_sum(var);
         std_cd = sqrt(var / nc);
@@ -142,26 +197,36 @@ pareto_front_hv_kernel(int B, int P, const float* __restrict__ points, const int
       double* o = stats + (size_t)b * 5;
       o[0] = max_d; o[1] = dis_d; o[2] = p_inv; o[3] = sum_d; o[4] = std_cd;
     }
-    // ---- hypervolume of the front (:463-530): integral of the running maximum height over the sorted x ----
+    // ---- hypervolume of the list (:463-530): integral of the running maximum height over the x-sorted members ----
     if (hv) {
-      double area = 0.0, minx = INFINITY, miny = INFINITY;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int k = lane + 32 * s;
-        if (k < F) {
-          double h = 0.0;
-          for (int j = 0; j <= k; ++j) h = fmax(h, 1.0 - fmin(fy[warp][j], 1.0));      // the front is sorted by x
-          const double x0 = fmin(fx[warp][k], 1.0), x1 = (k + 1 < F) ? fmin(fx[warp][k + 1], 1.0) : 1.0;
-          area += (x1 - x0) * h;
-          minx = fmin(minx, fx[warp][k]);
-          miny = fmin(miny, fy[warp][k]);
+      const double* sx = fx[warp];
+      const double* sy = fy[warp];
+      if (resort) {                                          // the thinned list is in draw order: sort a copy by x
+        double* tx = reinterpret_cast<double*>(scratch[warp]);
+        double* ty = tx + MAXP;
+        for (int k = lane; k < F; k += 32) {
+          int r = 0;
+          const double xk = fx[warp][k];
+          for (int j = 0; j < F; ++j) r += (fx[warp][j] < xk || (fx[warp][j] == xk && j < k)) ? 1 : 0;
+          tx[r] = xk; ty[r] = fy[warp][k];
         }
+        __syncwarp();
+        sx = tx; sy = ty;
+      }
+      double area = 0.0, minx = INFINITY, miny = INFINITY;
+      for (int k = lane; k < F; k += 32) {
+        double h = 0.0;
+        for (int j = 0; j <= k; ++j) h = fmax(h, 1.0 - fmin(sy[j], 1.0));
+        const double x0 = fmin(sx[k], 1.0), x1 = (k + 1 < F) ? fmin(sx[k + 1], 1.0) : 1.0;
+        area += (x1 - x0) * h;
+        minx = fmin(minx, sx[k]);
+        miny = fmin(miny, sy[k]);
       }
       area = warp_sum(area);
       minx = warp_min(minx);
       miny = warp_min(miny);
       double out = 0.0;
-      if (F > 0 && !(F == 1 && fx[warp][0] == 1.0 && fy[warp][0] == 1.0))
+      if (F > 0 && !(F == 1 && sx[0] == 1.0 && sy[0] == 1.0))
         out = area - ((1.0 - rx) * (1.0 - minx) + (1.0 - ry) * (1.0 - miny) - (1.0 - rx) * (1.0 - ry));
       if (lane == 0) hv[b] = out;
     }
@@ -206,11 +271,13 @@ extern "C" {
 
 const char* tpareto_last_error(void) { return g_pareto_err.c_str(); }
 
-int tpareto_front_hv(int B, int P, const float* points, const int32_t* counts, const double* ref_point,
-                     int32_t* front_idx, int32_t* front_len, double* stats, double* hv, void* stream) {
+static int front_hv_impl(int B, int P, const float* points, const int32_t* counts, const double* ref_point,
+                         const int32_t* thin_pick, int max_front, int32_t* front_idx, int32_t* front_len, double* stats,
+                         double* hv, void* stream) {
   if (!points) return pfail(TFEM_ERR_ARG, "null argument");
   if (B < 0) return pfail(TFEM_ERR_ARG, "negative batch");
-  if (P < 1 || P > TPARETO_MAX_POINTS) return pfail(TFEM_ERR_ARG, "P must be in 1..64");
+  if (P < 1 || P > TPARETO_MAX_POINTS) return pfail(TFEM_ERR_ARG, "P must be in 1..256");
+  if (thin_pick && (max_front < 3 || max_front > 64)) return pfail(TFEM_ERR_ARG, "max_front must be in 3..64");
   if (reinterpret_cast<uintptr_t>(points) & 15u) return pfail(TFEM_ERR_ALIGN, "points must be 16-byte aligned");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return pfail(TFEM_ERR_CUDA, "no CUDA device: no CPU path");
@@ -221,11 +288,23 @@ int tpareto_front_hv(int B, int P, const float* points, const int32_t* counts, c
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int need = (B + WARPS - 1) / WARPS;
   const int grid = need < sms * 8 ? need : sms * 8;
-  pareto_front_hv_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(B, P, points, counts, rx, ry, front_idx, front_len,
-                                                                        stats, hv);
+  pareto_front_hv_kernel<<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(B, P, points, counts, rx, ry, thin_pick, max_front,
+                                                                        front_idx, front_len, stats, hv);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return pfail(TFEM_ERR_CUDA, std::string("pareto kernel: ") + cudaGetErrorString(e));
   return TFEM_OK;
+}
+
+int tpareto_front_hv(int B, int P, const float* points, const int32_t* counts, const double* ref_point,
+                     int32_t* front_idx, int32_t* front_len, double* stats, double* hv, void* stream) {
+  return front_hv_impl(B, P, points, counts, ref_point, nullptr, 50, front_idx, front_len, stats, hv, stream);
+}
+
+int tpareto_front_hv_thin(int B, int P, const float* points, const int32_t* counts, const double* ref_point,
+                          const int32_t* thin_pick, int max_front, int32_t* front_idx, int32_t* front_len, double* stats,
+                          double* hv, void* stream) {
+  if (!thin_pick) return pfail(TFEM_ERR_ARG, "null thin_pick");
+  return front_hv_impl(B, P, points, counts, ref_point, thin_pick, max_front, front_idx, front_len, stats, hv, stream);
 }
 
 int tpareto_state_data(int B, int P_in, int P_out, int max_front, const float* points, const int32_t* front_idx,

@@ -9,12 +9,13 @@ import torch
 
 from . import capi
 
-PARETO_EXPORTS = ("tpareto_last_error", "tpareto_front_hv", "tpareto_state_data")
-MAX_POINTS = 64
+PARETO_EXPORTS = ("tpareto_last_error", "tpareto_front_hv", "tpareto_front_hv_thin", "tpareto_state_data")
+MAX_POINTS = 256
 
 _lib = capi.lib
 _lib.tpareto_last_error.restype = C.c_char_p
 _lib.tpareto_front_hv.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 8
+_lib.tpareto_front_hv_thin.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 5
 _lib.tpareto_state_data.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
 
 
@@ -22,10 +23,14 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def front_hv(points: torch.Tensor, counts: torch.Tensor | None = None, ref_point=(1.0, 1.0)):
+def front_hv(points: torch.Tensor, counts: torch.Tensor | None = None, ref_point=(1.0, 1.0), thin_pick: torch.Tensor | None = None,
+             max_front: int = 50):
     """points [B,P,4] float32 CUDA (obj1, obj2, con1, con2), counts [B] int32 (valid points per environment).
     Returns ``front_idx`` [B,P] (front members in the reference's order, -1 padded), ``front_len`` [B],
-    ``stats`` [B,5] = (max_distance, dis_distance, p_norm_inv_cd, sum_distance, std_cd) and ``hv`` [B]."""
+    ``stats`` [B,5] = (max_distance, dis_distance, p_norm_inv_cd, sum_distance, std_cd) and ``hv`` [B].
+    ``thin_pick`` [B, max_front - 2] int32 CUDA: the draw ``random.sample(range(F - 2), max_front - 2)`` per environment,
+    applied to fronts of more than ``max_front`` members like ``utils.simple_cull`` does (:104-131); without it larger
+    fronts stay unthinned."""
     if not (points.is_cuda and points.dtype == torch.float32 and points.dim() == 3 and points.shape[2] == 4
             and points.is_contiguous()):
         raise ValueError("points must be a contiguous float32 CUDA tensor [B,P,4]")
@@ -38,10 +43,17 @@ def front_hv(points: torch.Tensor, counts: torch.Tensor | None = None, ref_point
     stats = torch.empty(B, 5, dtype=torch.float64, device=dev)
     hv = torch.empty(B, dtype=torch.float64, device=dev)
     ref = (C.c_double * 2)(float(ref_point[0]), float(ref_point[1]))
+    if thin_pick is not None and not (thin_pick.is_cuda and thin_pick.dtype == torch.int32 and thin_pick.is_contiguous()
+                                      and tuple(thin_pick.shape) == (B, max_front - 2)):
+        raise ValueError("thin_pick must be a contiguous int32 CUDA tensor [B, max_front - 2]")
     with torch.cuda.device(dev):
-        rc = _lib.tpareto_front_hv(B, P, _ptr(points), _ptr(counts), C.cast(ref, C.c_void_p), _ptr(front_idx),
-                                   _ptr(front_len), _ptr(stats), _ptr(hv),
-                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if thin_pick is None:
+            rc = _lib.tpareto_front_hv(B, P, _ptr(points), _ptr(counts), C.cast(ref, C.c_void_p), _ptr(front_idx),
+                                       _ptr(front_len), _ptr(stats), _ptr(hv), st)
+        else:
+            rc = _lib.tpareto_front_hv_thin(B, P, _ptr(points), _ptr(counts), C.cast(ref, C.c_void_p), _ptr(thin_pick),
+                                            int(max_front), _ptr(front_idx), _ptr(front_len), _ptr(stats), _ptr(hv), st)
     if rc != 0:
         raise capi.TfemError("libtfem pareto error %d: %s" % (rc, _lib.tpareto_last_error().decode()))
     return {"front_idx": front_idx, "front_len": front_len, "stats": stats, "hv": hv}

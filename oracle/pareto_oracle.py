@@ -15,8 +15,11 @@ Parity status: **pinned** -- ``tests/test_pareto_oracle.py`` runs both functions
 ``utils.py`` on random point sets (float64 inputs, so both sides compute in float64) and against
 ``tests/golden/pareto.npz`` recorded from the reference by ``tests/golden/make_golden_pareto.py``.  (With the driver's
 ``np.float32`` points the reference's scalar arithmetic runs in float32; the statistics then agree to ~1e-6.)
-The reference samples the front down with ``random.sample`` when it holds more than MAX_FRONT = 50 points (:135-142);
-callers here keep at most 50 points per environment, so that branch is out of reach.
+The reference samples the front down with ``random.sample`` when it holds more than MAX_FRONT = 50 points (:120-142): the
+first and the last member stay, 48 of the others are drawn from the list sorted by crowd distance (descending, stable)
+and keep the ORDER of the draw.  ``front_stats(points, thin_pick=...)`` reproduces it for an explicit draw: ``thin_pick`` is
+what ``random.sample(range(F - 2), MAX_FRONT - 2)`` returned (positions in that sorted list); the pinning test feeds the same
+positions to the reference by patching ``utils.random.sample``.
 """
 from __future__ import annotations
 
@@ -43,12 +46,32 @@ def front_indices(points):
     return front
 
 
-def front_stats(points):
-    """``simple_cull(points)``: (front [F,4], max_distance, dis_distance, p_norm_inv_cd, sum_distance, std_cd)"""
+def thin_order(f, thin_pick, max_front=MAX_FRONT):
+    """positions (into the obj1-sorted front ``f`` [F,>=2]) of the thinned front, in the reference's order (:104-131)"""
+    F = len(f)
+    d = np.sqrt((f[:-1, 0] - f[1:, 0]) ** 2 + (f[:-1, 1] - f[1:, 1]) ** 2)
+    crowd = np.empty(F)
+    crowd[0], crowd[-1] = d[0], d[-1]
+    crowd[1:-1] = d[:-1] + d[1:]
+    interior = sorted(range(1, F - 1), key=lambda i: crowd[i], reverse=True)      # stable: ties keep the obj1 order
+    pick = [int(k) for k in thin_pick]
+    if len(pick) != max_front - 2 or len(set(pick)) != len(pick) or min(pick) < 0 or max(pick) >= F - 2:
+        raise ValueError("thin_pick must hold %d distinct positions below %d" % (max_front - 2, F - 2))
+    return [0] + [interior[k] for k in pick] + [F - 1]
+
+
+def front_stats(points, thin_pick=None, max_front=MAX_FRONT):
+    """``simple_cull(points)``: (front [F,4], max_distance, dis_distance, p_norm_inv_cd, sum_distance, std_cd).  A front of
+    more than ``max_front`` members is thinned with the draw ``thin_pick`` (see the module docstring); the statistics are then
+    those of the thinned list in its draw order, as in the reference."""
     pts = np.asarray(points, dtype=np.float64)
     idx = front_indices(pts)
     f = pts[idx]
-    F = len(idx)
+    if len(idx) > max_front:
+        if thin_pick is None:
+            raise ValueError("front of %d members: the reference draws %d of them at random; pass thin_pick" % (len(idx), max_front - 2))
+        f = f[thin_order(f, thin_pick, max_front)]
+    F = len(f)
     if F >= 2:                                                                      # :159-166
         d = np.sqrt((f[:-1, 0] - f[1:, 0]) ** 2 + (f[:-1, 1] - f[1:, 1]) ** 2)
         max_d = float(d.max())

@@ -55,7 +55,7 @@ def test_golden_from_reference():
         check_against_oracle(out, pts32, g["counts"], ref)          # and exactly what the oracle gives on those inputs
 
 
-@pytest.mark.parametrize("B,P", [(1, 1), (257, 50), (4096, 64), (33, 7)])
+@pytest.mark.parametrize("B,P", [(1, 1), (257, 50), (4096, 64), (33, 7), (300, 200), (64, 256)])
 def test_random_batches_vs_oracle(B, P):
     rng = np.random.RandomState(B + P)
     pts = rng.rand(B, P, 4)
@@ -102,3 +102,44 @@ def test_state_data_matches_oracle_bit_for_bit(rows, max_front):
             wx[:m], wA[:m, :m] = x[:m], A[:m, :m]
             assert np.array_equal(x_p[b].view(np.uint32), wx.view(np.uint32)), (b, n)
             assert np.array_equal(A_p[b].view(np.uint32), wA.view(np.uint32)), (b, n)
+
+
+def test_large_fronts_are_thinned_with_the_callers_draw():
+    """the step-end cull of up to 50 + 150 accumulated candidates (master_DDPG_truss2D_MO.py:437): fronts of more than
+    MAX_FRONT = 50 members are thinned like utils.simple_cull does (:104-131) with the draw given as an input; order of the
+    thinned front exact, statistics and hypervolume of the thinned list to 1e-12 against the oracle (itself pinned against
+    the reference with the same draw, tests/test_pareto_oracle.py)"""
+    from mop_truss_marl_b200 import pareto
+    from oracle import pareto_oracle
+    rng = np.random.RandomState(9)
+    B, P = 48, 200
+    pts = np.zeros((B, P, 4), np.float32)
+    counts = rng.randint(120, P + 1, size=B).astype(np.int32)
+    for b in range(B):
+        n = counts[b]
+        t = np.sort(rng.rand(n))
+        curve = 1.0 - t ** (0.5 + rng.rand()) + (0.002 if b % 3 else 0.2) * rng.rand(n)     # every third batch: a short front
+        p = np.stack([t, curve, rng.rand(n) * 0.9, rng.rand(n) * 0.9], axis=1)
+        pts[b, :n] = p[rng.permutation(n)]
+    picks = np.zeros((B, 48), np.int32)
+    lens = []
+    for b in range(B):
+        F = len(pareto_oracle.front_indices(pts[b, :counts[b]].astype(np.float64)))
+        lens.append(F)
+        picks[b] = rng.permutation(max(F - 2, 48))[:48] if F > 50 else 0
+    assert sum(F > 50 for F in lens) >= 10 and sum(F <= 50 for F in lens) >= 5
+    ref = (0.9, 0.95)
+    out = pareto.front_hv(torch.from_numpy(pts).cuda(), torch.from_numpy(counts).cuda(), ref, thin_pick=torch.from_numpy(picks).cuda())
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    for b in range(B):
+        p64 = pts[b, :counts[b]].astype(np.float64)
+        f, max_d, dis_d, p_cd, sum_d, std_cd = pareto_oracle.front_stats(p64, thin_pick=picks[b] if lens[b] > 50 else None)
+        F = len(f)
+        assert F == min(lens[b], 50) and out["front_len"][b] == F
+        assert np.array_equal(p64[out["front_idx"][b, :F]], f) and (out["front_idx"][b, F:] == -1).all()
+        assert np.allclose(out["stats"][b], [max_d, dis_d, p_cd, sum_d, std_cd], rtol=1e-12, atol=1e-14), b
+        assert abs(out["hv"][b] - pareto_oracle.hypervolume(f, ref)) <= 1e-12, b
+    # without a draw a large front is returned whole
+    whole = pareto.front_hv(torch.from_numpy(pts).cuda(), torch.from_numpy(counts).cuda(), ref)
+    assert np.array_equal(whole["front_len"].cpu().numpy(), np.array(lens))

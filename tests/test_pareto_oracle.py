@@ -60,3 +60,37 @@ def test_oracle_matches_reference_utils():
         # the hypervolume of an arbitrary (dominated) list too
         hv_all = utils.union_rectangles_fastest([list(map(float, p)) for p in pts], +1, -1, ref_point=ref)
         assert abs(pareto_oracle.hypervolume(pts, ref) - hv_all) <= 1e-12
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not present")
+def test_thinning_of_large_fronts_matches_reference():
+    """fronts of more than MAX_FRONT = 50 members (the step-end cull of up to 50 + 150 accumulated candidates,
+    master_DDPG_truss2D_MO.py:437): the reference's random.sample is replaced by an explicit draw on both sides"""
+    utils = ref_harness.load_utils("small_bridge")
+    rng = np.random.RandomState(5)
+    done = 0
+    for trial in range(40):
+        n = rng.randint(120, 201)
+        t = np.sort(rng.rand(n))
+        pts = np.stack([t, 1.0 - t ** (0.5 + rng.rand()) + 0.002 * rng.rand(n), rng.rand(n) * 0.9, rng.rand(n) * 0.9], axis=1)
+        pts = pts[rng.permutation(n)]
+        F = len(pareto_oracle.front_indices(pts))
+        if F <= 50:
+            continue
+        pick = [int(k) for k in rng.permutation(F - 2)[:48]]
+        orig = utils.random.sample
+        utils.random.sample = lambda pop, k: [pop[i] for i in pick[:k]]
+        try:
+            want = utils.simple_cull([list(map(float, p)) for p in pts])
+        finally:
+            utils.random.sample = orig
+        got = pareto_oracle.front_stats(pts, thin_pick=pick)
+        assert len(want[0]) == 50 and np.array_equal(got[0], np.array(want[0]))
+        assert np.allclose(got[1:], want[1:], rtol=1e-12, atol=1e-14)
+        ref = [0.9, 0.95]
+        hv_want = utils.union_rectangles_fastest([list(f) for f in want[0]], +1, -1, ref_point=ref)
+        assert abs(pareto_oracle.hypervolume(got[0], ref) - hv_want) <= 1e-12
+        done += 1
+    assert done >= 10
+    with pytest.raises(ValueError):
+        pareto_oracle.front_stats(pts)                    # a large front needs the draw
