@@ -414,7 +414,7 @@ def train_leg(args, rank, local_rank, world, dev, steps=10, standalone=False, fa
             t[3].record()
         if trained:
             for k in range(3):
-                pols[k].set_weights(lrn.actor_weights(k))
+                pols[k].set_weights_device(lrn.actor_tensors(k))       # weight images rebuilt on the device
         # the game moves on along agent 0's child (the driver keeps a front of candidates; one parent per environment here)
         for name in ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range", "point"):
             getattr(parent, name).copy_(getattr(children[0], name))
@@ -448,7 +448,7 @@ def train_leg(args, rank, local_rank, world, dev, steps=10, standalone=False, fa
         same = bool(lo.item() == hi.item())
     line = {
         "workload": "%s B=%d per GPU: three-agent DDPG training loop (3 x actor act + 3 x FEM env-step, device replay, "
-                    "MADDPG train + update per game step, gradient all-reduce, actor weights pushed to the CUDA actors)" % (family, B),
+                    "MADDPG train + update per game step, gradient all-reduce, actor weight images rebuilt on the device)" % (family, B),
         "family": family, "envs_per_gpu": B, "n_gpus": world, "steps": steps,
         "value": 3 * B * world / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms,
         "updates_per_s": 1e3 / step_ms, "replay_transitions_per_step": int(keep.numel()), "learner_batch": lrn.batch_size,

@@ -54,6 +54,13 @@ int tactor_destroy(tactor_handle_t h);
  * layers (same layout as tactor_create) after the device has finished the forwards already queued. */
 int tactor_set_weights(tactor_handle_t h, const tactor_weights* w);
 
+/* The same from DEVICE memory, on `stream` (no host round trip, no device-wide synchronisation): what a learner whose
+ * parameters live on the GPU calls after every update (truss2D_RL.py:625 updates actor_model, :340 acts with it).  The
+ * operand images of the tensor-core kernel (power-of-two scales, fp16 hi / lo split, core-matrix layout, mma fragment
+ * image of the layer-1 kernels) are rebuilt by three small kernels; forwards queued later on the same stream see the new
+ * weights, forwards of OTHER streams must be ordered by the caller. */
+int tactor_set_weights_device(tactor_handle_t h, const tactor_weights* w_dev, void* stream);
+
 /* geo [B,N,2], topo [B,N,3] = sigmoid outputs of gcn_l4_1 / gcn_l4_2 (no noise). */
 int tactor_forward(tactor_handle_t h, int B, const tactor_inputs* in, float* geo, float* topo, void* stream);
 

@@ -22,7 +22,8 @@ class _Inputs(C.Structure):
                 ("P", C.c_int32)]
 
 
-ACTOR_EXPORTS = ("tactor_last_error", "tactor_create", "tactor_destroy", "tactor_set_weights", "tactor_forward", "tactor_act",
+ACTOR_EXPORTS = ("tactor_last_error", "tactor_create", "tactor_destroy", "tactor_set_weights", "tactor_set_weights_device",
+                 "tactor_forward", "tactor_act",
                  "tactor_act_dev", "tactor_reserve_calls", "tactor_launch_count", "tactor_status",
                  "tactor_selftest_tmem_layout")
 
@@ -31,6 +32,7 @@ _lib.tactor_last_error.restype = C.c_char_p
 _lib.tactor_create.argtypes = [C.POINTER(_Weights), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
 _lib.tactor_destroy.argtypes = [C.c_void_p]
 _lib.tactor_set_weights.argtypes = [C.c_void_p, C.POINTER(_Weights)]
+_lib.tactor_set_weights_device.argtypes = [C.c_void_p, C.POINTER(_Weights), C.c_void_p]
 _lib.tactor_forward.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.tactor_act.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                             C.c_float, C.c_uint64, C.c_void_p]
@@ -89,6 +91,19 @@ class BatchedActor:
         """replace all 13 layers (``actor_model.set_weights`` / ``load_weights`` on a live actor)"""
         w = self._pack(weights)
         _check(_lib.tactor_set_weights(self._h, C.byref(w)))
+
+    def set_weights_device(self, weights):
+        """the same from tensors that already live on the actor's device -- ``{layer: (kernel [in,out], bias [out])}`` of
+        contiguous float32 CUDA tensors, e.g. a learner's parameters -- on the current stream: no host round trip and no
+        device-wide synchronisation (``tactor_set_weights_device``)"""
+        w = _Weights()
+        for i, name in enumerate(ACTOR_LAYERS):
+            k, b = weights[name]
+            for t in (k, b):
+                if not (isinstance(t, torch.Tensor) and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous()):
+                    raise ValueError("layer %s: expected contiguous float32 tensors on %s" % (name, self.device))
+            w.kernel[i], w.bias[i] = k.data_ptr(), b.data_ptr()
+        _check(_lib.tactor_set_weights_device(self._h, C.byref(w), self._stream()))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

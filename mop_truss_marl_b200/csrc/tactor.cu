@@ -286,6 +286,107 @@ __global__ void __launch_bounds__(128) tmem_layout_selftest_kernel(uint32_t* out
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(32) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Device-side rebuild of the weight images (tactor_set_weights_device): the same layouts upload_weights builds on the host.
+struct PackArgs {
+  const float* kernel[TACTOR_NLAYERS];
+  const float* bias[TACTOR_NLAYERS];
+  float* d_w[TACTOR_NLAYERS];
+  float* d_b[TACTOR_NLAYERS];
+  __half* d_wimg[TACTOR_NLAYERS];      // layers 4..10
+  uint32_t* w1frag;
+  float* wscale_inv;                   // [NGEMM + 3]
+  float* wmax;                         // [TACTOR_NLAYERS] scratch: max(|W|, |b|) per layer
+  int ncta;
+};
+__constant__ int kInDev[TACTOR_NLAYERS] = {13, 13, 13, 4, 200, 200, 200, 200, 200, 200, 200, 200, 200};
+__constant__ int kOutDev[TACTOR_NLAYERS] = {200, 200, 200, 200, 200, 200, 200, 200, 200, 200, 200, 2, 3};
+
+// largest 2^s with wmax 2^s < 2^14 (clamped to 2^+-24), like pow2_scale on the host
+__device__ __forceinline__ float pow2_scale_dev(float wmax) {
+  int ex = 0;
+  if (wmax > 0.f) { frexpf(wmax, &ex); ex = 14 - ex; }
+  ex = ex > 24 ? 24 : (ex < -24 ? -24 : ex);
+  return ldexpf(1.f, ex);
+}
+
+__global__ void __launch_bounds__(256) pack_wmax_kernel(PackArgs a) {
+  __shared__ float red[8];
+  const int l = blockIdx.x, nW = kInDev[l] * kOutDev[l], nB = kOutDev[l];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < nW; i += 256) m = fmaxf(m, fabsf(a.kernel[l][i]));
+  for (int i = threadIdx.x; i < nB; i += 256) m = fmaxf(m, fabsf(a.bias[l][i]));
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    a.wmax[l] = m;
+    const float inv = 1.f / pow2_scale_dev(m);
+    if (l >= 4 && l <= 10) a.wscale_inv[l - 4] = inv;
+    if (l < 3) a.wscale_inv[tc::fused::NGEMM + l] = inv;
+  }
+}
+
+// packed [Kpad, 208] kernels and [208] biases of all 13 layers (grid: layer x blocks)
+__global__ void __launch_bounds__(256) pack_plain_kernel(PackArgs a) {
+  const int l = blockIdx.y, kin = kInDev[l], kout = kOutDev[l];
+  const int kpad = (kin + KC - 1) / KC * KC;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < kpad * LD; idx += gridDim.x * 256) {
+    const int i = idx / LD, o = idx - i * LD;
+    a.d_w[l][idx] = (i < kin && o < kout) ? a.kernel[l][(size_t)i * kout + o] : 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < LD) a.d_b[l][threadIdx.x] = threadIdx.x < kout ? a.bias[l][threadIdx.x] : 0.f;
+}
+
+// tcgen05 operand images of the seven [200,200] layers (grid: layer 4..10 x blocks): per 16-wide K chunk, per CTA of the pair
+// (its half of the 208 columns), [hi | lo][kb][n][8 halfs]; row k = 200 holds the bias
+__global__ void __launch_bounds__(256) pack_img_kernel(PackArgs a) {
+  const int l = 4 + blockIdx.y, K = kInDev[l], kout = kOutDev[l];
+  const int bn = tc::TCN / a.ncta, kpc = tc::KPC, nkb = tc::KCH / kpc;
+  const int nch = (K + 1 + tc::KCH - 1) / tc::KCH;
+  const int total = nch * a.ncta * 2 * nkb * bn * kpc;
+  const float scale = pow2_scale_dev(a.wmax[l]);
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
+    int r = idx;
+    const int t = r % kpc; r /= kpc;
+    const int nl = r % bn; r /= bn;
+    const int kb = r % nkb; r /= nkb;
+    const int part = r % 2; r /= 2;
+    const int half = r % a.ncta; r /= a.ncta;
+    const int c = r;
+    const int n = half * bn + nl, k = c * tc::KCH + kpc * kb + t;
+    float v = 0.f;
+    if (n < kout && k < K) v = a.kernel[l][(size_t)k * kout + n] * scale;
+    else if (n < kout && k == K) v = a.bias[l][n] * scale;
+    const __half hi = __float2half_rn(v);
+    a.d_wimg[l][idx] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
+  }
+}
+
+// mma.sync A fragments of [W1k ; b1k]^T for the three layer-1 kernels: [3][13 chunks][hi | lo][32 lanes][4]
+__global__ void __launch_bounds__(32) pack_w1frag_kernel(PackArgs a) {
+  const int l = blockIdx.y, c = blockIdx.x, lane = threadIdx.x, kout = kOutDev[l];
+  const float scale = pow2_scale_dev(a.wmax[l]);
+  auto we = [&](int cc, int f) -> float {
+    if (f >= kout || cc > 13) return 0.f;
+    return (cc < 13 ? a.kernel[l][(size_t)cc * kout + f] : a.bias[l][f]) * scale;
+  };
+  auto pack = [](float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  };
+  const int g = lane / 4, t = lane % 4, f0 = c * tc::KCH + g;
+  uint32_t* hi = a.w1frag + (((size_t)l * tc::pipe::NCH + c) * 2 + 0) * 128 + (size_t)lane * 4;
+  uint32_t* lo = a.w1frag + (((size_t)l * tc::pipe::NCH + c) * 2 + 1) * 128 + (size_t)lane * 4;
+  pack(we(2 * t, f0), we(2 * t + 1, f0), hi[0], lo[0]);
+  pack(we(2 * t, f0 + 8), we(2 * t + 1, f0 + 8), hi[1], lo[1]);
+  pack(we(2 * t + 8, f0), we(2 * t + 9, f0), hi[2], lo[2]);
+  pack(we(2 * t + 8, f0 + 8), we(2 * t + 9, f0 + 8), hi[3], lo[3]);
+}
+
 constexpr int pareto_smem(int P) { return (P * LD + 4 * LD + P * P + P * 4) * 4; }
 constexpr int PARETO_SMEM = pareto_smem(50);
 
@@ -304,6 +405,7 @@ struct tactor_handle_s {
   int pareto_dense = 0;                // TACTOR_PARETO_DENSE=1: always the dense kernels (A/B timing, tests)
   float* d_wimg[TACTOR_NLAYERS] = {};  // tcgen05 operand image of the hidden layers (hi/lo split, core-matrix layout)
   uint32_t* d_w1frag = nullptr;        // mma.sync A-fragment image of the three layer-1 kernels (tactor_pipe.cuh)
+  float* d_wmax = nullptr;             // [13] scratch of tactor_set_weights_device
   float* d_wscale_inv = nullptr;       // [NGEMM + 3] 1 / power-of-two scale of d_wimg[4 + g] and of the three layer-1 images
   int dev_flags = 0;                   // TACTOR_FLAGS (development switches of the actor kernel)
   int variant = 0;                     // generator phases / epilogue warps of actor_pipe_kernel (TACTOR_VARIANT, A/B timing)
@@ -593,6 +695,32 @@ int tactor_set_weights(tactor_handle_t h, const tactor_weights* w) {
   return TFEM_OK;
 }
 
+int tactor_set_weights_device(tactor_handle_t h, const tactor_weights* w, void* stream) {
+  if (!h || !w) return afail(TFEM_ERR_ARG, "null argument");
+  for (int l = 0; l < TACTOR_NLAYERS; ++l)
+    if (!w->kernel[l] || !w->bias[l]) return afail(TFEM_ERR_ARG, "missing layer weights");
+  Guard g(h->device);
+  cudaError_t e = cudaSuccess;
+  if (!h->d_wmax) e = cudaMalloc(&h->d_wmax, TACTOR_NLAYERS * sizeof(float));
+  if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("actor weights: ") + cudaGetErrorString(e));
+  tactor::PackArgs a{};
+  for (int l = 0; l < TACTOR_NLAYERS; ++l) {
+    a.kernel[l] = w->kernel[l]; a.bias[l] = w->bias[l];
+    a.d_w[l] = h->d_w[l]; a.d_b[l] = h->d_b[l];
+    a.d_wimg[l] = reinterpret_cast<__half*>(h->d_wimg[l]);
+  }
+  a.w1frag = h->d_w1frag; a.wscale_inv = h->d_wscale_inv; a.wmax = h->d_wmax; a.ncta = h->ncta;
+  cudaStream_t st = (cudaStream_t)stream;
+  tactor::pack_wmax_kernel<<<TACTOR_NLAYERS, 256, 0, st>>>(a);
+  tactor::pack_plain_kernel<<<dim3(16, TACTOR_NLAYERS), 256, 0, st>>>(a);
+  tactor::pack_img_kernel<<<dim3(32, 7), 256, 0, st>>>(a);
+  tactor::pack_w1frag_kernel<<<dim3(tactor::tc::pipe::NCH, 3), 32, 0, st>>>(a);
+  e = cudaGetLastError();
+  h->launches.fetch_add(4);
+  if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("actor weights: ") + cudaGetErrorString(e));
+  return TFEM_OK;
+}
+
 int tactor_destroy(tactor_handle_t h) {
   if (!h) return TFEM_OK;
   Guard g(h->device);
@@ -603,6 +731,7 @@ int tactor_destroy(tactor_handle_t h) {
   if (h->d_error) cudaFree(h->d_error);
   if (h->d_w1frag) cudaFree(h->d_w1frag);
   if (h->d_wscale_inv) cudaFree(h->d_wscale_inv);
+  if (h->d_wmax) cudaFree(h->d_wmax);
   delete h;
   return TFEM_OK;
 }

@@ -350,6 +350,11 @@ class MADDPGLearner:
             return [a.update() for a in self.agents]
         return None
 
+    def actor_tensors(self, k):
+        """agent k's online actor as ``{layer: (kernel, bias)}`` of its parameter tensors (no copy): for
+        ``BatchedActor.set_weights_device`` when the learner lives on the actor's GPU"""
+        return {name: (m.kernel.data, m.bias.data) for name, m in self.agents[k].actor.layers.items()}
+
     def actor_weights(self, k):
         """weights of agent k's online actor -- the model ``act`` uses (:340) -- for ``BatchedActor.set_weights``"""
         return self.agents[k].actor.export_weights()

@@ -340,3 +340,32 @@ def test_tridiagonal_pareto_branch_is_bit_identical_to_dense(N, B, P, monkeypatc
         outs[mode] = [t.clone() for t in (*o1, *o2)]
     for t0, t1 in zip(outs["0"], outs["1"]):
         assert torch.equal(t0, t1)
+
+
+@pytest.mark.parametrize("nodes,B", [(16, 40), (32, 12)])
+def test_set_weights_device_equals_host_path(nodes, B):
+    """tactor_set_weights_device rebuilds the operand images (scales, fp16 hi/lo split, core-matrix layout, layer-1 fragment
+    image) with kernels: a handle updated from device tensors gives bit-identical outputs to one built from the same
+    weights on the host, including weights whose scale exponent differs from the handle's previous ones"""
+    from mop_truss_marl_b200 import actor, tf_checkpoint
+    rng = np.random.RandomState(nodes)
+    w_old = tf_checkpoint.random_actor_weights(seed=1)
+    w_new = tf_checkpoint.random_actor_weights(seed=2)
+    for i, k in enumerate(w_new):                     # different magnitudes per layer -> different power-of-two scales
+        w_new[k] = (w_new[k][0] * np.float32(2.0 ** ((i % 5) - 2)), (rng.randn(*w_new[k][1].shape) * 0.05).astype(np.float32))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    r = lambda *s: torch.rand(*s, device="cuda", generator=g)   # noqa: E731
+    sc = 1.0 / nodes
+    inp = (r(B, nodes, 13), r(nodes, nodes) * sc, r(B, nodes, nodes) * sc, r(B, nodes, nodes) * sc, r(B, nodes, nodes) * sc,
+           r(B, 5, 4), r(B, 5, 5) * 0.2)
+    host = actor.BatchedActor(w_new, nodes, B)
+    dev = actor.BatchedActor(w_old, nodes, B)
+    dev.forward(*inp)
+    dev.set_weights_device({k: (torch.from_numpy(np.ascontiguousarray(a)).cuda(), torch.from_numpy(np.ascontiguousarray(b)).cuda())
+                            for k, (a, b) in w_new.items()})
+    o_host, o_dev = host.forward(*inp), dev.forward(*inp)
+    torch.cuda.synchronize()
+    host.check(); dev.check()
+    assert torch.equal(o_host[0], o_dev[0]) and torch.equal(o_host[1], o_dev[1])
+    with pytest.raises(ValueError):
+        dev.set_weights_device({k: (torch.from_numpy(a), torch.from_numpy(b)) for k, (a, b) in w_new.items()})   # host tensors
