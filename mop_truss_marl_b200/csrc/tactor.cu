@@ -197,15 +197,45 @@ pareto_tri_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, 
   bool off = false;
   for (int i = lane; i < 3 * 52; i += 32) (&dg[0][0])[i] = 0.f;
   __syncwarp();
-  int i = 0, j = lane;
-  while (j >= P) { j -= P; ++i; }
-  for (int idx = lane; idx < P * P; idx += 32) {
-    const float v = __ldg(A + idx);
+  auto take = [&](float v, int i, int j) {
     const int dj = j - i;
     if (dj >= -1 && dj <= 1) dg[dj + 1][i] = v;
     else off = off || (v != 0.f);
-    j += 32;
+  };
+  const int PP = P * P;
+  if ((PP & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0) {
+    // 128-bit loads, four in flight per lane (the matrix is 10 KB for P = 50: the scan is a latency chain otherwise)
+    const float4* A4 = reinterpret_cast<const float4*>(A);
+    const int n4 = PP >> 2;
+    for (int q0 = lane; q0 < n4; q0 += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + 32 * u;
+        v[u] = q < n4 ? __ldg(A4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + 32 * u;
+        if (q < n4) {
+          int i = (4 * q) / P, j = 4 * q - i * P;
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            take(e[t], i, j);
+            if (++j == P) { j = 0; ++i; }
+          }
+        }
+      }
+    }
+  } else {
+    int i = 0, j = lane;
     while (j >= P) { j -= P; ++i; }
+    for (int idx = lane; idx < PP; idx += 32) {
+      take(__ldg(A + idx), i, j);
+      j += 32;
+      while (j >= P) { j -= P; ++i; }
+    }
   }
   for (int p = lane; p < P; p += 32) x_s[warp][p] = __ldg(reinterpret_cast<const float4*>(x_p + (size_t)b * P * 4) + p);
   off = __any_sync(0xffffffffu, off);
@@ -232,21 +262,29 @@ pareto_tri_kernel(const float* __restrict__ x_p, const float* __restrict__ A_p, 
 #pragma unroll
   for (int k = 0; k < NC; ++k) { tp[k] = 0.f; sum[0][k] = sum[1][k] = sum[2][k] = sum[3][k] = 0.f; }
   trow(0, tc);
-  const bool sliced = P > PSMALL;                            // the dense kernel for P > 16 pools in four slices of 13 rows
-  for (int p = 0; p < valid; ++p) {
-    trow(p + 1, tn);
-    const float al = dg[0][p], ad = dg[1][p], au = dg[2][p];
-    const int sl = sliced ? p / PSL : 0;
+  // the dense kernel for P > 16 pools in four slices of 13 rows, the small one in a single run: same grouping here
+  const int slice = (P > PSMALL) ? PSL : 64;
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      float u = 0.f;
-      if (p > 0) u = fmaf(al, tp[k], u);
-      u = fmaf(ad, tc[k], u);
-      if (p + 1 < P) u = fmaf(au, tn[k], u);
-      const float r = fmaxf(u + bias[k], 0.f);
-      if (sl == 0) sum[0][k] += r; else if (sl == 1) sum[1][k] += r; else if (sl == 2) sum[2][k] += r; else sum[3][k] += r;
-      tp[k] = tc[k]; tc[k] = tn[k];
+  for (int sl = 0; sl < 4; ++sl) {
+    float acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[k] = 0.f;
+    const int p_end = min(valid, (sl + 1) * slice);
+    for (int p = sl * slice; p < p_end; ++p) {
+      trow(p + 1, tn);
+      const float al = dg[0][p], ad = dg[1][p], au = dg[2][p];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        float u = 0.f;
+        if (p > 0) u = fmaf(al, tp[k], u);
+        u = fmaf(ad, tc[k], u);
+        if (p + 1 < P) u = fmaf(au, tn[k], u);
+        acc[k] += fmaxf(u + bias[k], 0.f);
+        tp[k] = tc[k]; tc[k] = tn[k];
+      }
     }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) sum[sl][k] = acc[k];
   }
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
