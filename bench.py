@@ -378,17 +378,7 @@ def train_leg(args, rank, local_rank, world, dev, steps=10, standalone=False, fa
     keep = torch.arange(0, B, B // 64, device=dev)[:64]                                   # 64 transitions per step enter the replay
     acts = [(torch.empty(B, N, 2, device=dev), torch.empty(B, N, 3, device=dev)) for _ in range(3)]
     ev = lambda: torch.cuda.Event(enable_timing=True)                                    # noqa: E731
-    ar_events = []
-    orig_allreduce = learner_mod.allreduce_flat
-
-    def timed_allreduce(params, group=None):
-        e0, e1 = ev(), ev()
-        e0.record()
-        n = orig_allreduce(params, group)
-        e1.record()
-        ar_events.append((e0, e1))
-        return n
-    learner_mod.allreduce_flat = timed_allreduce
+    use_graph = not getattr(args, "train_eager", False)
 
     def state_of(e):
         return {"x_n": e.x_n, "A_n": e.A_n, "A_s": e.A_s, "A_n_ts": e.A_n_ts, "A_n_cs": e.A_n_cs, "x_p": x_p, "A_p": A_p}
@@ -423,18 +413,33 @@ def train_leg(args, rank, local_rank, world, dev, steps=10, standalone=False, fa
         return t
     for _ in range(3):
         one_step(False)
+    if use_graph:
+        lrn.capture_graph()          # one MADDPG.train() = one cudaGraphLaunch from here on (the all-reduces are graph nodes)
+        for _ in range(2):
+            one_step(False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ar_events.clear()
-    el0 = lrn.allreduced_elements
+    # elements one update all-reduces (six flat buffers: three critics, three actors)
+    sizes = [sum(p.numel() for p in m.parameters()) for a in lrn.agents for m in (a.critic, a.actor)]
     t0 = time.perf_counter()
     stamps = [one_step(True) for _ in range(steps)]
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3 / steps
-    learner_mod.allreduce_flat = orig_allreduce
     seg = lambda a, b: float(np.mean([s[a].elapsed_time(s[b]) for s in stamps]))       # noqa: E731
-    ar_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in ar_events)) / steps
+    # the six all-reduces of one update, timed on their own (inside the update they are nodes of the captured graph)
+    ar_ms = 0.0
+    if world > 1:
+        bufs = [torch.zeros(n, device=dev) for n in sizes]
+        for rep_ in range(12):
+            e0, e1 = ev(), ev()
+            e0.record()
+            for b_ in bufs:
+                dist.all_reduce(b_)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep_ >= 2:
+                ar_ms += e0.elapsed_time(e1) / 10
     step_ms = _max_over_ranks(wall_ms, dev, world)
     for p_ in pols:
         p_.check()
@@ -453,11 +458,12 @@ def train_leg(args, rank, local_rank, world, dev, steps=10, standalone=False, fa
         "value": 3 * B * world / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms,
         "updates_per_s": 1e3 / step_ms, "replay_transitions_per_step": int(keep.numel()), "learner_batch": lrn.batch_size,
         "stages_ms": {"rollout_3x_act_3x_env_step": seg(0, 1), "replay_push": seg(1, 2), "learner_train_update": seg(2, 3),
-                      "of_which_all_reduce": ar_ms, "weight_push_and_state_advance": seg(3, 4)},
+                      "weight_push_and_state_advance": seg(3, 4)},
+        "learner_update": "one captured CUDA graph per MADDPG.train()" if use_graph else "eager PyTorch",
         "all_reduce": {"backend": dist.get_backend() if world > 1 else None, "ranks": world,
-                       "calls_per_step": len(ar_events) / steps,
-                       "bytes_per_step": 4 * (lrn.allreduced_elements - el0) / steps,
-                       "share_of_step": ar_ms / step_ms},
+                       "calls_per_step": 6 if world > 1 else 0,
+                       "bytes_per_step": 4 * sum(sizes) if world > 1 else 0,
+                       "ms_per_step_standalone": ar_ms, "share_of_step": ar_ms / step_ms},
         "models_identical_across_ranks": same,
         "rewards": "synthetic (minus the child's objectives)", "data": "synthetic",
     }
@@ -484,6 +490,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (BASELINE configs 3 and 4 shapes, actor at P = 50, training leg)")
     ap.add_argument("--train", action="store_true", help="only the training loop of BASELINE config 5 (large roof, MADDPG update with gradient all-reduce)")
     ap.add_argument("--train-steps", type=int, default=0, help="timed steps of the training leg (default: 10, or --steps with --train)")
+    ap.add_argument("--train-eager", action="store_true", help="training leg: run the learner update eagerly instead of as a captured CUDA graph")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

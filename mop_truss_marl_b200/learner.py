@@ -137,12 +137,14 @@ def allreduce_flat(params, group=None):
 
 
 def _clip_global_norm(params, max_norm=1.0):
-    """keras ``clipnorm``: every gradient tensor is clipped to ``max_norm`` on its OWN norm"""
-    for p in params:
-        if p.grad is not None:
-            nrm = p.grad.norm()
-            if nrm > max_norm:
-                p.grad.mul_(max_norm / nrm)
+    """keras ``clipnorm``: every gradient tensor is clipped to ``max_norm`` on its OWN norm (branch-free on the device: no
+    host synchronisation, capturable in a CUDA graph)"""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    norms = torch._foreach_norm(grads)
+    scales = [torch.clamp(max_norm / (n + 1e-30), max=1.0) for n in norms]
+    torch._foreach_mul_(grads, scales)
 
 
 class _Agent:
@@ -150,7 +152,8 @@ class _Agent:
         self.actor, self.target_actor = ActorNet(hidden, seed=seed).to(device), ActorNet(hidden, seed=seed).to(device)
         self.critic, self.target_critic = CriticNet(hidden, n_q, seed=seed + 1).to(device), CriticNet(hidden, n_q, seed=seed + 1).to(device)
         self.lr, self.tau, self.update_num = lr, 0.005, 0
-        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=lr, eps=1e-7)
+        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=lr, eps=1e-7,
+                                           capturable=torch.device(device).type == "cuda")
         self.update_init()
 
     @staticmethod
@@ -227,8 +230,13 @@ class DeviceReplay:
         self.head = (self.head + n) % self.capacity
         self.size = min(self.capacity, self.size + n)
 
-    def sample(self, batch_size):
-        idx = torch.randint(0, self.size, (batch_size,), device=self.device, generator=self.gen)
+    def draw(self, batch_size):
+        """indices of a uniform sample of the stored transitions"""
+        return torch.randint(0, self.size, (batch_size,), device=self.device, generator=self.gen)
+
+    def sample(self, batch_size, idx=None):
+        if idx is None:
+            idx = self.draw(batch_size)
 
         def st(d):
             return (d["x_n"][idx], self.A_n, d["A_s"][idx], d["A_n_ts"][idx], d["A_n_cs"][idx], d["x_p"][idx], d["A_p"][idx])
@@ -254,6 +262,7 @@ class MADDPGLearner:
         self.allreduced_elements = 0
         self.last_losses = None
         self.honour_done = False           # False = the reference's behaviour (its terminal test never fires, see train())
+        self._graph, self._graph_idx = None, None
         self.device_replay = None          # a DeviceReplay: train() samples from it instead of the host-side deque
         self.keep_losses_on_device = False  # True: no host synchronisation inside train() (last_losses holds tensors)
 
@@ -286,6 +295,10 @@ class MADDPGLearner:
         if self.device_replay is not None:
             if len(self.device_replay) < self.batch_size:
                 return False
+            if self._graph is not None:                      # the whole update as ONE captured CUDA graph
+                self._graph_idx.copy_(self.device_replay.draw(self.batch_size))
+                self._graph.replay()
+                return True
             S, NS, A, R, done = self.device_replay.sample(self.batch_size)
         else:
             if len(self.memory) < self.batch_size:
@@ -297,6 +310,56 @@ class MADDPGLearner:
                   torch.stack([m[1][k][1] for m in samples]).to(self.device)) for k in range(3)]
             R = torch.stack([m[2] for m in samples]).to(self.device)                    # [B,3]
             done = torch.tensor([m[4] for m in samples], device=self.device)
+        self._update_from_batch(S, NS, A, R, done)
+        return True
+
+    def capture_graph(self):
+        """Capture one whole ``train()`` -- sampling by index, the nine target-actor and nine target-critic forwards, three
+        critic regressions and three actor ascents with their gradient all-reduces and optimiser steps (~6 000 small kernels
+        at batch 32) -- into a CUDA graph; later ``train()`` calls draw new indices and replay it.  Needs the device
+        replay and a CUDA device.  The three warm-up updates PyTorch asks for before a capture run on a side stream and
+        are undone afterwards (models and optimiser states are restored), so capturing does not change the training."""
+        if self.device_replay is None or self.device.type != "cuda" or len(self.device_replay) < self.batch_size:
+            raise RuntimeError("capture_graph needs a filled DeviceReplay on a CUDA device")
+        self.keep_losses_on_device = True                   # no host read-back inside a capture
+        models = [m for a in self.agents for m in (a.actor, a.critic, a.target_actor, a.target_critic)]
+        saved = [{k: v.clone() for k, v in m.state_dict().items()} for m in models]
+        saved_opt = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                     for a in self.agents for st in a.critic_opt.state.values()]
+        self._graph_idx = self.device_replay.draw(self.batch_size)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._update_from_batch(*self.device_replay.sample(self.batch_size, idx=self._graph_idx))
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._update_from_batch(*self.device_replay.sample(self.batch_size, idx=self._graph_idx))
+        with torch.no_grad():                               # undo the warm-up and capture-time updates
+            for m, sd in zip(models, saved):
+                m.load_state_dict(sd)
+            it = iter(saved_opt)
+            for a in self.agents:
+                for st in a.critic_opt.state.values():
+                    old = next(it, None)
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            if old is not None and k in old:
+                                v.copy_(old[k])
+                            else:
+                                v.zero_()
+            if not saved_opt:                               # the optimiser had no state yet: back to step 0
+                for a in self.agents:
+                    for st in a.critic_opt.state.values():
+                        for v in st.values():
+                            if torch.is_tensor(v):
+                                v.zero_()
+        self._graph = graph
+        return graph
+
+    def _update_from_batch(self, S, NS, A, R, done):
         order = {0: (0, 1, 2), 1: (1, 0, 2), 2: (2, 0, 1)}                           # own action first (:560-562)
         with torch.no_grad():
             # next actions of every target actor on every agent's next state, then the target critics (:564-606)
@@ -336,12 +399,14 @@ class MADDPGLearner:
             # a NEW Adam every call (:625): Keras applies lr sqrt(1 - b2) / (1 - b1) * m / (sqrt(v) + eps) with m = (1 - b1) g,
             # v = (1 - b2) g^2 on the first step, i.e. lr * g / (|g| + eps / sqrt(1 - b2)), eps = 1e-7, b2 = 0.999
             with torch.no_grad():
-                for p in ag.actor.parameters():
-                    p.add_(-(ag.lr * 0.1) * p.grad / (p.grad.abs() + 1e-7 / (1.0 - 0.999) ** 0.5))
+                params = list(ag.actor.parameters())
+                grads = [p.grad for p in params]
+                denom = torch._foreach_abs(grads)
+                torch._foreach_add_(denom, 1e-7 / (1.0 - 0.999) ** 0.5)
+                torch._foreach_addcdiv_(params, grads, denom, value=-(ag.lr * 0.1))
             losses.append((c_loss.detach(), a_loss.detach()) if self.keep_losses_on_device
                           else (float(c_loss.detach()), float(a_loss.detach())))
         self.last_losses = losses
-        return True
 
     def update(self):
         """``MADDPG.update`` (:692-697): every 300 actor calls let each agent check its own counter"""

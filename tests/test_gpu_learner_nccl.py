@@ -56,3 +56,33 @@ def test_nccl_gradient_allreduce_keeps_cuda_ranks_identical(tmp_path):
     assert torch.equal(r0["flat"], r1["flat"])                   # averaged gradients -> bit-identical weights on both GPUs
     assert r0["elements"] == r1["elements"] > 0
     assert r0["actor_vs_twin"] <= 2e-5 and r1["actor_vs_twin"] <= 2e-5   # CUDA actor == differentiable twin after the update
+
+
+def test_captured_update_equals_eager_update():
+    """MADDPGLearner.capture_graph(): one train() as a replayed CUDA graph gives the same parameters as the eager update on
+    the same sampled indices (the warm-up updates of the capture are undone), here on one GPU without a process group"""
+    from mop_truss_marl_b200 import learner
+    dev = torch.device("cuda", 0)
+    N, P, B = 16, 3, 64
+
+    def make():
+        lrn = learner.MADDPGLearner(lr=1e-3, hidden=200, n_q=32, batch_size=8, device=dev, seed=5)
+        lrn.device_replay = learner.DeviceReplay(256, N, P, dev, seed=7)
+        g = torch.Generator(device=dev).manual_seed(11)
+        r = lambda *s: torch.rand(*s, device=dev, generator=g)                                     # noqa: E731
+
+        def state():
+            return {"x_n": r(B, N, 13), "A_n": torch.full((N, N), 1.0 / N, device=dev), "A_s": r(B, N, N) / N,
+                    "A_n_ts": r(B, N, N) / N, "A_n_cs": r(B, N, N) / N, "x_p": r(B, P, 4), "A_p": r(B, P, P) / P}
+        lrn.device_replay.push(state(), [(r(B, N, 2), r(B, N, 3)) for _ in range(3)], r(B, 3), [state() for _ in range(3)], 0.0)
+        return lrn
+    eager, graphed = make(), make()
+    graphed.capture_graph()
+    graphed.device_replay.gen.set_state(eager.device_replay.gen.get_state())      # the capture drew one index set
+    for _ in range(4):
+        assert eager.train() and graphed.train()
+    torch.cuda.synchronize()
+    for a, b in zip(eager.agents, graphed.agents):
+        for m1, m2 in ((a.actor, b.actor), (a.critic, b.critic)):
+            for p1, p2 in zip(m1.parameters(), m2.parameters()):
+                assert torch.allclose(p1, p2, rtol=0, atol=1e-6), float((p1 - p2).abs().max())
