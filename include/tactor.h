@@ -46,7 +46,8 @@ typedef struct tactor_inputs {
 
 const char* tactor_last_error(void);
 
-/* nodes = N (16 or 32), max_batch = largest B of any later call (workspace is allocated once). */
+/* nodes = N: 16 or 32 (the test/ families), or 12 (the 6 x 2 shapes of train/code: every tensor keeps its [B,12,...] shape,
+ * the graphs are padded to 16 nodes internally); max_batch = largest B of any later call (workspace is allocated once). */
 int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device, tactor_handle_t* out);
 int tactor_destroy(tactor_handle_t h);
 

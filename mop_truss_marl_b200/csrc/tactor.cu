@@ -425,6 +425,35 @@ __global__ void __launch_bounds__(32) pack_w1frag_kernel(PackArgs a) {
   pack(we(2 * t + 8, f0 + 8), we(2 * t + 9, f0 + 8), hi[3], lo[3]);
 }
 
+// 12-node graphs (the 6 x 2 shapes of train/code) run on the 16-node build: every environment is padded to 16 rows with zero
+// features and zero adjacency rows / columns (a padded node neither sends nor receives), the kernel divides the pooled
+// scramble by the real node count and writes only the real rows.
+__global__ void __launch_bounds__(256)
+pad_nodes_kernel(int B, int n, const float* __restrict__ x_n, const float* __restrict__ A_n, const float* __restrict__ A_s,
+                 const float* __restrict__ A_ts, const float* __restrict__ A_cs, float* __restrict__ x_o, float* __restrict__ An_o,
+                 float* __restrict__ As_o, float* __restrict__ Ats_o, float* __restrict__ Acs_o) {
+  constexpr int NP = 16;
+  const int per_env = NP * 13 + 3 * NP * NP;
+  const long long total = (long long)B * per_env;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int b = (int)(idx / per_env), r = (int)(idx % per_env);
+    if (r < NP * 13) {
+      const int i = r / 13, c = r % 13;
+      x_o[(size_t)b * NP * 13 + r] = i < n ? x_n[((size_t)b * n + i) * 13 + c] : 0.f;
+    } else {
+      const int t = (r - NP * 13) / (NP * NP), e = (r - NP * 13) % (NP * NP), i = e / NP, j = e % NP;
+      const float* src = t == 0 ? A_s : t == 1 ? A_ts : A_cs;
+      float* dst = t == 0 ? As_o : t == 1 ? Ats_o : Acs_o;
+      dst[(size_t)b * NP * NP + e] = (i < n && j < n) ? src[((size_t)b * n + i) * n + j] : 0.f;
+    }
+  }
+  if (blockIdx.x == 0)
+    for (int e = threadIdx.x; e < NP * NP; e += 256) {
+      const int i = e / NP, j = e % NP;
+      An_o[e] = (i < n && j < n) ? A_n[i * n + j] : 0.f;
+    }
+}
+
 constexpr int pareto_smem(int P) { return (P * LD + 4 * LD + P * P + P * 4) * 4; }
 constexpr int PARETO_SMEM = pareto_smem(50);
 
@@ -436,6 +465,8 @@ thread_local std::string g_actor_err;
 }
 struct tactor_handle_s {
   int device = 0, nodes = 0, max_batch = 0;
+  int n_real = 0;                      // nodes of the caller's graphs (12: padded to 16 internally; else = nodes)
+  float* pad[5] = {};                  // padded x_n, A_n, A_s, A_n_ts, A_n_cs of a 12-node handle
   float* d_w[TACTOR_NLAYERS] = {};     // packed [Kpad, 208]
   float* d_b[TACTOR_NLAYERS] = {};     // [208]
   float* pooled = nullptr;             // [max_batch, 208] Pareto embedding
@@ -466,7 +497,7 @@ struct Guard {
   ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-template <int NODES, int NCTA, int NPH, int NEPIW>
+template <int NODES, int NCTA, int NPH, int NEPIW, int NREAL = NODES>
 cudaError_t launch_pipe(tactor::tc::fused::Params& p, int M, int sms, cudaStream_t st) {
   using namespace tactor;
   const int tiles = (M + tc::TCM - 1) / tc::TCM;
@@ -494,12 +525,12 @@ cudaError_t launch_pipe(tactor::tc::fused::Params& p, int M, int sms, cudaStream
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = (NCTA == 1) ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, tc::pipe::actor_pipe_kernel<NODES, NCTA, NPH, NEPIW>, p);
+  return cudaLaunchKernelEx(&cfg, tc::pipe::actor_pipe_kernel<NODES, NCTA, NPH, NEPIW, NREAL>, p);
 }
 
-template <int NODES, int NCTA, int NPH, int NEPIW>
+template <int NODES, int NCTA, int NPH, int NEPIW, int NREAL = NODES>
 cudaError_t set_pipe_smem() {
-  return cudaFuncSetAttribute(tactor::tc::pipe::actor_pipe_kernel<NODES, NCTA, NPH, NEPIW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(tactor::tc::pipe::actor_pipe_kernel<NODES, NCTA, NPH, NEPIW, NREAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               tactor::tc::pipe::pipe_smem_bytes<NODES, NCTA>());
 }
 
@@ -678,7 +709,8 @@ cudaError_t run_forward(tactor_handle_s* h, int B, const tactor_inputs* in, floa
   p.w_head[0] = h->d_w[11]; p.w_head[1] = h->d_w[12]; p.b_head[0] = h->d_b[11]; p.b_head[1] = h->d_b[12];
   p.geo = geo; p.topo = topo; p.M = M; p.error_flag = h->d_error; p.dev_flags = h->dev_flags;
   p.noise = nz.on; p.mu = nz.mu; p.theta = nz.theta; p.sigma = nz.sigma; p.seed = nz.seed; p.call = nz.call; p.seed_call = nz.seed_call;
-  cudaError_t e = launch_pipe_variant<NODES>(h->ncta, h->variant, p, M, h->sms, st);
+  cudaError_t e = (h->n_real == 12) ? launch_pipe<16, 1, 2, 4, 12>(p, M, h->sms, st)      // the padded 12-node build
+                                    : launch_pipe_variant<NODES>(h->ncta, h->variant, p, M, h->sms, st);
   h->launches.fetch_add(2);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -691,14 +723,16 @@ const char* tactor_last_error(void) { return g_actor_err.c_str(); }
 int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device, tactor_handle_t* out) {
   if (!w || !out) return afail(TFEM_ERR_ARG, "null argument");
   *out = nullptr;
-  if (nodes != 16 && nodes != 32) return afail(TFEM_ERR_UNSUPPORTED, "nodes must be 16 or 32");
+  if (nodes != 12 && nodes != 16 && nodes != 32) return afail(TFEM_ERR_UNSUPPORTED, "nodes must be 12, 16 or 32");
+  const int n_real = nodes;
+  if (nodes == 12) nodes = 16;          // 12-node graphs (train/code) are padded to the 16-node build, see pad_nodes_kernel
   if (max_batch <= 0) return afail(TFEM_ERR_ARG, "max_batch must be positive");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return afail(TFEM_ERR_CUDA, "no CUDA device: no CPU path");
   if (device < 0 || device >= ndev) return afail(TFEM_ERR_ARG, "bad device index");
   tactor_handle_s* h = new (std::nothrow) tactor_handle_s();
   if (!h) return afail(TFEM_ERR_ARG, "out of host memory");
-  h->device = device; h->nodes = nodes; h->max_batch = max_batch;
+  h->device = device; h->nodes = nodes; h->n_real = n_real; h->max_batch = max_batch;
   if (const char* v = getenv("TACTOR_NCTA")) h->ncta = (atoi(v) == 2) ? 2 : 1;     // development switches (A/B timing)
   if (const char* v = getenv("TACTOR_VARIANT")) h->variant = atoi(v);
   if (const char* v = getenv("TACTOR_FLAGS")) h->dev_flags = atoi(v);
@@ -711,11 +745,16 @@ int tactor_create(const tactor_weights* w, int nodes, int max_batch, int device,
   if (e == cudaSuccess) e = cudaMalloc(&h->d_error, 65536);
   if (e == cudaSuccess) e = cudaMemset(h->d_error, 0, 65536);
   if (e == cudaSuccess) e = (nodes == 16) ? set_pipe_smem_variant<16>(h->ncta, h->variant) : set_pipe_smem_variant<32>(h->ncta, h->variant);
+  if (e == cudaSuccess && n_real == 12) e = set_pipe_smem<16, 1, 2, 4, 12>();
   if (e == cudaSuccess)
     e = (nodes == 16) ? cudaFuncSetAttribute(tactor::pareto_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM)
                       : cudaFuncSetAttribute(tactor::pareto_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tactor::PARETO_SMEM);
   if (e == cudaSuccess) e = cudaMalloc(&h->pooled, (size_t)max_batch * tactor::LD * 4);
   if (e == cudaSuccess) e = cudaMalloc(&h->pareto_flag, (size_t)max_batch * sizeof(int));
+  if (n_real != nodes) {
+    const size_t sz[5] = {(size_t)max_batch * 16 * 13, 16 * 16, (size_t)max_batch * 256, (size_t)max_batch * 256, (size_t)max_batch * 256};
+    for (int k = 0; k < 5 && e == cudaSuccess; ++k) e = cudaMalloc(&h->pad[k], sz[k] * sizeof(float));
+  }
   if (const char* v = getenv("TACTOR_PARETO_DENSE")) h->pareto_dense = (v[0] == '1');
   if (e != cudaSuccess) { tactor_destroy(h); return afail(TFEM_ERR_CUDA, std::string("actor setup: ") + cudaGetErrorString(e)); }
   *out = h;
@@ -765,6 +804,7 @@ int tactor_destroy(tactor_handle_t h) {
   for (int l = 0; l < TACTOR_NLAYERS; ++l) { if (h->d_w[l]) cudaFree(h->d_w[l]); if (h->d_b[l]) cudaFree(h->d_b[l]); }
   if (h->pooled) cudaFree(h->pooled);
   if (h->pareto_flag) cudaFree(h->pareto_flag);
+  for (float* p : h->pad) if (p) cudaFree(p);
   for (int l = 0; l < TACTOR_NLAYERS; ++l) if (h->d_wimg[l]) cudaFree(h->d_wimg[l]);
   if (h->d_error) cudaFree(h->d_error);
   if (h->d_w1frag) cudaFree(h->d_w1frag);
@@ -782,7 +822,8 @@ static int check_inputs(tactor_handle_t h, int B, const tactor_inputs* in, float
   if (in->P < 1 || in->P > 50) return afail(TFEM_ERR_ARG, "P must be in 1..50 (MAX_FRONT)");
   const void* vec[] = {in->A_n, in->A_s, in->A_n_ts, in->A_n_cs, in->x_n};     // read with 128-bit loads / 16-byte async copies
   for (const void* p : vec)
-    if (reinterpret_cast<uintptr_t>(p) & 15u) return afail(TFEM_ERR_ALIGN, "x_n and the adjacency tensors must be 16-byte aligned");
+    if (h->n_real == h->nodes && (reinterpret_cast<uintptr_t>(p) & 15u))
+      return afail(TFEM_ERR_ALIGN, "x_n and the adjacency tensors must be 16-byte aligned");
   return TFEM_OK;
 }
 
@@ -791,6 +832,17 @@ static int forward_impl(tactor_handle_t h, int B, const tactor_inputs* in, float
   if (int rc = check_inputs(h, B, in, geo, topo)) return rc;
   if (B == 0) return TFEM_OK;
   Guard g(h->device);
+  tactor_inputs padded;
+  if (h->n_real != h->nodes) {          // 12 -> 16 nodes: zero-padded copies of the graph tensors in handle-owned buffers
+    const long long total = (long long)B * (16 * 13 + 3 * 256);
+    const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    tactor::pad_nodes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, h->n_real, in->x_n, in->A_n, in->A_s, in->A_n_ts, in->A_n_cs,
+                                                                      h->pad[0], h->pad[1], h->pad[2], h->pad[3], h->pad[4]);
+    h->launches.fetch_add(1);
+    padded = *in;
+    padded.x_n = h->pad[0]; padded.A_n = h->pad[1]; padded.A_s = h->pad[2]; padded.A_n_ts = h->pad[3]; padded.A_n_cs = h->pad[4];
+    in = &padded;
+  }
   cudaError_t e = (h->nodes == 16) ? run_forward<16>(h, B, in, geo, topo, nz, (cudaStream_t)stream)
                                    : run_forward<32>(h, B, in, geo, topo, nz, (cudaStream_t)stream);
   if (e != cudaSuccess) return afail(TFEM_ERR_CUDA, std::string("actor forward: ") + cudaGetErrorString(e));

@@ -104,7 +104,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 #define PROF_FLUSH() do { } while (0)
 #endif
 
-template <int NODES, int NCTA, int NPH, int NEPIW>
+// NREAL: nodes of a real graph when the tensors are padded to NODES rows per environment (12 in 16: the train/code shapes),
+// else NODES -- a compile-time constant, so that the production instantiations keep their shifts in the pooled scramble
+template <int NODES, int NCTA, int NPH, int NEPIW, int NREAL = NODES>
 __global__ void __launch_bounds__(pipe_threads<NPH, NEPIW>(), 1)
 actor_pipe_kernel(const __grid_constant__ Params P) {
   constexpr int NGENW = 4 * NPH, W_ISSUER = NGENW + NEPIW, W_PRODUCER = W_ISSUER + 1, PTHREADS = pipe_threads<NPH, NEPIW>();
@@ -466,7 +468,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
                       const int r = 32 * q + 16 * kr + 8 * b + 2 * t4 + i;
                       if (g == 4) {
                         // the reference's stack-and-reshape scramble: x14b[b,n,h] = pooled[b,(n*200+h)/N] (truss2D_RL.py:89-95)
-                        v[b][i] = Pl[(r / NODES) * 208 + ((r % NODES) * KH + feat) / NODES];
+                        v[b][i] = (NREAL == NODES || (r % NODES) < NREAL) ? Pl[(r / NODES) * 208 + ((r % NODES) * KH + feat) / NREAL] : 0.f;   // (padding rows of a 12-in-16 graph: 0)
                       } else {
                         v[b][i] = H[r * LDH + feat];             // layer 3: rows of the five-way sum
                       }
@@ -619,13 +621,14 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           }
           __syncwarp();
           const int row = row0 + r;
-          if (row < M) {
-            float* dst = (hd == 0 ? P.geo : P.topo) + (size_t)row * nout;
+          if (row < M && (NREAL == NODES || n < NREAL)) {      // padding rows of a 12-in-16 graph are not outputs
+            const size_t orow = (NREAL == NODES) ? (size_t)row : (size_t)(row / NODES) * NREAL + n;
+            float* dst = (hd == 0 ? P.geo : P.topo) + orow * nout;
             uint64_t seed = P.seed, call = P.call;
             if (P.noise && P.seed_call) { seed = P.seed_call[0]; call += P.seed_call[1]; }
             for (int t = 0; t < nout; ++t) {
               float v = 1.f / (1.f + expf(-o[t]));
-              if (P.noise) v = ou_step(v, P.mu, P.theta, P.sigma, seed, call, (uint64_t)(hd + 1), (uint64_t)row * nout + t);
+              if (P.noise) v = ou_step(v, P.mu, P.theta, P.sigma, seed, call, (uint64_t)(hd + 1), (uint64_t)orow * nout + t);
               dst[t] = v;
             }
           }

@@ -369,3 +369,41 @@ def test_set_weights_device_equals_host_path(nodes, B):
     assert torch.equal(o_host[0], o_dev[0]) and torch.equal(o_host[1], o_dev[1])
     with pytest.raises(ValueError):
         dev.set_weights_device({k: (torch.from_numpy(a), torch.from_numpy(b)) for k, (a, b) in w_new.items()})   # host tensors
+
+
+@pytest.mark.parametrize("B,P", [(37, 1), (64, 20), (9, 7)])
+def test_twelve_node_graphs_of_the_training_shapes(B, P):
+    """The 6 x 2 shapes of train/code have 12 nodes: the handle pads every graph to 16 rows internally (zero features, zero
+    adjacency rows / columns), divides the pooled scramble by the real node count and writes [B,12,...] outputs; checked
+    against the float64 oracle run on the unpadded 12-node tensors, with the trained checkpoint"""
+    from mop_truss_marl_b200 import actor
+    from oracle.actor_oracle import actor_forward
+    rng = np.random.RandomState(B)
+    w = trained_weights(2)
+    inp = random_inputs(rng, B, 12, P)
+    a = actor.BatchedActor(w, 12, max_batch=B)
+    dev = [torch.from_numpy(t).cuda() for t in inp]
+    geo, topo = a.forward(*dev)
+    a.check()
+    g64, t64 = actor_forward(w, *inp)
+    assert geo.shape == (B, 12, 2) and topo.shape == (B, 12, 3)
+    assert np.abs(geo.cpu().numpy() - g64).max() <= ATOL and np.abs(topo.cpu().numpy() - t64).max() <= ATOL
+    geo2, topo2 = a.act(*dev)                              # noise on the 12 real rows only, deterministic per (seed, call)
+    assert geo2.shape == (B, 12, 2) and bool(torch.isfinite(topo2).all())
+
+
+def test_training_shape_closed_loop():
+    """actor + env-step on a train/code family (12 nodes, no symmetry step): a short closed loop stays healthy"""
+    from mop_truss_marl_b200 import actor, batched_env
+    B = 256
+    env = batched_env.BatchedTrussEnv("train2_roof", B, device="cuda:0")
+    env.reset()
+    pol = actor.BatchedActor(trained_weights(1), env.N, B)
+    x_p = torch.tensor([1.0, 1.0, 1.0, 1.0 / 20], device="cuda").repeat(B, 1, 1).contiguous()
+    A_p = torch.ones(B, 1, 1, device="cuda")
+    for _ in range(6):
+        geo, topo = pol.act(env.x_n, env.A_n, env.A_s, env.A_n_ts, env.A_n_cs, x_p, A_p)
+        env.step(geo, topo, (torch.rand(B, device="cuda") >= 0.5).to(torch.uint8))
+    torch.cuda.synchronize()
+    pol.check()
+    assert int(env.status.abs().max()) == 0 and bool(torch.isfinite(env.point).all())
