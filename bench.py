@@ -662,6 +662,34 @@ def main():
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    # ---- e2e with the raw tables travelling as their live columns in BOTH directions (extra key, next to `e2e`) -----------
+    e2e_compact = None
+    if use_actor:
+        cb = [roll.alloc_host(raw_tables=False), roll.alloc_host(raw_tables=False)]
+        for k in cb[0]:
+            if k in bufs[flip[0]]:
+                cb[0][k].copy_(bufs[flip[0]][k])
+        cflip = [0]
+
+        def compact_step():
+            roll.step(cb[cflip[0]], coin_host, x_p_host, A_p_host, cb[1 - cflip[0]])
+            cflip[0] = 1 - cflip[0]
+        for _ in range(3):
+            compact_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            compact_step()
+        torch.cuda.synchronize()
+        c_ms = _max_over_ranks((time.perf_counter() - t0) * 1e3 / ke, dev, world)
+        ch2d, cd2h = roll.bytes_per_step(raw_tables=False)
+        e2e_compact = {"value": B * world / (c_ms * 1e-3), "unit": UNIT, "ms_per_step": c_ms, "h2d_bytes_per_step": ch2d,
+                       "d2h_bytes_per_step": cd2h,
+                       "path": "as `e2e`, but the host state tuple carries nN_x_n / nN_x_e as the one column of each that "
+                               "_game_modify / _set_model read (node_y [B,N], element_section [B,E]) in both directions; "
+                               "HostRollout.alloc_host(raw_tables=False)"}
     # ---- e2e, resident state: what a batched driver does when the state tuple lives with the environment object (as it
     # does inside the reference's own Game / gen_model objects): per step the host sends the coins and the Pareto-front
     # graph and receives point + status; only the states it wants to archive would be fetched (not timed here).  Reported
@@ -770,6 +798,7 @@ def main():
             "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "path": e2e_path,
                     "h2d_gbs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9, "d2h_gbs_per_rank": d2h / (e2e_ms * 1e-3) / 1e9},
+            "e2e_compact_state": e2e_compact,
             "e2e_resident_state": e2e_res,
             "gpu_launches": launches,
             "clocks": clocks,

@@ -77,11 +77,17 @@ class HostRollout:
         except Exception:
             pass
 
-    def alloc_host(self, compact: bool = True):
+    def alloc_host(self, compact: bool = True, raw_tables: bool = True):
         """pinned host buffers for one state tuple (+ point, status, actions); ``compact``: also the compact copies of
-        the two live table columns (``COMPACT``), which the next step uploads instead of the full raw tables"""
+        the two live table columns (``COMPACT``), which the next step uploads instead of the full raw tables;
+        ``raw_tables=False`` (needs ``compact``): a state tuple WITHOUT ``nN_x_n`` / ``nN_x_e`` -- the driver only ever feeds
+        them back into ``_game_modify`` / ``_set_model`` (``master_DDPG_truss2D_MO.py:250-260, 755``), which read one column
+        of each, so the compact columns carry everything it uses and the step downloads 3.8 KB less per small environment"""
         env = self.env
-        h = {k: torch.empty(getattr(env, k).shape, dtype=getattr(env, k).dtype).pin_memory() for k in STATE_OUT}
+        if not raw_tables and not compact:
+            raise ValueError("a state tuple without the raw tables needs their compact columns")
+        h = {k: torch.empty(getattr(env, k).shape, dtype=getattr(env, k).dtype).pin_memory() for k in STATE_OUT
+             if raw_tables or k not in ("nN_x_n", "nN_x_e")}
         h["a_geo"] = torch.empty(env.B, env.N, 2).pin_memory()
         h["a_topo"] = torch.empty(env.B, env.N, 3).pin_memory()
         if compact:
@@ -99,10 +105,11 @@ class HostRollout:
         """drop the CUDA graphs cached for host buffers seen so far (call before freeing such buffers)"""
         _check(_lib.trollout_forget_buffers(self._h))
 
-    def bytes_per_step(self, P: int = 1, compact: bool = True):
+    def bytes_per_step(self, P: int = 1, compact: bool = True, raw_tables: bool = True):
         a, b = C.c_size_t(), C.c_size_t()
         _check(_lib.trollout_bytes_per_env(self._h, int(P), 1 if compact else 0, C.byref(a), C.byref(b)))
-        return a.value * self.env.B, b.value * self.env.B
+        down = b.value - (0 if raw_tables else 4 * (12 * self.env.N + 21 * self.env.E))
+        return a.value * self.env.B, down * self.env.B
 
     def step(self, state_host: dict, coin_host, x_p_host: torch.Tensor, A_p_host: torch.Tensor, out_host: dict,
              n_pf_host=None):
@@ -123,10 +130,14 @@ class HostRollout:
         io = _IO()
         shapes["node_y"], shapes["element_section"] = (B, N), (B, E)
         compact_in = all(k in state_host for k in COMPACT)
+        compact_out = all(k in out_host for k in COMPACT)
         for k in STATE_IN:
             if not (compact_in and k in ("nN_x_n", "nN_x_e")):     # not read when the compact columns travel
                 setattr(io.inp, k, chk(state_host[k], shapes[k]))
-            setattr(io.out, k, chk(out_host[k], shapes[k]))
+            if k in out_host:
+                setattr(io.out, k, chk(out_host[k], shapes[k]))
+            elif not (compact_out and k in ("nN_x_n", "nN_x_e")):
+                raise ValueError("out_host lacks %r (only the raw tables may be left out, when their compact columns are there)" % k)
         for k in COMPACT:
             if compact_in:
                 setattr(io.inp, k, chk(state_host[k], shapes[k]))

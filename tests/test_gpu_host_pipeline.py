@@ -174,3 +174,39 @@ def test_closed_loop_episode_stays_healthy(family, B):
     nx = env.N // 2
     assert float((y[:, nx:] - y[:, :nx]).min()) >= float(scal[2]) - 1e-6      # at least d_min deep everywhere
     assert env.game_step == 501                                # the reference counts from 1 (truss2D_ENV.py:242)
+
+
+def test_state_tuple_without_raw_tables():
+    """HostRollout.alloc_host(raw_tables=False): the raw tables travel as their live columns in both directions; every other
+    member of the tuple is bit-identical to the full-tuple path over several fed-back steps"""
+    from mop_truss_marl_b200 import actor, batched_env, tf_checkpoint
+    from mop_truss_marl_b200.host_pipeline import HostRollout, STATE_IN
+    B, dev = 160, torch.device("cuda", 0)
+    env = batched_env.BatchedTrussEnv("small_bridge", B, device=dev)
+    env.reset()
+    w = tf_checkpoint.random_actor_weights(seed=3)
+    pols = [actor.BatchedActor(w, env.N, B, device=dev, seed=9) for _ in range(2)]
+    rolls = [HostRollout(env, pols[k], pieces=2) for k in range(2)]
+    full = [rolls[0].alloc_host(), rolls[0].alloc_host()]
+    slim = [rolls[1].alloc_host(raw_tables=False), rolls[1].alloc_host(raw_tables=False)]
+    assert "nN_x_e" not in slim[0] and "element_section" in slim[0]
+    for k in STATE_IN:
+        full[0][k].copy_(getattr(env, k))
+    torch.cuda.synchronize()
+    HostRollout.fill_compact(full[0])
+    for k in slim[0]:
+        if k in full[0]:
+            slim[0][k].copy_(full[0][k])
+    x_p = torch.tensor([1.0, 1.0, 1.0, 1.0 / 50]).repeat(B, 1, 1).contiguous().pin_memory()
+    A_p = torch.ones(B, 1, 1).pin_memory()
+    rng = np.random.RandomState(1)
+    for it in range(4):
+        coin = torch.from_numpy((rng.rand(B) >= 0.5).astype(np.uint8)).pin_memory()
+        rolls[0].step(full[it & 1], coin, x_p, A_p, full[1 - (it & 1)])
+        rolls[1].step(slim[it & 1], coin, x_p, A_p, slim[1 - (it & 1)])
+        torch.cuda.synchronize()
+        for k in slim[1 - (it & 1)]:
+            assert torch.equal(slim[1 - (it & 1)][k], full[1 - (it & 1)][k]), (it, k)
+    up_f, down_f = rolls[0].bytes_per_step()
+    up_s, down_s = rolls[1].bytes_per_step(raw_tables=False)
+    assert up_s == up_f and down_f - down_s == 4 * B * (12 * env.N + 21 * env.E)
