@@ -38,6 +38,8 @@ def check_base(d):
 def test_reference_arm_line():
     d = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-step-seconds", "0.4")
     check_base(d)
+    # the same `config` object as the B200 arm prints (the driver compares them)
+    assert {"workload", "family", "envs_per_gpu", "nodes", "elements", "free_dofs", "l2", "actions", "parallelism"} <= set(d["config"])
     assert d["impl"] == "reference" and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
@@ -58,3 +60,19 @@ def test_b200_arm_line():
     c = d["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(c)
     assert d["status_nonzero_envs"] == 0
+    # round-2 keys: per-rank link rates, the compact-state end-to-end number, the legs at BASELINE configs 3 / 4 shapes
+    assert d["e2e"]["h2d_gbs_per_rank"] > 0 and d["e2e"]["d2h_gbs_per_rank"] > 0
+    assert d["e2e_compact_state"]["d2h_bytes_per_step"] < d["e2e"]["d2h_bytes_per_step"]
+    ex = d["extra"]
+    assert ex["config3"]["family"] == "small_roof" and ex["config3"]["envs_per_gpu"] == 16384 and ex["config3"]["value"] > 0
+    assert ex["config4"]["family"] == "large_bridge" and ex["config4"]["envs_per_gpu"] == 1024
+    assert 0 < ex["config3"]["roofline_fem"]["frac"] < 1 and ex["actor_pareto_P50"]["P"] == 50
+    assert d["config"]["nodes"] == 16 and d["config"]["free_dofs"] == 28
+
+
+@pytest.mark.gpu
+def test_training_leg_line():
+    d = run_bench("--train", "--steps", "3")
+    assert d["family"] == "large_roof" and d["envs_per_gpu"] == 1024 and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["models_identical_across_ranks"] is True and d["learner_update"].startswith("one captured CUDA graph")
+    assert set(d["stages_ms"]) >= {"rollout_3x_act_3x_env_step", "replay_push", "learner_train_update"}
