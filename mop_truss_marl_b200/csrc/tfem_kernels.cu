@@ -136,6 +136,17 @@ __device__ __forceinline__ double pivot_rcp(double a) {
   return fma(x, e, x);
 }
 
+// development ablations (profiles/README.md, round 2: what the solve costs inside the step kernel); results are wrong on purpose
+#ifdef TFEM_ABLATE_FACTOR
+#define ABL_F && j < 1
+#else
+#define ABL_F
+#endif
+#ifdef TFEM_ABLATE_BACKSUB
+#define ABL_B && j > NI - 2
+#else
+#define ABL_B
+#endif
 template <int NX>
 struct Dims {
   static constexpr int N = 2 * NX;
@@ -442,7 +453,7 @@ tfem_step_kernel(const StepArgs args) {
       const int tgt_off = tb * BAND + (ta - tb);
       double* col = Kb;
 #pragma unroll 4
-      for (int j = 0; j < NI; ++j, col += BAND) {
+      for (int j = 0; j < NI ABL_F; ++j, col += BAND) {
         const double inv = pivot_rcp(col[0]);
         const double la = col[ta] * inv;                      // L[j+a][j]
         const double upd = fma(-la, col[tb], col[tgt_off]);
@@ -464,7 +475,7 @@ tfem_step_kernel(const StepArgs args) {
       if (i % BAND) Kb[i] *= dinv[i / BAND];
     __syncwarp();
     // back substitution L^T x = w, column oriented
-    for (int j = NI - 1; j > 0; --j) {
+    for (int j = NI - 1; j > 0 ABL_B; --j) {
       const double xj = z[j];
       const int a = lane + 1;
       if (a <= 7 && j - a >= 0) z[j - a] = fma(-Kb[(j - a) * BAND + a], xj, z[j - a]);
