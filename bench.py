@@ -279,6 +279,22 @@ def _max_over_ranks(ms, dev, world):
     return ms
 
 
+def e2e_piece_schedule(spec, B):
+    """--e2e-pieces: "3" -> 3 equal pieces; "512,1536,2048" -> those sizes; "0.125,0.375,0.5" -> fractions of B rounded to 32"""
+    parts = [p for p in str(spec).split(",") if p]
+    if len(parts) == 1 and "." not in parts[0]:
+        return int(parts[0])
+    vals = [float(p) for p in parts]
+    if all(v < 1 for v in vals):
+        sizes = [max(32, int(round(v * B / 32)) * 32) for v in vals[:-1]]
+        sizes.append(B - sum(sizes))
+    else:
+        sizes = [int(v) for v in vals]
+    if min(sizes) <= 0 or sum(sizes) != B:
+        raise SystemExit("--e2e-pieces %s does not add up to the batch %d" % (spec, B))
+    return sizes
+
+
 def fem_leg(family, B, rank, world, dev, flush, what, steps=50, warmup=5):
     """FEM env-step alone (resident uniform actions, own state fed back) at one of BASELINE.json's named shapes"""
     import torch
@@ -485,7 +501,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-step-seconds", type=float, default=0.0, help="--impl reference: CPU seconds per bench step (default: sized for a ~2 minute run)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    ap.add_argument("--e2e-pieces", type=int, default=2, help="pieces the batch is cut into on the end-to-end path")
+    ap.add_argument("--e2e-pieces", type=str, default="2",
+                    help="end-to-end path: number of equal pieces the batch is cut into, or a comma list of piece sizes "
+                         "(fractions of the batch if they are below 1)")
     ap.add_argument("--no-actor", action="store_true", help="drive the env with resident uniform actions instead of the actor")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (BASELINE configs 3 and 4 shapes, actor at P = 50, training leg)")
     ap.add_argument("--train", action="store_true", help="only the training loop of BASELINE config 5 (large roof, MADDPG update with gradient all-reduce)")
@@ -611,7 +629,7 @@ def main():
         # the caller holds the state tuple on the host (like the reference driver); per step it goes to the
         # device, the actor acts on it, the env steps, and the new state tuple + actions come back
         from mop_truss_marl_b200.host_pipeline import HostRollout, STATE_IN
-        roll = HostRollout(env, pol, pieces=args.e2e_pieces)
+        roll = HostRollout(env, pol, pieces=e2e_piece_schedule(args.e2e_pieces, B))
         bufs = [roll.alloc_host(), roll.alloc_host()]
         for k in STATE_IN:
             bufs[0][k].copy_(getattr(env, k))

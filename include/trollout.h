@@ -66,6 +66,12 @@ const char* trollout_last_error(void);
 int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int pieces, trollout_handle_t* out);
 int trollout_destroy(trollout_handle_t h);
 
+/* Replaces the equal pieces of trollout_create by an explicit schedule: n sizes (environments), multiples of 32 except
+ * the last, adding up to at least max_batch.  A small first piece starts the downloads early -- the device->host leg is
+ * the longest of the three (the child state is twice the parent's live columns) -- while later pieces stay large enough
+ * to fill the GPU.  Drops the step graphs cached so far. */
+int trollout_set_pieces(trollout_handle_t h, const int32_t* sizes, int n);
+
 /* OU-noise parameters as in tactor_act.  Returns after the last piece has landed in the host buffers. */
 int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float mu, float theta, float sigma,
                        uint64_t seed);

@@ -26,7 +26,8 @@ constexpr size_t MAX_GRAPHS = 4, MAX_SEEN = 8;
 struct trollout_handle_s {
   tfem_handle_t env = nullptr;
   tactor_handle_t actor = nullptr;
-  int device = 0, max_batch = 0, piece = 0;
+  int device = 0, max_batch = 0;
+  std::vector<int> piece_len;                      // environments per piece (multiples of 32 but the last), sum >= max_batch
   tfem_dims dims{};
   Dev d;
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -63,6 +64,17 @@ cudaError_t dalloc(trollout_handle_s* h, T** p, size_t count) {
   if (e == cudaSuccess) h->allocs.push_back(*p);
   return e;
 }
+// one (upload done, kernels done) event pair per piece
+cudaError_t piece_events(trollout_handle_s* h, size_t n) {
+  cudaError_t e = cudaSuccess;
+  while (h->ev_in.size() < n && e == cudaSuccess) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+    if (e == cudaSuccess) { h->ev_in.push_back(a); e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming); }
+    if (e == cudaSuccess) h->ev_run.push_back(b);
+  }
+  return e;
+}
 }  // namespace
 
 extern "C" {
@@ -78,7 +90,8 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
   h->env = env; h->actor = actor; h->max_batch = max_batch;
   if (tfem_get_dims(env, &h->dims) != TFEM_OK) { delete h; return rfail(TFEM_ERR_ARG, "bad env handle"); }
   int piece = (max_batch + pieces - 1) / pieces;
-  h->piece = (piece + 31) / 32 * 32;               // piece boundaries on 32 environments: every sub-array stays 16-byte aligned
+  piece = (piece + 31) / 32 * 32;                  // piece boundaries on 32 environments: every sub-array stays 16-byte aligned
+  for (int lo = 0; lo < max_batch; lo += piece) h->piece_len.push_back(piece);
   h->device = h->dims.device;
   if (h->device < 0) { delete h; return rfail(TFEM_ERR_CUDA, "tables-only env handle: libtfem has no CPU path"); }
   int prev_dev = -1;
@@ -116,13 +129,7 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
-  const int npieces = (max_batch + h->piece - 1) / h->piece;
-  for (int i = 0; i < npieces && e == cudaSuccess; ++i) {
-    cudaEvent_t a, b;
-    e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
-    if (e == cudaSuccess) { h->ev_in.push_back(a); e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming); }
-    if (e == cudaSuccess) h->ev_run.push_back(b);
-  }
+  if (e == cudaSuccess) e = piece_events(h, h->piece_len.size());
   if (prev_dev >= 0) cudaSetDevice(prev_dev);
   if (e != cudaSuccess) {
     trollout_destroy(h);
@@ -154,6 +161,25 @@ int trollout_bytes_per_env(trollout_handle_t h, int P, int compact_columns, size
   if (h2d) *h2d = graph + (compact_columns ? cols : tables) + 1 + 4 * ((size_t)P * 4 + (size_t)P * P);
   if (d2h) *d2h = graph + tables + (compact_columns ? cols : 0) + 4 * 4 + 4 + 4 * (N * 2 + N * 3);
   return TFEM_OK;
+}
+
+int trollout_set_pieces(trollout_handle_t h, const int32_t* sizes, int n) {
+  if (!h || !sizes || n < 1 || n > 64) return rfail(TFEM_ERR_ARG, "1..64 piece sizes are required");
+  long long sum = 0;
+  for (int i = 0; i < n; ++i) {
+    if (sizes[i] <= 0 || (i + 1 < n && sizes[i] % 32 != 0))
+      return rfail(TFEM_ERR_ARG, "piece sizes must be positive, and multiples of 32 except the last");
+    sum += sizes[i];
+  }
+  if (sum < h->max_batch) return rfail(TFEM_ERR_ARG, "the piece sizes must add up to max_batch");
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  cudaSetDevice(h->device);
+  const cudaError_t e = piece_events(h, (size_t)n);
+  if (prev_dev >= 0) cudaSetDevice(prev_dev);
+  if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout pieces: ") + cudaGetErrorString(e));
+  h->piece_len.assign(sizes, sizes + n);
+  return trollout_forget_buffers(h);               // the cached graphs were captured with the old boundaries
 }
 
 int trollout_forget_buffers(trollout_handle_t h) {
@@ -190,8 +216,9 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
     cudaEventRecord(h->tl[0], h->s_in);
   }
   int piece_idx = 0;
-  for (int lo = 0; lo < B && e == cudaSuccess; lo += h->piece, ++piece_idx) {
-    const size_t l = (size_t)lo, nb = (size_t)((lo + h->piece <= B) ? h->piece : (B - lo));
+  for (int lo = 0; lo < B && e == cudaSuccess; lo += h->piece_len[piece_idx], ++piece_idx) {
+    const int len = h->piece_len[piece_idx];
+    const size_t l = (size_t)lo, nb = (size_t)((lo + len <= B) ? len : (B - lo));
     // ---- upload ----
     up(d.x_n + l * N * 13, si.x_n + l * N * 13, nb * N * 13 * 4);
     up(d.A_s + l * N * N, si.A_s + l * N * N, nb * N * N * 4);

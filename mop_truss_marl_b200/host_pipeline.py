@@ -21,7 +21,7 @@ STATE_OUT = ("x_n", "A_s", "A_n_ts", "A_n_cs", "nN_x_n", "nN_x_e", "move_range",
 # that carries them uploads 208 instead of 3 792 bytes per small environment for the two raw tables
 COMPACT = ("node_y", "element_section")
 ROLLOUT_EXPORTS = ("trollout_last_error", "trollout_create", "trollout_destroy", "trollout_step_host",
-                   "trollout_bytes_per_env", "trollout_forget_buffers")
+                   "trollout_bytes_per_env", "trollout_forget_buffers", "trollout_set_pieces")
 
 
 class _State(C.Structure):
@@ -41,6 +41,7 @@ _lib.trollout_destroy.argtypes = [C.c_void_p]
 _lib.trollout_step_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(_IO), C.c_float, C.c_float, C.c_float, C.c_uint64]
 _lib.trollout_bytes_per_env.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
 _lib.trollout_forget_buffers.argtypes = [C.c_void_p]
+_lib.trollout_set_pieces.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int]
 
 
 def _check(rc):
@@ -55,16 +56,27 @@ def _hp(t):
 class HostRollout:
     """``env``: BatchedTrussEnv (family, device), ``actor``: BatchedActor on the same device; ``pieces``: how many
     pieces the batch is cut into (each should still fill the GPU: about 148 tiles of 128 actor rows, i.e. ~1000
-    small / ~500 large environments)."""
+    small / ~500 large environments), or a list of piece sizes (multiples of 32 but the last, adding up to the batch):
+    a small first piece starts the downloads -- the longest of the three legs -- early."""
 
-    def __init__(self, env, actor, pieces: int = 2):
+    def __init__(self, env, actor, pieces=2):
         self.env, self.actor = env, actor
         self._h = C.c_void_p()
+        sizes = None if isinstance(pieces, int) else [int(v) for v in pieces]
         with torch.cuda.device(env.device):
-            _check(_lib.trollout_create(env.handle.ptr, actor._h, env.B, int(pieces), C.byref(self._h)))
-        step = -(-env.B // max(1, int(pieces)))
-        step = -(-step // 32) * 32
-        self.ranges = [(lo, min(lo + step, env.B)) for lo in range(0, env.B, step)]
+            _check(_lib.trollout_create(env.handle.ptr, actor._h, env.B, 1 if sizes else int(pieces), C.byref(self._h)))
+        if sizes:
+            if sum(sizes) != env.B:
+                raise ValueError("the piece sizes must add up to the batch (%d)" % env.B)
+            _check(_lib.trollout_set_pieces(self._h, (C.c_int32 * len(sizes))(*sizes), len(sizes)))
+            edges = [0]
+            for v in sizes:
+                edges.append(edges[-1] + v)
+            self.ranges = list(zip(edges[:-1], edges[1:]))
+        else:
+            step = -(-env.B // max(1, int(pieces)))
+            step = -(-step // 32) * 32
+            self.ranges = [(lo, min(lo + step, env.B)) for lo in range(0, env.B, step)]
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -9,7 +9,8 @@ torch = pytest.importorskip("torch")
 
 @pytest.mark.parametrize("family,B,pieces,compact", [("small_bridge", 77, 3, True), ("large_roof", 70, 2, True),
                                                      ("small_roof", 8, 1, True), ("small_bridge", 77, 3, False),
-                                                     ("large_bridge", 40, 2, False)])
+                                                     ("large_bridge", 40, 2, False),
+                                                     ("small_bridge", 300, [32, 192, 76], True)])   # trollout_set_pieces
 def test_host_rollout_equals_resident_path(family, B, pieces, compact):
     """compact: the state tuple carries node_y / element_section (the two table columns _set_model reads) and uploads
     those instead of the full raw tables; without them the full tables go up.  Same bits either way."""
@@ -27,7 +28,8 @@ def test_host_rollout_equals_resident_path(family, B, pieces, compact):
     A_p = torch.rand(B, 2, 2, device=dev, generator=g)
     x_p_host, A_p_host = x_p.cpu().pin_memory(), A_p.cpu().pin_memory()
     roll = HostRollout(envs[1], pols[1], pieces=pieces)
-    assert len(roll.ranges) == pieces and roll.ranges[0][0] == 0 and roll.ranges[-1][1] == B
+    assert len(roll.ranges) == (pieces if isinstance(pieces, int) else len(pieces))
+    assert roll.ranges[0][0] == 0 and roll.ranges[-1][1] == B
     bufs = [roll.alloc_host(compact), roll.alloc_host(compact)]
     for k in STATE_IN:
         bufs[0][k].copy_(getattr(envs[1], k))
