@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -52,6 +53,10 @@ struct trollout_handle_s {
   bool use_graph = true;
   bool timeline = false;                           // TROLLOUT_TIMELINE=1: print per-piece event times (direct path)
   std::vector<cudaEvent_t> tl;
+  // TROLLOUT_HOSTTIME=1: host-side time of the graph path, printed by trollout_destroy: [checks + key, graph launch, wait]
+  bool hosttime = false;
+  double host_ns[3] = {0, 0, 0};
+  long host_steps = 0;
 };
 
 namespace {
@@ -125,6 +130,7 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->h_ctr), 16, cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (const char* v = getenv("TROLLOUT_NO_GRAPH")) h->use_graph = (v[0] == '0');
+  if (const char* v = getenv("TROLLOUT_HOSTTIME")) h->hosttime = (v[0] == '1');
   if (const char* v = getenv("TROLLOUT_TIMELINE")) { h->timeline = (v[0] == '1'); if (h->timeline) h->use_graph = false; }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking);
@@ -141,6 +147,10 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
 
 int trollout_destroy(trollout_handle_t h) {
   if (!h) return TFEM_OK;
+  if (h->hosttime && h->host_steps)
+    fprintf(stderr, "[trollout host time, us per replayed step over %ld steps] checks %.1f | cudaGraphLaunch %.1f | wait %.1f\n",
+            h->host_steps, h->host_ns[0] / h->host_steps * 1e-3, h->host_ns[1] / h->host_steps * 1e-3,
+            h->host_ns[2] / h->host_steps * 1e-3);
   for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -322,6 +332,7 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
                         io->n_pf, so.x_n, so.A_s, so.A_n_ts, so.A_n_cs, so.nN_x_n, so.nN_x_e, so.move_range, so.node_y,
                         so.element_section, io->point, io->status, io->a_geo, io->a_topo};
   const bool noise = !(sigma == 0.f && theta == 0.f);
+  const auto t_begin = std::chrono::steady_clock::now();
   if (h->use_graph) {
     std::vector<uintptr_t> key;
     for (const void* p : ptrs) key.push_back(reinterpret_cast<uintptr_t>(p));
@@ -386,8 +397,17 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
       h->h_ctr[0] = seed;
       h->h_ctr[1] = tactor_reserve_calls(h->actor, noise ? (uint32_t)hit->pieces : 0u, hit->actor_launches);
       tfem_book_launches(h->env, hit->env_launches);
+      const auto t_launch = std::chrono::steady_clock::now();
       e = cudaGraphLaunch(hit->exec, h->s_in);
+      const auto t_wait = std::chrono::steady_clock::now();
       if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_in);
+      if (h->hosttime) {
+        const auto t_end = std::chrono::steady_clock::now();
+        h->host_ns[0] += std::chrono::duration<double, std::nano>(t_launch - t_begin).count();
+        h->host_ns[1] += std::chrono::duration<double, std::nano>(t_wait - t_launch).count();
+        h->host_ns[2] += std::chrono::duration<double, std::nano>(t_end - t_wait).count();
+        ++h->host_steps;
+      }
       if (e != cudaSuccess) return rfail(TFEM_ERR_CUDA, std::string("rollout step: ") + cudaGetErrorString(e));
       return TFEM_OK;
     }
