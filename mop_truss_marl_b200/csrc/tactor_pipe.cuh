@@ -36,6 +36,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "tactor_tc.cuh"
 
 namespace tactor {
@@ -289,7 +291,12 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       PROF_WAIT(0, ok = mbar_wait(x_full + 8 * (it & 1), (uint32_t)((it >> 1) & 1)) && ok);
       const float* Xraw = Xr2 + (it & 1) * TCM * 13;
       const float* Pl = Pl2 + (it & 1) * ENVS * 208;
-      if (32 * q >= rows_here) {
+      // HALF-LIVE piece (16-node graphs, a tile of the last wave cut in two): its four environments sit one per 32-row
+      // group (tile rows 32 e .. 32 e + 15 = environment e), so that every generator warp carries 16 rows -- half of a full
+      // tile's tensor-core and conversion work per chunk -- instead of two warps carrying 32 and two idling: the piece's
+      // chunks are then paced by the tcgen05 MMAs rather than by the generators
+      const bool hl = (NODES == 16) && P.split_f == 2 && item >= P.split_from;
+      if (!hl && 32 * q >= rows_here) {
         // dead row group of a split tile: keep the barrier protocol going, produce nothing (the tensor core reads
         // whatever these TMEM lanes hold; rows are independent and the epilogue never looks at them)
         for (int uu = 0; uu < NGEMM * NCH; ++uu) {
@@ -307,6 +314,10 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       // The warp's 32 rows are two 16-row blocks mt = 0, 1.  NODES = 16: block mt is environment 2q + mt and mixes with
       // itself only (KB = 1); NODES = 32: both blocks belong to environment q and every (mt, kb) pair of 16 x 16 sub-blocks of
       // the adjacency matrix takes part.  kr(mt, kb) = the 16-row block of the warp that holds the k rows of the pair.
+      // HL (half-live piece, see above): block 0 only, environment q.
+      auto item_body = [&](auto hl_tag) {
+      constexpr bool HL = decltype(hl_tag)::value;
+      constexpr int MT = HL ? 1 : 2;                           // live 16-row blocks of the warp
       auto kr_of = [](int mt, int kb) { return NODES == 16 ? mt : kb; };
       // the 16 x 16 block (rows nb.., columns 16 kb..) of a row-major [N][N] matrix in global memory, as the four float2 of this
       // lane's A fragment
@@ -340,8 +351,8 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       auto fetch_adj = [&](int g) {
         const float* t = adj_tensor(g);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          int env = env0 + (32 * q + 16 * mt) / NODES;       // clamped into the batch (rows past the batch are never written)
+        for (int mt = 0; mt < MT; ++mt) {
+          int env = env0 + (HL ? q : (32 * q + 16 * mt) / NODES);   // clamped into the batch (rows past the batch are never written)
           env = env * NODES < M ? env : (M / NODES - 1);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) adj_load(t + (size_t)env * NODES * NODES, mt, kb, araw[mt][kb]);
@@ -352,7 +363,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
       //      zfr[8-row block of the warp][hi | lo][c 0..7 | c 8..15 (c = 13: the constant 1 that multiplies the bias row)] ----
       uint32_t zfr[4][2][2];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         float z[2][4];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) z[nt][0] = z[nt][1] = z[nt][2] = z[nt][3] = 0.f;
@@ -360,7 +371,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         for (int kb = 0; kb < KB; ++kb) {
           uint32_t ahi[4], alo[4];
           an_frag(mt, kb, ahi, alo);
-          const float* xr = Xraw + (32 * q + 16 * kr_of(mt, kb) + 2 * t4) * 13;
+          const float* xr = Xraw + ((HL ? 16 : 32) * q + 16 * kr_of(mt, kb) + 2 * t4) * 13;   // rows of the staged block (contiguous from row0)
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt) {
             const int c = 8 * nt + g8;
@@ -403,13 +414,13 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
         // ---- per-GEMM setup: adjacency fragments; pull the next GEMM's rows towards the SM ----
         if (g == 1 || g == 2 || g == 3 || g == 6) {
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) adj_split(araw[mt][kb], afr[mt][kb][0], afr[mt][kb][1]);
           if (g < 6) fetch_adj(g < 3 ? g + 1 : 6);
         } else {
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) an_frag(mt, kb, afr[mt][kb][0], afr[mt][kb][1]);
         }
@@ -445,7 +456,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
             const uint4 wl = *reinterpret_cast<const uint4*>(w1f + ((c * 2 + 1) * 32 + lane) * 4);
             const uint32_t whi[4] = {wh.x, wh.y, wh.z, wh.w}, wlo[4] = {wl.x, wl.y, wl.z, wl.w};
 #pragma unroll
-            for (int ntr = 0; ntr < 4; ++ntr) {
+            for (int ntr = 0; ntr < 2 * MT; ++ntr) {
               float xt[4] = {0.f, 0.f, 0.f, 0.f};
               hmma_split(xt, whi, wlo, zfr[ntr][0], zfr[ntr][1]);
 #pragma unroll
@@ -455,7 +466,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
             }
           } else {
 #pragma unroll
-            for (int kr = 0; kr < 2; ++kr)
+            for (int kr = 0; kr < MT; ++kr)
 #pragma unroll
               for (int nt = 0; nt < 2; ++nt) {
                 const int feat = k0 + 8 * nt + g8;
@@ -468,7 +479,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
                       const int r = 32 * q + 16 * kr + 8 * b + 2 * t4 + i;
                       if (g == 4) {
                         // the reference's stack-and-reshape scramble: x14b[b,n,h] = pooled[b,(n*200+h)/N] (truss2D_RL.py:89-95)
-                        v[b][i] = (NREAL == NODES || (r % NODES) < NREAL) ? Pl[(r / NODES) * 208 + ((r % NODES) * KH + feat) / NREAL] : 0.f;   // (padding rows of a 12-in-16 graph: 0)
+                        v[b][i] = (NREAL == NODES || (r % NODES) < NREAL) ? Pl[(HL ? q : r / NODES) * 208 + ((r % NODES) * KH + feat) / NREAL] : 0.f;   // (padding rows of a 12-in-16 graph: 0)
                       } else {
                         v[b][i] = H[r * LDH + feat];             // layer 3: rows of the five-way sum
                       }
@@ -485,7 +496,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           // ---- Y = A_g . X on the tensor core, split, store from the accumulator layout ----
           uint32_t oh[2][4], ol[2][4];
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
+          for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
               float y[4] = {0.f, 0.f, 0.f, 0.f};
@@ -505,7 +516,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           if (u >= PAST) PROF_WAIT(2, ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok);        // chunk u-PAST consumed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
+          for (int mt = 0; mt < MT; ++mt) {
             const uint32_t lane_sel = (uint32_t)(32 * q + 16 * mt) << 16;
             tmem_st_16x128b_x2(tmem_base + lane_sel + (uint32_t)(TM_AHI + ACOLS * sa), oh[mt]);
             tmem_st_16x128b_x2(tmem_base + lane_sel + (uint32_t)(TM_ALO + ACOLS * sa), ol[mt]);
@@ -517,6 +528,13 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           if (c < NPH) hand_off();
         }
         hand_off();                                            // the accumulator of this GEMM must not wait for the next one
+      }
+      };  // item_body
+      if constexpr (NODES == 16) {
+        if (hl) item_body(std::true_type{});
+        else item_body(std::false_type{});
+      } else {
+        item_body(std::false_type{});
       }
     }  // items
     if (bad && P.error_flag) atomicOr(P.error_flag, 2);        // an input left the fp16 range (or NaN)
@@ -535,7 +553,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
     for (int item = blockIdx.x, it = 0; item < P.n_items; item += gridDim.x, ++it) {
       int row0, rows_here;
       item_rows(item, row0, rows_here);
-      const bool live = 32 * q < rows_here;                    // dead row group of a split tile: barriers only
+      const bool hl = (NODES == 16) && P.split_f == 2 && item >= P.split_from;   // half-live piece: lanes 0..15 of every row group
+      const bool live = hl || 32 * q < rows_here;              // dead row group of a split tile: barriers only
+      const float nonfinite_in = nonfinite;
       for (int g = 0; g < NGEMM; ++g) {
         const int G = it * NGEMM + g, b = G & 1;               // GEMM counter across items: accumulator and parity
         PROF_WAIT(0, ok = mbar_wait(acc_full + 8 * b, (uint32_t)((G >> 1) & 1)) && ok);
@@ -620,8 +640,8 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
             o[0] = fmaf(a, uj.x, o[0]); o[1] = fmaf(a, uj.y, o[1]); o[2] = fmaf(a, uj.z, o[2]);
           }
           __syncwarp();
-          const int row = row0 + r;
-          if (row < M && (NREAL == NODES || n < NREAL)) {      // padding rows of a 12-in-16 graph are not outputs
+          const int row = row0 + (hl ? 16 * q + lane : r);
+          if (row < M && (!hl || lane < 16) && (NREAL == NODES || n < NREAL)) {      // padding rows of a 12-in-16 graph are not outputs
             const size_t orow = (NREAL == NODES) ? (size_t)row : (size_t)(row / NODES) * NREAL + n;
             float* dst = (hd == 0 ? P.geo : P.topo) + orow * nout;
             uint64_t seed = P.seed, call = P.call;
@@ -634,6 +654,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           }
         }
       }
+      if (hl && lane >= 16) nonfinite = nonfinite_in;          // the dead lanes of a half-live piece multiply whatever their TMEM rows hold
     }  // items
     if (!(nonfinite == 0.f) && P.error_flag) atomicOr(P.error_flag, 2);   // an activation left the fp16 range (or NaN)
   } else if (warp == W_ISSUER) {
