@@ -281,6 +281,8 @@ def _max_over_ranks(ms, dev, world):
 
 def e2e_piece_schedule(spec, B):
     """--e2e-pieces: "3" -> 3 equal pieces; "512,1536,2048" -> those sizes; "0.125,0.375,0.5" -> fractions of B rounded to 32"""
+    if str(spec) == "auto":
+        return "auto"
     parts = [p for p in str(spec).split(",") if p]
     if len(parts) == 1 and "." not in parts[0]:
         return int(parts[0])
@@ -501,9 +503,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-step-seconds", type=float, default=0.0, help="--impl reference: CPU seconds per bench step (default: sized for a ~2 minute run)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    ap.add_argument("--e2e-pieces", type=str, default="2",
-                    help="end-to-end path: number of equal pieces the batch is cut into, or a comma list of piece sizes "
-                         "(fractions of the batch if they are below 1)")
+    ap.add_argument("--e2e-pieces", type=str, default="auto",
+                    help="end-to-end path: 'auto' (HostRollout's choice: ~5.7 MB of download per piece), the number of equal "
+                         "pieces the batch is cut into, or a comma list of piece sizes (fractions of the batch if below 1)")
     ap.add_argument("--no-actor", action="store_true", help="drive the env with resident uniform actions instead of the actor")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (BASELINE configs 3 and 4 shapes, actor at P = 50, training leg)")
     ap.add_argument("--train", action="store_true", help="only the training loop of BASELINE config 5 (large roof, MADDPG update with gradient all-reduce)")
@@ -645,7 +647,9 @@ def main():
             flip[0] = 1 - flip[0]
         h2d, d2h = roll.bytes_per_step()
         e2e_path = ("pinned host state tuple + Pareto graph -> device -> tactor_act + tfem_step -> host (state tuple, point, "
-                    "status, actions); trollout_step_host (host_pipeline.HostRollout), %d pieces on 3 streams" % len(roll.ranges))
+                    "status, actions); trollout_step_host (host_pipeline.HostRollout), %d pieces on 3 streams, %s" % (
+                        len(roll.ranges), "copy engines" if os.environ.get("TROLLOUT_ZEROCOPY", "1") == "0" else
+                        "one transfer kernel per piece and direction reading / writing the mapped pinned host arrays"))
     else:
         host = {
             "set_node": env.nN_x_n.cpu().pin_memory(), "set_element": env.nN_x_e.cpu().pin_memory(),

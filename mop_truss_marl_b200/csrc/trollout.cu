@@ -21,6 +21,51 @@ struct Dev {
   uint8_t* coin = nullptr;
 };
 constexpr int PMAX = 50;
+
+// Captured (pinned + mapped) steps move the arrays of a piece across the link with ONE kernel per direction that reads / writes
+// the mapped host memory directly, instead of one DMA copy per array: 11 up + 13 down per piece, each with a few microseconds
+// of fixed cost on its copy engine -- which is what made more than two pieces a loss.  TROLLOUT_ZEROCOPY=0 goes back to the
+// copy engines (2: kernel for the download only, 3: for the upload only); TROLLOUT_ZC_UP / TROLLOUT_ZC_DOWN: CTAs of the two
+// kernels (32 each: enough requests in flight for the link, few enough SMs taken from the actor and the env-step).
+constexpr int COPY_MAX = 16;
+struct CopyList {
+  void* dst[COPY_MAX];
+  const void* src[COPY_MAX];
+  unsigned long long end16[COPY_MAX];       // running total of 16-byte units up to and including array i
+  unsigned int bytes[COPY_MAX];             // bytes of array i (the tail below 16 bytes is copied bytewise)
+  int n;
+};
+__global__ void __launch_bounds__(256) copy_arrays_kernel(const __grid_constant__ CopyList L) {
+  const unsigned long long total = L.n ? L.end16[L.n - 1] : 0ull;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  // four independent 16-byte loads per thread in flight before the first store (reads of host memory have microseconds of latency)
+  for (unsigned long long u0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u0 < total; u0 += 4 * stride) {
+    uint4 v[4];
+    uint4* out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned long long u = u0 + i * stride;
+      out[i] = nullptr;
+      if (u < total) {
+        int a = 0;
+        while (u >= L.end16[a]) ++a;
+        const unsigned long long k = u - (a ? L.end16[a - 1] : 0ull);
+        v[i] = reinterpret_cast<const uint4*>(L.src[a])[k];
+        out[i] = reinterpret_cast<uint4*>(L.dst[a]) + k;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (out[i]) *out[i] = v[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 16 * COPY_MAX) {                  // byte tails
+    const int a = threadIdx.x >> 4, j = threadIdx.x & 15;
+    if (a < L.n) {
+      const unsigned int full = L.bytes[a] & ~15u;
+      if (full + j < L.bytes[a]) reinterpret_cast<unsigned char*>(L.dst[a])[full + j] = reinterpret_cast<const unsigned char*>(L.src[a])[full + j];
+    }
+  }
+}
 constexpr size_t MAX_GRAPHS = 4, MAX_SEEN = 8;
 }  // namespace
 
@@ -54,6 +99,10 @@ struct trollout_handle_s {
   bool timeline = false;                           // TROLLOUT_TIMELINE=1: print per-piece event times (direct path)
   std::vector<cudaEvent_t> tl;
   // TROLLOUT_HOSTTIME=1: host-side time of the graph path, printed by trollout_destroy: [checks + key, graph launch, wait]
+  bool zerocopy = true;                            // TROLLOUT_ZEROCOPY=0 turns it off
+  bool zc_capture = false;                         // the step being captured: every host buffer is mapped at its own address
+  int zc_up = 32, zc_down = 32;                    // CTAs of the copy kernels (TROLLOUT_ZC_UP / TROLLOUT_ZC_DOWN); mode 2: download only, 3: upload only
+  int zc_mode = 1;
   bool hosttime = false;
   double host_ns[3] = {0, 0, 0};
   long host_steps = 0;
@@ -130,6 +179,9 @@ int trollout_create(tfem_handle_t env, tactor_handle_t actor, int max_batch, int
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->h_ctr), 16, cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (const char* v = getenv("TROLLOUT_NO_GRAPH")) h->use_graph = (v[0] == '0');
+  if (const char* v = getenv("TROLLOUT_ZEROCOPY")) { h->zc_mode = atoi(v); h->zerocopy = h->zc_mode >= 1; }
+  if (const char* v = getenv("TROLLOUT_ZC_UP")) { h->zc_up = atoi(v); if (h->zc_up < 1) h->zc_up = 1; }
+  if (const char* v = getenv("TROLLOUT_ZC_DOWN")) { h->zc_down = atoi(v); if (h->zc_down < 1) h->zc_down = 1; }
   if (const char* v = getenv("TROLLOUT_HOSTTIME")) h->hosttime = (v[0] == '1');
   if (const char* v = getenv("TROLLOUT_TIMELINE")) { h->timeline = (v[0] == '1'); if (h->timeline) h->use_graph = false; }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
@@ -213,13 +265,41 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
   // a failure in the middle of a step must not return while copies issued for earlier pieces still touch the
   // caller's host buffers
   auto drain = [&]() { cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_run); cudaStreamSynchronize(h->s_out); };
+  // zero-copy path: only for the captured (all-pinned) step
+  const bool zc = h->zerocopy && ctr_dev != nullptr && h->zc_capture;
+  CopyList ups{}, downs{};
+  auto add = [&](CopyList& L, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return;
+    if (L.n >= COPY_MAX || (reinterpret_cast<uintptr_t>(dst) & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || bytes > 0xffffffffull) {
+      e = cudaErrorInvalidValue;
+      return;
+    }
+    L.dst[L.n] = dst; L.src[L.n] = src; L.bytes[L.n] = (unsigned int)bytes;
+    L.end16[L.n] = (L.n ? L.end16[L.n - 1] : 0ull) + bytes / 16;
+    ++L.n;
+  };
+  const bool zc_u = zc && h->zc_mode != 2, zc_d = zc && h->zc_mode != 3;
+  auto flush = [&](CopyList& L, cudaStream_t st) {
+    if (e == cudaSuccess && L.n) {
+      copy_arrays_kernel<<<(st == h->s_in) ? h->zc_up : h->zc_down, 256, 0, st>>>(L);
+      e = cudaGetLastError();
+    }
+    L.n = 0;
+  };
   auto up = [&](void* dst, const void* src, size_t bytes) {
-    if (e == cudaSuccess && src) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->s_in);
+    if (e != cudaSuccess || !src) return;
+    if (zc_u) add(ups, dst, src, bytes);
+    else e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->s_in);
   };
   auto down = [&](void* dst, const void* src, size_t bytes) {
-    if (e == cudaSuccess && dst) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->s_out);
+    if (e != cudaSuccess || !dst) return;
+    if (zc_d) add(downs, dst, src, bytes);
+    else e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->s_out);
   };
-  if (ctr_dev) up(h->d_ctr, h->h_ctr, 16);
+  if (ctr_dev) {
+    up(h->d_ctr, h->h_ctr, 16);
+    flush(ups, h->s_in);
+  }
   if (h->timeline && !ctr_dev) {
     const size_t need = 1 + 4 * h->ev_in.size();
     while (h->tl.size() < need) { cudaEvent_t ev; cudaEventCreate(&ev); h->tl.push_back(ev); }
@@ -246,6 +326,7 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
     up(d.A_p + l * P * P, io->A_p + l * P * P, nb * P * P * 4);
     if (io->coin) up(d.coin + l, io->coin + l, nb);
     if (io->n_pf) up(d.n_pf + l, io->n_pf + l, nb * 4);
+    flush(ups, h->s_in);
     if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[piece_idx], h->s_in);
     if (h->timeline && !ctr_dev) cudaEventRecord(h->tl[1 + 4 * piece_idx + 0], h->s_in);
     // ---- act + step ----
@@ -288,6 +369,7 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
     down(io->status ? io->status + l : nullptr, d.status + l, nb * 4);
     down(io->a_geo ? io->a_geo + l * N * 2 : nullptr, d.a_geo + l * N * 2, nb * N * 2 * 4);
     down(io->a_topo ? io->a_topo + l * N * 3 : nullptr, d.a_topo + l * N * 3, nb * N * 3 * 4);
+    flush(downs, h->s_out);
     if (h->timeline && !ctr_dev) cudaEventRecord(h->tl[1 + 4 * piece_idx + 2], h->s_out);
   }
   if (join) {
@@ -302,10 +384,11 @@ static int enqueue_step(trollout_handle_s* h, int B, const trollout_io* io, floa
   return TFEM_OK;
 }
 
-static bool pinned(const void* p) {
+static bool pinned(const void* p, bool* mapped = nullptr) {
   if (!p) return true;
   cudaPointerAttributes a{};
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (mapped && a.devicePointer != p) *mapped = false;   // unified addressing: a kernel can use the host address as it is
   return a.type == cudaMemoryTypeHost;
 }
 
@@ -349,9 +432,11 @@ int trollout_step_host(trollout_handle_t h, int B, const trollout_io* io, float 
         if (h->seen_once.size() >= MAX_SEEN) h->seen_once.erase(h->seen_once.begin());
         h->seen_once.push_back(key);
       } else {
-        bool all_pinned = true;
-        for (const void* p : ptrs) all_pinned = all_pinned && pinned(p);
+        bool all_pinned = true, all_mapped = true;
+        for (const void* p : ptrs) all_pinned = all_pinned && pinned(p, &all_mapped);
+        all_mapped = all_mapped && pinned(h->h_ctr, &all_mapped);
         if (all_pinned) {
+          h->zc_capture = all_mapped;
           trollout_handle_s::Graph ng;
           const int64_t env0 = tfem_launch_count(h->env), act0 = tactor_launch_count(h->actor);
           e = cudaStreamBeginCapture(h->s_in, cudaStreamCaptureModeRelaxed);

@@ -10,6 +10,7 @@ and piece i-1 downloads (PCIe is full duplex).  PyTorch only provides the pinned
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -57,14 +58,31 @@ class HostRollout:
     """``env``: BatchedTrussEnv (family, device), ``actor``: BatchedActor on the same device; ``pieces``: how many
     pieces the batch is cut into (each should still fill the GPU: about 148 tiles of 128 actor rows, i.e. ~1000
     small / ~500 large environments), or a list of piece sizes (multiples of 32 but the last, adding up to the batch):
-    a small first piece starts the downloads -- the longest of the three legs -- early."""
+    a small first piece starts the downloads -- the longest of the three legs -- early.  ``"auto"`` (default): about 5.7 MB of
+    download per piece, at most 8 pieces -- the optimum measured with the zero-copy transfer kernels of the captured step
+    (6 pieces for 4096 small bridges; ``profiles/README.md``); 2 when ``TROLLOUT_ZEROCOPY=0`` sends every array through the
+    copy engines, whose per-copy cost makes more pieces a loss."""
 
-    def __init__(self, env, actor, pieces=2):
+    def __init__(self, env, actor, pieces="auto"):
         self.env, self.actor = env, actor
         self._h = C.c_void_p()
-        sizes = None if isinstance(pieces, int) else [int(v) for v in pieces]
+        auto = isinstance(pieces, str)
+        if auto and pieces != "auto":
+            raise ValueError("pieces: an int, a list of sizes or 'auto'")
+        sizes = None if (auto or isinstance(pieces, int)) else [int(v) for v in pieces]
         with torch.cuda.device(env.device):
-            _check(_lib.trollout_create(env.handle.ptr, actor._h, env.B, 1 if sizes else int(pieces), C.byref(self._h)))
+            _check(_lib.trollout_create(env.handle.ptr, actor._h, env.B, 1 if (sizes or auto) else int(pieces), C.byref(self._h)))
+        if auto:
+            pieces = 2
+            if os.environ.get("TROLLOUT_ZEROCOPY", "1") != "0":
+                down = C.c_size_t()
+                _check(_lib.trollout_bytes_per_env(self._h, 1, 1, None, C.byref(down)))
+                pieces = max(1, min(8, int(round(env.B * down.value / 5.7e6))))
+            pieces = max(1, min(pieces, env.B // 128)) if env.B >= 128 else 1
+            step = -(-(-(-env.B // pieces)) // 32) * 32
+            sizes = []
+            while sum(sizes) < env.B:
+                sizes.append(min(step, env.B - sum(sizes)))
         if sizes:
             if sum(sizes) != env.B:
                 raise ValueError("the piece sizes must add up to the batch (%d)" % env.B)
