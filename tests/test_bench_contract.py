@@ -76,3 +76,15 @@ def test_training_leg_line():
     assert d["family"] == "large_roof" and d["envs_per_gpu"] == 1024 and d["value"] > 0 and d["n_gpus"] == 1
     assert d["models_identical_across_ranks"] is True and d["learner_update"].startswith("one captured CUDA graph")
     assert set(d["stages_ms"]) >= {"rollout_3x_act_3x_env_step", "replay_push", "learner_train_update"}
+
+
+def test_e2e_piece_schedule_argument():
+    """--e2e-pieces: 'auto' (HostRollout decides), a count of equal pieces, explicit sizes, or fractions of the batch"""
+    import bench
+    assert bench.e2e_piece_schedule("auto", 4096) == "auto"
+    assert bench.e2e_piece_schedule("3", 4096) == 3
+    assert bench.e2e_piece_schedule("512,1536,2048", 4096) == [512, 1536, 2048]
+    frac = bench.e2e_piece_schedule("0.125,0.375,0.5", 4096)
+    assert frac == [512, 1536, 2048] and all(v % 32 == 0 for v in frac[:-1])
+    with pytest.raises(SystemExit):
+        bench.e2e_piece_schedule("512,512", 4096)
