@@ -491,36 +491,9 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           }
           PROF_ADD(5, PROF_NOW() - prof_t1);
           if (it == 1) PROF_TRACE((warp * 48 + prof_v) * 4 + 1, PROF_NOW());
-#ifndef TACTOR_LATE_HANDOFF
           hand_off();                                          // publish the previous chunk's stage
-#endif
           const long long prof_t2 = PROF_NOW();
           // ---- Y = A_g . X on the tensor core, split, store from the accumulator layout ----
-#ifdef TACTOR_LATE_HANDOFF
-          uint32_t oh[2][4], ol[2][4];
-          float yy[2][2][4];
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              yy[mt][nt][0] = yy[mt][nt][1] = yy[mt][nt][2] = yy[mt][nt][3] = 0.f;
-#pragma unroll
-              for (int kb = 0; kb < KB; ++kb) {
-                const int kr = kr_of(mt, kb);
-                hmma_split(yy[mt][nt], afr[mt][kb][0], afr[mt][kb][1], xb[kr][nt][0], xb[kr][nt][1]);
-              }
-            }
-          hand_off();
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              float* y = yy[mt][nt];
-              if (k0 + 8 * nt == KH && t4 == 0) { y[0] = 1.f; y[2] = 1.f; }
-              split2(y[0], y[1], oh[mt][2 * nt], ol[mt][2 * nt]);
-              split2(y[2], y[3], oh[mt][2 * nt + 1], ol[mt][2 * nt + 1]);
-            }
-#else
           uint32_t oh[2][4], ol[2][4];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
@@ -538,7 +511,6 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
               split2(y[0], y[1], oh[mt][2 * nt], ol[mt][2 * nt]);              // lane g8,     column 4 nt + t4
               split2(y[2], y[3], oh[mt][2 * nt + 1], ol[mt][2 * nt + 1]);      // lane g8 + 8, column 4 nt + t4
             }
-#endif
           PROF_ADD(6, PROF_NOW() - prof_t2);
           if (it == 1) PROF_TRACE((warp * 48 + prof_v) * 4 + 2, PROF_NOW());
           if (u >= PAST) PROF_WAIT(2, ok = mbar_wait(a_empty + 8 * sa, ((u / PAST) - 1) & 1) && ok);        // chunk u-PAST consumed
@@ -719,13 +691,7 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
               const uint32_t a_hi = tmem_base + (uint32_t)TM_AHI + (uint32_t)ACOLS * sa, a_lo = tmem_base + (uint32_t)TM_ALO + (uint32_t)ACOLS * sa;
               const uint64_t d_hi = d_hi0 + D_STAGE * sw, d_lo = d_hi + D_LO;
               mma_split<NCTA>(dacc, a_hi, d_hi, c != 0);       // Yhi.Whi + Yhi.Wlo + Ylo.Whi (the tail chunk is zero-padded)
-#ifdef TACTOR_MMA_GAP
-              { const long long t_ = clock64(); while (clock64() - t_ < TACTOR_MMA_GAP) { } }
-#endif
               mma_split<NCTA>(dacc, a_hi, d_lo, 1);
-#ifdef TACTOR_MMA_GAP
-              { const long long t_ = clock64(); while (clock64() - t_ < TACTOR_MMA_GAP) { } }
-#endif
               mma_split<NCTA>(dacc, a_lo, d_hi, 1);
               mma_commit<NCTA>(w_empty + 8 * sw);
               mma_commit<NCTA>(a_empty + 8 * sa);
