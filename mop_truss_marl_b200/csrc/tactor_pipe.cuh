@@ -588,14 +588,16 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
           // accumulator entry here, before the ReLU can hide it: one FFMA per entry instead of range tracking in the generators
 #pragma unroll
           for (int t = 0; t < 8; ++t) nonfinite = fmaf(v[t], 0.f, nonfinite);
-#pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t] * wsi, 0.f);   // the bias rode along as row 200 of the W image
+          // relu(D / S) with the bias riding along as row 200 of the W image; 1/S is a power of two, so relu(D) (1/S) + H in one
+          // FFMA gives the bits of relu(D / S) + H
           if (g <= 4) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
             float4* dst = reinterpret_cast<float4*>(hrow + 8 * CBS * i);
             float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
             if (g > 0) { o0 = dst[0]; o1 = dst[1]; }
-            dst[0] = make_float4(v[0] + o0.x, v[1] + o0.y, v[2] + o0.z, v[3] + o0.w);
-            dst[1] = make_float4(v[4] + o1.x, v[5] + o1.y, v[6] + o1.z, v[7] + o1.w);
+            dst[0] = make_float4(fmaf(v[0], wsi, o0.x), fmaf(v[1], wsi, o0.y), fmaf(v[2], wsi, o0.z), fmaf(v[3], wsi, o0.w));
+            dst[1] = make_float4(fmaf(v[4], wsi, o1.x), fmaf(v[5], wsi, o1.y), fmaf(v[6], wsi, o1.z), fmaf(v[7], wsi, o1.w));
             if (g == 4) {                                      // H is complete in these 8 columns of this warp's rows
               __threadfence_block();
               __syncwarp();
@@ -605,6 +607,8 @@ actor_pipe_kernel(const __grid_constant__ Params P) {
               }
             }
           } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t] * wsi, 0.f);
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
               const float4 w = *reinterpret_cast<const float4*>(wh + (8 * (cb0 + CBS * i) + t) * 4);
