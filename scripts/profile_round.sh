@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 CMD="python bench.py --steps 4 --warmup 3 --cpu-seconds 0.1 --no-extras"
 $CMD > gpurun_out/r2_plain_bench.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 60 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/r2_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/r2_ncu_launches.log 2>&1
 echo launches rc=$?
 ncu --set full --clock-control none --import-source on -k regex:actor_pipe -s 4 -c 1 -f -o gpurun_out/r2_prof_actor $CMD > gpurun_out/r2_ncu_actor.log 2>&1
 echo actor rc=$?
