@@ -13,6 +13,12 @@
  * time a set of buffer addresses is seen and replayed afterwards (four graphs are kept: a driver that ping-pongs two
  * state tuples alternates between two of them); replayed steps give the bits of directly enqueued ones, OU noise
  * included.  TROLLOUT_NO_GRAPH=1 disables the graphs, TROLLOUT_TIMELINE=1 prints a per-piece event timeline to stderr.
+ *
+ * In a captured step the arrays of a piece cross the link through ONE transfer kernel per direction that reads / writes the
+ * pinned host arrays at their mapped addresses (unified addressing, verified per buffer; otherwise, on the uncaptured path
+ * and with TROLLOUT_ZEROCOPY=0 every array is a cudaMemcpyAsync on a copy engine).  Same bytes over the link, but none of
+ * the per-copy cost of the 11 + 13 arrays of a piece, so the batch can be cut finer (trollout_set_pieces).
+ * TROLLOUT_HOSTTIME=1 prints the host-side share of the replayed steps (checks, cudaGraphLaunch, wait) at destroy time.
  */
 #ifndef TROLLOUT_H_
 #define TROLLOUT_H_
