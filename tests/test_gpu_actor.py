@@ -147,11 +147,14 @@ def test_set_weights_and_learner_round_trip():
     a.check()
 
 
-@pytest.mark.parametrize("nodes,B", [(16, 300), (16, 100), (32, 150), (16, 2400), (32, 1300)])
+@pytest.mark.parametrize("nodes,B", [(16, 300), (16, 100), (32, 150), (16, 2400), (32, 1300), (16, 1600), (16, 1590)])
 def test_last_wave_split_is_bit_identical(nodes, B, monkeypatch):
     """tiles of the last partial wave are cut into 2 or 4 row pieces, and with more work items than SMs the kernel is
     persistent (a CTA walks several items with running barrier counters); rows are independent, so the outputs must
-    equal those of the plain one-CTA-per-tile launch (TACTOR_NO_SPLIT=1) bit for bit.  B = 2400 / 1300: 312 / 412 items"""
+    equal those of the plain one-CTA-per-tile launch (TACTOR_NO_SPLIT=1) bit for bit.  B = 2400 / 1300: 312 / 412 items;
+    B = 300: two-way pieces of 16-node graphs are laid out half-live (one environment per 32-row group); B = 1600 / 1590:
+    148 full tiles followed by 104 half-live pieces in the same CTAs (both generator instantiations in one launch), the
+    last piece of 1590 partly past the batch"""
     from mop_truss_marl_b200 import actor, tf_checkpoint
     w = tf_checkpoint.random_actor_weights(seed=3)
     g = torch.Generator(device="cuda").manual_seed(1)
