@@ -535,8 +535,9 @@ cudaError_t set_pipe_smem() {
 }
 
 // Build variants of actor_pipe_kernel: (generator phases, epilogue warps).  0 = (2, 4) is the production choice (measured
-// fastest for both node counts: 0.188 ms small bridge 4096, 0.775 ms large bridge 8192; (2, 8) 0.194 / 0.881); the others are
-// kept for A/B timing (TACTOR_VARIANT).  The CTA-pair build exists for variant 0 only.
+// fastest for both node counts on the final build: 0.181 ms small bridge 4096, 0.706 ms large bridge 8192; (3, 4) 0.186 / 0.787,
+// (2, 8) 0.186 / 0.870, (3, 8) 0.192 / 0.807, (4, 4) 0.188 / 0.780); the others are kept for A/B timing (TACTOR_VARIANT).
+// The CTA-pair build exists for variant 0 only.
 template <int NODES>
 cudaError_t set_pipe_smem_variant(int ncta, int variant) {
   if (ncta == 2) return set_pipe_smem<NODES, 2, 2, 8>();
