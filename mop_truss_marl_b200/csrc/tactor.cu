@@ -536,7 +536,8 @@ cudaError_t set_pipe_smem() {
 
 // Build variants of actor_pipe_kernel: (generator phases, epilogue warps).  0 = (2, 4) is the production choice (measured
 // fastest for both node counts on the final build: 0.181 ms small bridge 4096, 0.706 ms large bridge 8192; (3, 4) 0.186 / 0.787,
-// (2, 8) 0.186 / 0.870, (3, 8) 0.192 / 0.807, (4, 4) 0.188 / 0.780); the others are kept for A/B timing (TACTOR_VARIANT).
+// (2, 8) 0.186 / 0.870, (3, 8) 0.192 / 0.807, (4, 4) 0.188 / 0.780, 5 = (1, 4) 0.208 / 0.853 -- half the generator warps, 15 % slower:
+// the two phases of a row group share a scheduler and mostly run in lock-step); the others are kept for A/B timing (TACTOR_VARIANT).
 // The CTA-pair build exists for variant 0 only.
 template <int NODES>
 cudaError_t set_pipe_smem_variant(int ncta, int variant) {
@@ -546,6 +547,7 @@ cudaError_t set_pipe_smem_variant(int ncta, int variant) {
     case 2: return set_pipe_smem<NODES, 1, 2, 8>();
     case 3: return set_pipe_smem<NODES, 1, 3, 8>();
     case 4: return set_pipe_smem<NODES, 1, 4, 4>();
+    case 5: return set_pipe_smem<NODES, 1, 1, 4>();
     default: return set_pipe_smem<NODES, 1, 2, 4>();
   }
 }
@@ -557,6 +559,7 @@ cudaError_t launch_pipe_variant(int ncta, int variant, tactor::tc::fused::Params
     case 2: return launch_pipe<NODES, 1, 2, 8>(p, M, sms, st);
     case 3: return launch_pipe<NODES, 1, 3, 8>(p, M, sms, st);
     case 4: return launch_pipe<NODES, 1, 4, 4>(p, M, sms, st);
+    case 5: return launch_pipe<NODES, 1, 1, 4>(p, M, sms, st);
     default: return launch_pipe<NODES, 1, 2, 4>(p, M, sms, st);
   }
 }
