@@ -10,7 +10,8 @@ torch = pytest.importorskip("torch")
 @pytest.mark.parametrize("family,B,pieces,compact", [("small_bridge", 77, 3, True), ("large_roof", 70, 2, True),
                                                      ("small_roof", 8, 1, True), ("small_bridge", 77, 3, False),
                                                      ("large_bridge", 40, 2, False),
-                                                     ("small_bridge", 300, [32, 192, 76], True)])   # trollout_set_pieces
+                                                     ("small_bridge", 300, [32, 192, 76], True),    # trollout_set_pieces
+                                                     ("small_bridge", 1500, "auto", True), ("small_roof", 60, "auto", True)])
 def test_host_rollout_equals_resident_path(family, B, pieces, compact):
     """compact: the state tuple carries node_y / element_section (the two table columns _set_model reads) and uploads
     those instead of the full raw tables; without them the full tables go up.  Same bits either way."""
@@ -28,7 +29,10 @@ def test_host_rollout_equals_resident_path(family, B, pieces, compact):
     A_p = torch.rand(B, 2, 2, device=dev, generator=g)
     x_p_host, A_p_host = x_p.cpu().pin_memory(), A_p.cpu().pin_memory()
     roll = HostRollout(envs[1], pols[1], pieces=pieces)
-    assert len(roll.ranges) == (pieces if isinstance(pieces, int) else len(pieces))
+    if pieces == "auto":                                 # ~5.7 MB of download per piece: 2 pieces for 1500 small bridges, 1 for 60
+        assert len(roll.ranges) == (2 if B == 1500 else 1) and all(lo % 32 == 0 for lo, _ in roll.ranges)
+    else:
+        assert len(roll.ranges) == (pieces if isinstance(pieces, int) else len(pieces))
     assert roll.ranges[0][0] == 0 and roll.ranges[-1][1] == B
     bufs = [roll.alloc_host(compact), roll.alloc_host(compact)]
     for k in STATE_IN:
